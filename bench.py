@@ -1,0 +1,405 @@
+#!/usr/bin/env python
+"""bench.py -- KL-NMF iterations/sec on the BASELINE.json workload (see DESIGN.md "Measurement").
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode tf32x3|tf32|fp64]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+One "step" = one reference iteration (objective + ratio + coefficient update + dictionary
+update, nmf.py:212-222) over the whole workload.  Default workload = BASELINE.json configs[4]
+(cfg5: dense fit, n=4,000,000 x f=8192, k=512), STRONG scaling: the same 4M samples are
+row-sharded over the N ranks; the only exchange is the all-reduce of the k x f numerator.
+
+Prints ONE JSON line on rank 0.  `value` = iterations/s with X resident in HBM (device time,
+CUDA events on the engine's stream, max over ranks); `e2e` = the same metric through the
+public API (KLdivNMF.fit_transform on a pinned HOST array: H2D of X and D2H of W inside the
+timed region); `roofline` = the dominant contraction kernel against the measured TF32 peak;
+`cpu_baseline` = the float64 numpy oracle on this box's host cores on a bounded row-subsample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (n_total, f, k, kind, description)
+    "cfg5": (4_000_000, 8192, 512, "dense_fit", "cfg5 dense fit n=4000000 f=8192 k=512 (BASELINE.json configs[4])"),
+    "cfg3": (1_000_000, 4096, 256, "dense_transform", "cfg3 transform n=1000000 f=4096 k=256 (BASELINE.json configs[2])"),
+    "cfg4": (2_000_000, 50_000, 256, "sparse_fit", "cfg4 sparse fit n=2000000 f=50000 density=0.005 k=256 (BASELINE.json configs[3])"),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--mode", default=os.environ.get("KLNMF_BENCH_MODE", "tf32x3"))
+    ap.add_argument("--workload", default=os.environ.get("KLNMF_BENCH_WORKLOAD", "cfg5"), choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="override the total sample count (development only)")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--alt-mode", default=os.environ.get("KLNMF_BENCH_ALT", "tf32"),
+                    help="second arithmetic mode reported under alt_modes ('' to skip)")
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------------------------------------
+# clocks sampling (B200_PROFILING.md recipe)
+# ------------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self._stop_evt = index, [], threading.Event()
+
+    def run(self):
+        while not self._stop_evt.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                parts = [p.strip() for p in out.strip().split(",")]
+                if len(parts) >= 7:
+                    self.samples.append(parts)
+            except Exception:
+                pass
+            self._stop_evt.wait(0.2)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=3)
+        sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+        mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+        reasons = set()
+        for s in self.samples:
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], s[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.samples)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_burst": d["bf16_tflops"], "bf16_sustained": d["bf16_tflops_sustained"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_burst": 1590.0, "bf16_sustained": 1400.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+# ------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the float64 numpy oracle on host cores, bounded row-subsample
+# ------------------------------------------------------------------------------------------------
+def cpu_sample(workload, n_total, f, k, kind, steps, warmup):
+    from oracle import klnmf_oracle as O
+    import scipy.sparse as sp
+    rs = np.random.RandomState(0)
+    if kind == "sparse_fit":
+        n_cpu, m = 2048, int(round(f * 0.005))
+        X = sp.random(n_cpu, f, density=0.005, random_state=rs, format="csr")
+        X.data = 1.0 - X.data
+        sample = "sparse n_cpu=%d of n=%d rows, f=%d, density 0.005, k=%d" % (n_cpu, n_total, f, k)
+    else:
+        n_cpu = 2048 if k >= 512 else 4096
+        X = rs.random_sample((n_cpu, f))
+        sample = "dense n_cpu=%d of n=%d rows, f=%d, k=%d" % (n_cpu, n_total, f, k)
+    np.random.seed(0)
+    H = O.init_dictionary(k, f)
+    W = np.asarray(X.dot(H.T))
+    fit = kind != "dense_transform"
+    times = []
+    for it in range(warmup + steps):
+        t0 = time.perf_counter()
+        O.error(X, W, H)                      # the reference computes the objective every iteration (nmf.py:214)
+        W, H = O.update(X, W, H, fit=fit)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    t_step = float(np.mean(times))
+    # cost is exactly linear in n at fixed f, k: extrapolate to the full workload
+    value = (1.0 / t_step) * (n_cpu / float(n_total))
+    cores = os.cpu_count()
+    try:
+        from threadpoolctl import threadpool_info
+        nth = [i.get("num_threads") for i in threadpool_info() if i.get("user_api") == "blas"]
+        if nth:
+            cores = max(nth)
+    except Exception:
+        pass
+    return {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port",
+            "sample": sample + ", %d timed iterations, %.2f s each, extrapolated linearly in n" % (len(times), t_step)}, t_step
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n_total, f, k, kind, desc = WORKLOADS[args.workload]
+    if args.n:
+        n_total = args.n
+    steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+    base, t_step = cpu_sample(args.workload, n_total, f, k, kind, steps, warmup)
+    line = {"impl": "reference", "metric": "KL-NMF iterations/sec", "value": base["value"], "unit": "iterations/s",
+            "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 / base["value"],
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": desc, "n": n_total, "f": f, "k": k, "note": "float64 numpy restatement of the "
+                       "reference (oracle/klnmf_oracle.py) on host cores; bounded row-subsample extrapolated in n"},
+            "cpu_baseline": base,
+            "e2e": {"value": base["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+# our arm
+# ------------------------------------------------------------------------------------------------
+def dist_setup(args):
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    return rank, world, local, dist
+
+
+def allreduce_max(dist, local, x):
+    if dist is None:
+        return x
+    import torch
+    t = torch.tensor([x], dtype=torch.float64, device="cuda:%d" % local)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
+def barrier(dist, local):
+    if dist is not None:
+        import torch
+        dist.barrier()
+        torch.cuda.synchronize(local)
+
+
+def timed_run(eng, steps, warmup, fit, dist, local):
+    """W untimed iterations, then EXACTLY `steps` timed ones, barrier + sync on both sides."""
+    ninf = -float("inf")
+    if warmup > 0:
+        eng.run(warmup, ninf, fit)
+    barrier(dist, local)
+    c0 = eng.counters()
+    errs, _ = eng.run(steps, ninf, fit)
+    barrier(dist, local)
+    c1 = eng.counters()
+    ms, cnt = eng.last_run_profile()
+    assert len(errs) == steps, "the timed region did not run %d iterations" % steps
+    total_ms = allreduce_max(dist, local, ms["total"])
+    return total_ms, ms, cnt, c1["launches"] - c0["launches"], errs
+
+
+def make_engine(_native, n_local, f, k, kind, mode, local, rank, world, H0, scratch):
+    eng = _native.Engine(n_local, f, k, mode=mode, device=local, scratch_limit=scratch)
+    if kind == "sparse_fit":
+        eng.fill_csr_synthetic(int(round(f * 0.005)), 1234 + rank)
+    else:
+        eng.fill_dense_synthetic(1234 + rank)
+    if world > 1:
+        from multimodal_b200 import distributed as D
+        _native.nccl_load()
+        eng.comm_init(D.broadcast_unique_id(), rank, world)
+    eng.set_dictionary(H0)
+    eng.init_coefficients()
+    return eng
+
+
+def phase_roofline(ms, cnt, n_local, f, k, kind, steps, peaks, mode):
+    if kind == "sparse_fit":
+        # compulsory bytes of one sparse iteration (CSR once, W r+w, H r + numerator w)
+        nnz = n_local * int(round(f * 0.005))
+        alg = 8.0 * nnz + 4.0 * (n_local + 1) + 8.0 * n_local * k + 8.0 * k * f
+        t = (ms["ratio"] + ms["numerator"]) / max(steps, 1) * 1e-3
+        ach = alg / t / 1e9
+        return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                "traffic": None, "kernel": "sparse_rows_kernel + sparse_scatter_kernel", "peak_source": peaks["source"]}
+    names = {"ratio": "tc_gemm_kernel<ratio: S=W.H, Q=(X+eps)/(S+eps), KL>",
+             "coefficient": "tc_gemm_kernel<coefficient: W'=W(.)(Q.H^T)>",
+             "numerator": "tc_gemm_kernel<numerator: N+=W'^T.Q>"}
+    if mode == "fp64":
+        names = {k_: v.replace("tc_gemm_kernel", "generic_gemm_kernel<double>") for k_, v in names.items()}
+    dom = max(names, key=lambda p: ms[p])
+    launches = max(cnt[dom], 1)
+    flops_per_launch = 2.0 * n_local * k * f * steps / launches        # each contraction is 2 n k f per iteration
+    avg_s = ms[dom] / launches * 1e-3
+    ach = flops_per_launch / avg_s / 1e12
+    peak = peaks["bf16_sustained"] / 2.0                                 # TF32 dense = half the BF16 rate
+    if mode == "fp64":
+        peak = 40.0
+    r = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+         "kernel": names[dom], "avg_launch_ms": ms[dom] / launches, "launches": launches,
+         "peak_source": ("TF32 = 1/2 x sustained cuBLAS bf16, " + peaks["source"]) if mode != "fp64" else "nominal B200 FP64",
+         "phase_ms_per_step": {p: ms[p] / max(steps, 1) for p in ("ratio", "coefficient", "numerator", "dictionary", "allreduce")}}
+    if mode == "tf32x3":
+        r["issued_frac"] = 3.0 * ach / peak      # three TF32 MMAs are issued per algorithmic product
+    return r
+
+
+def run_e2e(args, n_local, f, k, kind, mode, local, rank, world, dist, X_host, H0, steps):
+    """The public API on HOST data: H2D of X, `steps` iterations, D2H of W (and H), all timed."""
+    from multimodal_b200.lib.nmf import KLdivNMF
+    import multimodal_b200.lib.nmf as nmfmod
+    est = KLdivNMF(n_components=k, max_iter=steps, tol=0, mode=mode, device=local)
+    est._init_dictionary = H0
+    if kind == "dense_transform":
+        est.components_ = H0
+    barrier(dist, local)
+    t0 = time.perf_counter()
+    if world > 1:
+        from multimodal_b200 import distributed as D
+        sh = D.ShardedNMF(k, max_iter=steps, tol=0, mode=mode, device=local)
+        sh.components_ = H0
+        W = sh.fit_transform(X_host, n_local * world, H0=H0, fit=(kind != "dense_transform"))
+    elif kind == "dense_transform":
+        W = est.transform(X_host)
+    else:
+        W = est.fit_transform(X_host)
+    barrier(dist, local)
+    dt = time.perf_counter() - t0
+    dt = allreduce_max(dist, local, dt)
+    h2d = X_host.nbytes if not hasattr(X_host, "nnz") else (X_host.data.nbytes + X_host.indices.nbytes + X_host.indptr.nbytes)
+    d2h = W.nbytes + (H0.nbytes if kind != "dense_transform" else 0)
+    del nmfmod
+    return dt, h2d, d2h
+
+
+def run_ours(args):
+    rank, world, local, dist = dist_setup(args)
+    os.environ.setdefault("KLNMF_PROFILE", "1")
+    from multimodal_b200 import _native
+    from multimodal_b200 import distributed as D
+    n_total, f, k, kind, desc = WORKLOADS[args.workload]
+    if args.n:
+        n_total = args.n
+        desc += " [n overridden to %d]" % n_total
+    bounds = D.shard_bounds(n_total, world)
+    n_local = bounds[rank + 1] - bounds[rank]
+    fit = kind != "dense_transform"
+    peaks = measured_peaks()
+
+    np.random.seed(0)
+    H0 = np.abs(np.random.random((k, f))) + .01
+    H0 = H0 / (1.e-16 + H0.sum(axis=1, keepdims=True))
+    if dist is not None:
+        H0 = D.broadcast_object(H0, 0)
+
+    def one_mode(mode, with_clocks):
+        x_bytes = n_local * f * (8 if mode == "fp64" else 4)
+        # leave room for X + the W ping-pong (+ lo parts) on a 192 GB part
+        scratch = (8 << 30) if x_bytes > (100 << 30) else (16 << 30)
+        eng = make_engine(_native, n_local, f, k, kind, mode, local, rank, world, H0, scratch)
+        sampler = ClockSampler(local) if with_clocks else None
+        if sampler:
+            sampler.start()
+        total_ms, ms, cnt, launches, errs = timed_run(eng, args.steps, args.warmup, fit, dist, local)
+        clocks = sampler.stop() if sampler else None
+        return eng, total_ms, ms, cnt, launches, errs, clocks
+
+    eng, total_ms, ms, cnt, launches, errs, clocks = one_mode(args.mode, True)
+    value = args.steps / (total_ms * 1e-3)
+    roof = phase_roofline(ms, cnt, n_local, f, k, kind, args.steps, peaks, args.mode)
+
+    # ---- end-to-end leg through the public API on host buffers ---------------------------------
+    e2e = None
+    if not args.no_e2e:
+        import psutil
+        x_bytes = n_local * f * 4
+        avail = psutil.virtual_memory().available
+        try:
+            lim = open("/sys/fs/cgroup/memory.max").read().strip()
+            if lim.isdigit():
+                avail = min(avail, int(lim))
+        except Exception:
+            pass
+        rows = n_local
+        if kind != "sparse_fit" and x_bytes * 2.5 > avail:
+            rows = max(1024, int(avail / 2.5 / (f * 4)) // 1024 * 1024)
+        rows = min(rows, n_local)
+        if kind == "sparse_fit":
+            e2e = {"value": None, "unit": "iterations/s", "note": "e2e leg not implemented for the synthetic CSR workload"}
+        else:
+            import torch
+            Xh = torch.empty((rows, f), dtype=torch.float32, pin_memory=True).numpy()
+            if rows == n_local:
+                eng.get_dense(Xh)
+                eng.close()
+            else:
+                eng.close()
+                with _native.Engine(rows, f, k, mode=args.mode, device=local) as e2:
+                    e2.fill_dense_synthetic(1234 + rank)
+                    e2.get_dense(Xh)
+            dt, h2d, d2h = run_e2e(args, rows, f, k, kind, args.mode, local, rank, world, dist, Xh, H0, args.steps)
+            scale = rows / float(n_local)
+            e2e = {"value": args.steps / dt * scale, "unit": "iterations/s",
+                   "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
+                   "seconds": dt, "rows_per_rank": rows,
+                   "note": ("one KLdivNMF.%s call of %d iterations on a pinned host float32 array; X crosses PCIe once "
+                            "per call, so per-step bytes are the call's bytes / steps" %
+                            ("transform" if not fit else "fit_transform", args.steps)) +
+                           ("" if rows == n_local else "; host RAM too small for the full shard: measured on %d rows and "
+                            "scaled linearly in n" % rows)}
+            del Xh
+    try:
+        eng.close()
+    except Exception:
+        pass
+
+    alt = {}
+    if args.alt_mode and args.alt_mode != args.mode:
+        e2, t2, ms2, cnt2, l2, _, _ = one_mode(args.alt_mode, False)
+        e2.close()
+        r2 = phase_roofline(ms2, cnt2, n_local, f, k, kind, args.steps, peaks, args.alt_mode)
+        alt[args.alt_mode] = {"value": args.steps / (t2 * 1e-3), "ms_per_step": t2 / args.steps, "roofline_frac": r2["frac"],
+                              "roofline_achieved": r2["achieved"], "kernel": r2["kernel"]}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cpu, _ = cpu_sample(args.workload, n_total, f, k, kind, 2, 1)
+
+    if rank == 0:
+        line = {"metric": "KL-NMF iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+                "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.mode,
+                "data": "synthetic",
+                "config": {"workload": desc, "n": n_total, "f": f, "k": k, "mode": args.mode,
+                           "rows_per_rank": n_local, "l2": "inputs (%.1f GB per rank) are larger than the 126 MB L2"
+                           % (n_local * f * 4 / 1e9), "objective_first_last": [float(errs[0]), float(errs[-1])]},
+                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
+                "cpu_baseline": cpu, "alt_modes": alt}
+        print(json.dumps(line))
+    if dist is not None:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

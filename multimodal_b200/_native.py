@@ -1,0 +1,330 @@
+"""ctypes binding of libklnmf.so (include/klnmf.h) -- the only way into the CUDA engine.
+
+There is no CPU implementation behind this module: if the shared library is missing,
+or no B200 is visible, every entry point raises.  numpy <-> device copies are done by
+the library's own `*_host` entry points; torch is only used by callers that already
+hold device tensors (bench) or need torch.distributed for the NCCL bootstrap.
+"""
+import ctypes
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "csrc", "libklnmf.so")
+
+MODE_TF32, MODE_TF32X3, MODE_FP64 = 0, 1, 2
+MODES = {"tf32": MODE_TF32, "tf32x3": MODE_TF32X3, "fp64": MODE_FP64}
+F32, F64 = 0, 1
+
+_c_i64 = ctypes.c_int64
+_c_int = ctypes.c_int
+_c_vp = ctypes.c_void_p
+_c_dbl = ctypes.c_double
+
+# name -> (restype, argtypes); must list every symbol include/klnmf.h declares
+PROTOTYPES = {
+    "klnmf_abi_version": (_c_int, []),
+    "klnmf_last_error": (ctypes.c_char_p, []),
+    "klnmf_device_count": (_c_int, []),
+    "klnmf_create": (_c_int, [ctypes.POINTER(_c_vp), _c_int, _c_i64, _c_i64, _c_i64, _c_int]),
+    "klnmf_destroy": (_c_int, [_c_vp]),
+    "klnmf_set_stream": (_c_int, [_c_vp, _c_vp]),
+    "klnmf_set_scratch_limit": (_c_int, [_c_vp, _c_i64]),
+    "klnmf_set_dense_host": (_c_int, [_c_vp, _c_vp, _c_int, _c_i64]),
+    "klnmf_set_dense_device": (_c_int, [_c_vp, _c_vp, _c_int, _c_i64]),
+    "klnmf_set_csr_host": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_i64]),
+    "klnmf_set_csr_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_i64]),
+    "klnmf_check_input": (_c_int, [_c_vp, ctypes.POINTER(ctypes.c_int32)]),
+    "klnmf_set_dictionary_host": (_c_int, [_c_vp, _c_vp, _c_i64]),
+    "klnmf_get_dictionary_host": (_c_int, [_c_vp, _c_vp, _c_i64]),
+    "klnmf_init_coefficients": (_c_int, [_c_vp]),
+    "klnmf_set_coefficients_host": (_c_int, [_c_vp, _c_vp, _c_i64]),
+    "klnmf_get_coefficients_host": (_c_int, [_c_vp, _c_vp, _c_i64]),
+    "klnmf_coefficients_device": (_c_int, [_c_vp, ctypes.POINTER(_c_vp), ctypes.POINTER(_c_i64),
+                                           ctypes.POINTER(_c_int)]),
+    "klnmf_dictionary_device": (_c_int, [_c_vp, ctypes.POINTER(_c_vp), ctypes.POINTER(_c_i64),
+                                         ctypes.POINTER(_c_int)]),
+    "klnmf_run": (_c_int, [_c_vp, _c_int, _c_dbl, _c_int, _c_vp, ctypes.POINTER(_c_int),
+                           ctypes.POINTER(_c_int)]),
+    "klnmf_error": (_c_int, [_c_vp, ctypes.POINTER(_c_dbl)]),
+    "klnmf_dictionary_step": (_c_int, [_c_vp]),
+    "klnmf_ratio_host": (_c_int, [_c_vp, _c_vp, _c_int, _c_i64]),
+    "klnmf_sddmm_host": (_c_int, [_c_vp, _c_vp]),
+    "klnmf_reconstruct_host": (_c_int, [_c_vp, _c_vp, _c_i64, _c_i64, _c_vp, _c_i64]),
+    "klnmf_nccl_load": (_c_int, [ctypes.c_char_p]),
+    "klnmf_nccl_unique_id": (_c_int, [_c_vp]),
+    "klnmf_comm_init": (_c_int, [_c_vp, _c_vp, _c_int, _c_int]),
+    "klnmf_fill_dense_synthetic": (_c_int, [_c_vp, ctypes.c_uint64]),
+    "klnmf_fill_csr_synthetic": (_c_int, [_c_vp, _c_i64, ctypes.c_uint64]),
+    "klnmf_get_dense_host": (_c_int, [_c_vp, _c_vp, _c_int, _c_i64]),
+    "klnmf_counters": (_c_int, [_c_vp, ctypes.POINTER(_c_i64)]),
+    "klnmf_last_run_profile": (_c_int, [_c_vp, ctypes.POINTER(_c_dbl), ctypes.POINTER(_c_i64)]),
+    "klnmf_contract_host": (_c_int, [_c_int, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_vp, _c_int, _c_vp]),
+    "klnmf_engine_name": (ctypes.c_char_p, [_c_vp]),
+}
+
+_lib = None
+
+
+class KlnmfError(RuntimeError):
+    pass
+
+
+def load():
+    """dlopen libklnmf.so (building it first when the sources are newer and nvcc exists)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        from . import build as _build
+        _build.build()
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in PROTOTYPES.items():
+        fn = getattr(lib, name)          # AttributeError here == header/library mismatch
+        fn.restype = res
+        fn.argtypes = args
+    if lib.klnmf_abi_version() != 1:
+        raise KlnmfError("libklnmf ABI mismatch")
+    _lib = lib
+    return lib
+
+
+def device_count():
+    return load().klnmf_device_count()
+
+
+def _check(rc):
+    if rc != 0:
+        msg = load().klnmf_last_error().decode("utf-8", "replace")
+        if rc == -3:
+            raise KlnmfError("libklnmf needs a B200 (sm_100a) device and has no CPU path: " + msg)
+        if rc == -1:
+            raise ValueError(msg)
+        if rc == -6:
+            raise MemoryError(msg)
+        raise KlnmfError("libklnmf error %d: %s" % (rc, msg))
+
+
+def resolve_mode(mode):
+    if mode is None:
+        mode = os.environ.get("KLNMF_MODE", "tf32x3")
+    if isinstance(mode, str):
+        if mode not in MODES:
+            raise ValueError("unknown arithmetic mode %r (expected one of %s)" % (mode, sorted(MODES)))
+        return MODES[mode]
+    return int(mode)
+
+
+def _as_f64(a):
+    return np.ascontiguousarray(a, dtype=np.float64)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(_c_vp)
+
+
+class Engine(object):
+    """One klnmf context: a shard of samples on one GPU."""
+
+    def __init__(self, n, f, k, mode=None, device=0, scratch_limit=None):
+        self.lib = load()
+        self.n, self.f, self.k = int(n), int(f), int(k)
+        self.mode = resolve_mode(mode)
+        h = _c_vp()
+        _check(self.lib.klnmf_create(ctypes.byref(h), int(device), self.n, self.f, self.k, self.mode))
+        self.h = h
+        self._keep = []          # host/device buffers the context borrows
+        if scratch_limit:
+            _check(self.lib.klnmf_set_scratch_limit(self.h, int(scratch_limit)))
+
+    # -- lifetime -------------------------------------------------------------------
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.klnmf_destroy(self.h)
+            self.h = None
+            self._keep = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    @property
+    def engine_name(self):
+        return self.lib.klnmf_engine_name(self.h).decode()
+
+    # -- data -------------------------------------------------------------------------
+    def set_dense(self, X):
+        """X: C-contiguous float32/float64 ndarray (n, f) on the host."""
+        if X.dtype == np.float32:
+            dt = F32
+        else:
+            X = np.asarray(X, dtype=np.float64)
+            dt = F64
+        if not X.flags.c_contiguous:
+            X = np.ascontiguousarray(X)
+        assert X.shape == (self.n, self.f)
+        _check(self.lib.klnmf_set_dense_host(self.h, _ptr(X), dt, X.strides[0] // X.itemsize if self.n > 1 else self.f))
+
+    def set_dense_device(self, ptr, dtype, ld, keepalive=None):
+        self._keep.append(keepalive)
+        _check(self.lib.klnmf_set_dense_device(self.h, _c_vp(ptr), dtype, int(ld)))
+
+    def set_csr(self, X):
+        """X: scipy CSR (n, f), canonical (no duplicates), explicit zeros removed."""
+        indptr = np.ascontiguousarray(X.indptr, dtype=np.int64)
+        indices = np.ascontiguousarray(X.indices, dtype=np.int32)
+        if X.data.dtype == np.float32:
+            data, dt = np.ascontiguousarray(X.data), F32
+        else:
+            data, dt = np.ascontiguousarray(X.data, dtype=np.float64), F64
+        assert X.shape == (self.n, self.f)
+        _check(self.lib.klnmf_set_csr_host(self.h, _ptr(indptr), _ptr(indices), _ptr(data), dt, int(X.nnz)))
+
+    def check_input(self):
+        out = (ctypes.c_int32 * 2)()
+        _check(self.lib.klnmf_check_input(self.h, out))
+        return bool(out[0]), bool(out[1])
+
+    def fill_dense_synthetic(self, seed):
+        _check(self.lib.klnmf_fill_dense_synthetic(self.h, int(seed)))
+
+    def fill_csr_synthetic(self, nnz_per_row, seed):
+        _check(self.lib.klnmf_fill_csr_synthetic(self.h, int(nnz_per_row), int(seed)))
+
+    def get_dense(self, out):
+        dt = F32 if out.dtype == np.float32 else F64
+        _check(self.lib.klnmf_get_dense_host(self.h, _ptr(out), dt, out.strides[0] // out.itemsize))
+        return out
+
+    # -- state ---------------------------------------------------------------------------
+    def set_dictionary(self, H):
+        H = _as_f64(H)
+        assert H.shape == (self.k, self.f), (H.shape, (self.k, self.f))
+        _check(self.lib.klnmf_set_dictionary_host(self.h, _ptr(H), self.f))
+
+    def get_dictionary(self):
+        H = np.empty((self.k, self.f), dtype=np.float64)
+        _check(self.lib.klnmf_get_dictionary_host(self.h, _ptr(H), self.f))
+        return H
+
+    def init_coefficients(self):
+        _check(self.lib.klnmf_init_coefficients(self.h))
+
+    def set_coefficients(self, W):
+        W = _as_f64(W)
+        assert W.shape == (self.n, self.k), (W.shape, (self.n, self.k))
+        _check(self.lib.klnmf_set_coefficients_host(self.h, _ptr(W), self.k))
+
+    def get_coefficients(self):
+        W = np.empty((self.n, self.k), dtype=np.float64)
+        _check(self.lib.klnmf_get_coefficients_host(self.h, _ptr(W), self.k))
+        return W
+
+    # -- compute ----------------------------------------------------------------------------
+    def run(self, max_iter, tol_abs, fit):
+        """Returns (errors ndarray, n_iter) with the reference's meaning of both."""
+        errs = np.empty(max(int(max_iter), 1), dtype=np.float64)
+        ne, ni = _c_int(0), _c_int(0)
+        _check(self.lib.klnmf_run(self.h, int(max_iter), float(tol_abs), 1 if fit else 0, _ptr(errs),
+                                  ctypes.byref(ne), ctypes.byref(ni)))
+        return errs[:ne.value].copy(), ni.value
+
+    def error(self):
+        out = _c_dbl(0.0)
+        _check(self.lib.klnmf_error(self.h, ctypes.byref(out)))
+        return out.value
+
+    def dictionary_step(self):
+        _check(self.lib.klnmf_dictionary_step(self.h))
+
+    def ratio(self, nnz=None):
+        if nnz is None:
+            out = np.empty((self.n, self.f), dtype=np.float64)
+            _check(self.lib.klnmf_ratio_host(self.h, _ptr(out), F64, self.f))
+        else:
+            out = np.empty(int(nnz), dtype=np.float64)
+            _check(self.lib.klnmf_ratio_host(self.h, _ptr(out), F64, int(nnz)))
+        return out
+
+    def sddmm(self, nnz):
+        out = np.empty(int(nnz), dtype=np.float64)
+        _check(self.lib.klnmf_sddmm_host(self.h, _ptr(out)))
+        return out
+
+    def reconstruct(self, H_dest):
+        H_dest = _as_f64(H_dest)
+        assert H_dest.shape[0] == self.k
+        fd = H_dest.shape[1]
+        out = np.empty((self.n, fd), dtype=np.float64)
+        _check(self.lib.klnmf_reconstruct_host(self.h, _ptr(H_dest), fd, fd, _ptr(out), fd))
+        return out
+
+    # -- multi GPU -----------------------------------------------------------------------------
+    def comm_init(self, uid, rank, world):
+        buf = (ctypes.c_char * 128).from_buffer_copy(bytes(uid))
+        _check(self.lib.klnmf_comm_init(self.h, ctypes.cast(buf, _c_vp), int(rank), int(world)))
+
+    # -- accounting ------------------------------------------------------------------------------
+    def counters(self):
+        out = (_c_i64 * 4)()
+        _check(self.lib.klnmf_counters(self.h, out))
+        return {"launches": out[0], "nccl_calls": out[1], "h2d_bytes": out[2], "d2h_bytes": out[3]}
+
+    def last_run_profile(self):
+        ms = (_c_dbl * 6)()
+        cnt = (_c_i64 * 5)()
+        _check(self.lib.klnmf_last_run_profile(self.h, ms, cnt))
+        names = ["ratio", "coefficient", "numerator", "dictionary", "allreduce", "total"]
+        return ({n: ms[i] for i, n in enumerate(names)}, {n: cnt[i] for i, n in enumerate(names[:5])})
+
+
+def nccl_unique_id(libnccl_path=None):
+    lib = load()
+    if libnccl_path is None:
+        libnccl_path = find_libnccl()
+    _check(lib.klnmf_nccl_load(libnccl_path.encode() if libnccl_path else None))
+    buf = (ctypes.c_char * 128)()
+    _check(lib.klnmf_nccl_unique_id(ctypes.cast(buf, _c_vp)))
+    return bytes(buf)
+
+
+def nccl_load(libnccl_path=None):
+    lib = load()
+    if libnccl_path is None:
+        libnccl_path = find_libnccl()
+    _check(lib.klnmf_nccl_load(libnccl_path.encode() if libnccl_path else None))
+
+
+def find_libnccl():
+    """The NCCL that ships with torch (nvidia-nccl-cu12 wheel), else the system one."""
+    try:
+        import nvidia.nccl
+        for base in list(nvidia.nccl.__path__):
+            cand = os.path.join(base, "lib", "libnccl.so.2")
+            if os.path.exists(cand):
+                return cand
+    except Exception:
+        pass
+    return None
+
+
+def contract(A, B, mode, a_trans=False, b_trans=False, device=0):
+    """Diagnostic: op(A).op(B) through the dense engine of `mode` (see klnmf_contract_host)."""
+    lib = load()
+    A, B = _as_f64(A), _as_f64(B)
+    M, K = (A.shape[1], A.shape[0]) if a_trans else A.shape
+    N = B.shape[0] if b_trans else B.shape[1]
+    assert (B.shape[1] if b_trans else B.shape[0]) == K
+    out = np.empty((M, N), dtype=np.float64)
+    _check(lib.klnmf_contract_host(int(device), resolve_mode(mode), M, N, K, _ptr(A), 1 if a_trans else 0,
+                                   _ptr(B), 1 if b_trans else 0, _ptr(out)))
+    return out

@@ -1,0 +1,966 @@
+// C ABI of libklnmf (include/klnmf.h): context, data movement, and the device-resident
+// iteration loop that replaces KLdivNMF.fit_transform's for-loop (nmf.py:212-222).
+#include <math.h>
+#include <stdarg.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "common.cuh"
+
+namespace klnmf {
+
+static thread_local char g_err[1024] = "";
+
+void set_error(const char *fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+namespace {
+
+struct PhaseEvents {
+  int phase;
+  cudaEvent_t a, b;
+};
+struct Profiler {
+  std::vector<PhaseEvents> ev;
+};
+
+inline bool dense_tc(const klnmf_ctx *c) { return c->es == 4 && !c->debug_simt; }
+
+int dense_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d) {
+  if (dense_tc(ctx)) return tc_gemm(ctx, epi, d);
+  return generic_gemm(ctx, ctx->es, epi, d);
+}
+
+int dmalloc(void **p, int64_t bytes) {
+  *p = nullptr;
+  if (bytes <= 0) bytes = 16;
+  cudaError_t e = cudaMalloc(p, (size_t)bytes);
+  if (e != cudaSuccess) {
+    set_error("cudaMalloc(%lld bytes) failed: %s", (long long)bytes, cudaGetErrorString(e));
+    cudaGetLastError();
+    return KLNMF_ENOMEM;
+  }
+  return KLNMF_OK;
+}
+
+int ensure_stage(klnmf_ctx *ctx, int64_t bytes) {
+  if (ctx->stage_bytes >= bytes) return KLNMF_OK;
+  if (ctx->stage) {
+    KL_CUDA(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->stage);
+    ctx->stage = nullptr;
+    ctx->stage_bytes = 0;
+  }
+  KL_TRY(dmalloc(&ctx->stage, bytes));
+  ctx->stage_bytes = bytes;
+  return KLNMF_OK;
+}
+
+constexpr int64_t kStageBytes = (int64_t)256 << 20;
+
+// Allocate W/H/numerator/control buffers once the data kind (dense / CSR) is known.
+int ensure_state(klnmf_ctx *ctx) {
+  if (ctx->W[0]) return KLNMF_OK;
+  const int64_t es = ctx->es;
+  ctx->ldw = round_up(ctx->k, 32);
+  int64_t h_rows, h_cols;
+  if (ctx->sparse) { ctx->ldh = round_up(ctx->k, 32); h_rows = ctx->f; h_cols = ctx->ldh; }
+  else { ctx->ldh = round_up(ctx->f, 32); h_rows = ctx->k; h_cols = ctx->ldh; }
+  const int64_t wbytes = (ctx->n > 0 ? ctx->n : 1) * ctx->ldw * es, hbytes = h_rows * h_cols * es;
+  for (int i = 0; i < 2; i++) {
+    KL_TRY(dmalloc(&ctx->W[i], wbytes));
+    KL_CUDA(cudaMemsetAsync(ctx->W[i], 0, wbytes, ctx->stream));
+    KL_TRY(dmalloc(&ctx->H[i], hbytes));
+    KL_CUDA(cudaMemsetAsync(ctx->H[i], 0, hbytes, ctx->stream));
+    if (ctx->split) {
+      KL_TRY(dmalloc(&ctx->Wlo[i], wbytes));
+      KL_CUDA(cudaMemsetAsync(ctx->Wlo[i], 0, wbytes, ctx->stream));
+      KL_TRY(dmalloc(&ctx->Hlo[i], hbytes));
+      KL_CUDA(cudaMemsetAsync(ctx->Hlo[i], 0, hbytes, ctx->stream));
+    }
+  }
+  KL_TRY(dmalloc(&ctx->num, hbytes));
+  KL_CUDA(cudaMemsetAsync(ctx->num, 0, hbytes, ctx->stream));
+  ctx->dred_len = 2 + ctx->ldw + 128;
+  KL_TRY(dmalloc((void **)&ctx->dred, ctx->dred_len * 8));
+  KL_CUDA(cudaMemsetAsync(ctx->dred, 0, ctx->dred_len * 8, ctx->stream));
+  KL_TRY(dmalloc((void **)&ctx->rowsumH, (ctx->k + 1) * 8));
+  KL_TRY(dmalloc((void **)&ctx->hsum, (ctx->k + 1) * 8));
+  KL_CUDA(cudaMemsetAsync(ctx->rowsumH, 0, (ctx->k + 1) * 8, ctx->stream));
+  if (!ctx->sparse) {
+    const int64_t per_row = round_up(ctx->f, 32) * es * (ctx->split ? 2 : 1);
+    int64_t rows = ctx->scratch_limit / per_row;
+    rows = rows / 128 * 128;
+    if (rows < 128) rows = 128;
+    if (rows > round_up(ctx->n, 128)) rows = round_up(ctx->n > 0 ? ctx->n : 1, 128);
+    ctx->panel_rows = rows;
+    ctx->ldq = round_up(ctx->f, 32);
+    KL_TRY(dmalloc(&ctx->Q, rows * ctx->ldq * es));
+    if (ctx->split) KL_TRY(dmalloc(&ctx->Qlo, rows * ctx->ldq * es));
+  }
+  return KLNMF_OK;
+}
+
+void release_data(klnmf_ctx *ctx) {
+  if (ctx->x_owned && ctx->X) cudaFree(ctx->X);
+  if (ctx->csr_owned) {
+    if (ctx->indptr) cudaFree(ctx->indptr);
+    if (ctx->indices) cudaFree(ctx->indices);
+    if (ctx->vals) cudaFree(ctx->vals);
+  }
+  if (ctx->qnz) cudaFree(ctx->qnz);
+  ctx->X = nullptr; ctx->indptr = nullptr; ctx->indices = nullptr; ctx->vals = nullptr; ctx->qnz = nullptr;
+  ctx->x_owned = ctx->csr_owned = false;
+  ctx->have_x = false;
+}
+
+int kind_guard(klnmf_ctx *ctx, bool sparse) {
+  KL_CHECK(!ctx->W[0] || ctx->sparse == sparse, KLNMF_ESTATE,
+           "a context serves either dense or CSR data for its whole life; create a new one");
+  ctx->sparse = sparse;
+  return KLNMF_OK;
+}
+
+// host (row-major, ld elements, dtype) -> device (es, dst_ld), optional transpose
+int upload_matrix(klnmf_ctx *ctx, const void *src, int dtype, int64_t ld, void *dst, int64_t dst_ld, int64_t rows,
+                  int64_t cols, bool transpose) {
+  if (rows <= 0 || cols <= 0) return KLNMF_OK;
+  const int64_t ses = dtype == KLNMF_F64 ? 8 : 4;
+  if (!transpose && ses == ctx->es) {
+    KL_CUDA(cudaMemcpy2DAsync(dst, dst_ld * ses, src, ld * ses, cols * ses, rows, cudaMemcpyHostToDevice, ctx->stream));
+    ctx->bytes_h2d += rows * cols * ses;
+    return KLNMF_OK;
+  }
+  int64_t chunk = kStageBytes / (cols * ses);
+  if (chunk < 1) chunk = 1;
+  KL_TRY(ensure_stage(ctx, (chunk < rows ? chunk : rows) * cols * ses));
+  for (int64_t r0 = 0; r0 < rows; r0 += chunk) {
+    const int64_t r = rows - r0 < chunk ? rows - r0 : chunk;
+    KL_CUDA(cudaMemcpy2DAsync(ctx->stage, cols * ses, (const char *)src + r0 * ld * ses, ld * ses, cols * ses, r,
+                              cudaMemcpyHostToDevice, ctx->stream));
+    void *d = transpose ? (void *)((char *)dst + r0 * ctx->es) : (void *)((char *)dst + r0 * dst_ld * ctx->es);
+    KL_TRY(launch_convert(ctx, ctx->stage, nullptr, dtype, cols, d, ctx->es, dst_ld, r, cols, transpose));
+    KL_CUDA(cudaStreamSynchronize(ctx->stream));   // staging buffer is reused
+    ctx->bytes_h2d += r * cols * ses;
+  }
+  return KLNMF_OK;
+}
+
+// device (es [+lo], src_ld) -> host double/float (ld), optional transpose (src is cols x rows then)
+int download_matrix(klnmf_ctx *ctx, const void *src, const void *src_lo, int64_t src_ld, void *dst, int dtype,
+                    int64_t ld, int64_t rows, int64_t cols, bool transposed_src) {
+  if (rows <= 0 || cols <= 0) return KLNMF_OK;
+  const int64_t des = dtype == KLNMF_F64 ? 8 : 4;
+  const int src_dtype = ctx->es == 8 ? KLNMF_F64 : KLNMF_F32;
+  if (!transposed_src && !src_lo && des == ctx->es) {
+    KL_CUDA(cudaMemcpy2DAsync(dst, ld * des, src, src_ld * des, cols * des, rows, cudaMemcpyDeviceToHost, ctx->stream));
+    KL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->bytes_d2h += rows * cols * des;
+    return KLNMF_OK;
+  }
+  if (transposed_src) {
+    // src is (cols x rows) with leading dimension src_ld; produce rows x cols on the host
+    KL_TRY(ensure_stage(ctx, rows * cols * des));
+    KL_TRY(launch_convert(ctx, src, src_lo, src_dtype, src_ld, ctx->stage, (int)des, cols, cols, rows, true));
+    KL_CUDA(cudaMemcpy2DAsync(dst, ld * des, ctx->stage, cols * des, cols * des, rows, cudaMemcpyDeviceToHost, ctx->stream));
+    KL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->bytes_d2h += rows * cols * des;
+    return KLNMF_OK;
+  }
+  int64_t chunk = kStageBytes / (cols * des);
+  if (chunk < 1) chunk = 1;
+  KL_TRY(ensure_stage(ctx, (chunk < rows ? chunk : rows) * cols * des));
+  for (int64_t r0 = 0; r0 < rows; r0 += chunk) {
+    const int64_t r = rows - r0 < chunk ? rows - r0 : chunk;
+    const void *s = (const char *)src + r0 * src_ld * ctx->es;
+    const void *sl = src_lo ? (const void *)((const char *)src_lo + r0 * src_ld * ctx->es) : nullptr;
+    KL_TRY(launch_convert(ctx, s, sl, src_dtype, src_ld, ctx->stage, (int)des, cols, r, cols, false));
+    KL_CUDA(cudaMemcpy2DAsync((char *)dst + r0 * ld * des, ld * des, ctx->stage, cols * des, cols * des, r,
+                              cudaMemcpyDeviceToHost, ctx->stream));
+    KL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->bytes_d2h += r * cols * des;
+  }
+  return KLNMF_OK;
+}
+
+struct PhaseTimer {
+  klnmf_ctx *ctx;
+  Profiler *prof;
+  int phase;
+  cudaEvent_t a = nullptr, b = nullptr;
+  PhaseTimer(klnmf_ctx *c, Profiler *p, int ph) : ctx(c), prof(p), phase(ph) {
+    if (prof) {
+      cudaEventCreate(&a);
+      cudaEventCreate(&b);
+      cudaEventRecord(a, ctx->stream);
+    }
+  }
+  ~PhaseTimer() {
+    if (prof) {
+      cudaEventRecord(b, ctx->stream);
+      prof->ev.push_back({phase, a, b});
+    }
+  }
+};
+
+// Local (per-rank) work of one iteration on the dense path: three contractions per row panel.
+int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bool dict_only = false,
+                    void *ratio_host = nullptr, int ratio_dtype = KLNMF_F64, int64_t ratio_ld = 0) {
+  const int64_t es = ctx->es;
+  const int cur = ctx->cur, hc = ctx->hcur;
+  const int *stop = only_error ? nullptr : ctx->flags + FL_STOP;
+  for (int64_t r0 = 0; r0 < ctx->n; r0 += ctx->panel_rows) {
+    const int64_t rows = ctx->n - r0 < ctx->panel_rows ? ctx->n - r0 : ctx->panel_rows;
+    const char *Wc = (const char *)ctx->W[cur] + r0 * ctx->ldw * es;
+    const char *Wclo = ctx->split ? (const char *)ctx->Wlo[cur] + r0 * ctx->ldw * es : nullptr;
+    char *Wn = (char *)ctx->W[cur ^ 1] + r0 * ctx->ldw * es;
+    char *Wnlo = ctx->split ? (char *)ctx->Wlo[cur ^ 1] + r0 * ctx->ldw * es : nullptr;
+    {  // ratio + objective: Q = (X+eps)/(W.H+eps)   (nmf.py:325-336, metrics.py:18-20)
+      PhaseTimer t(ctx, prof, PH_RATIO);
+      GemmDesc d{};
+      d.M = rows; d.N = ctx->f; d.K = ctx->k;
+      d.A = Wc; d.a_sm = ctx->ldw; d.a_sk = 1; d.A_lo = Wclo;
+      d.B = ctx->H[hc]; d.b_sk = ctx->ldh; d.b_sn = 1; d.B_lo = ctx->split ? ctx->Hlo[hc] : nullptr;
+      d.out = ctx->Q; d.ldo = ctx->ldq; d.out_lo = ctx->Qlo;
+      d.aux = (const char *)ctx->X + r0 * ctx->ldx * es; d.ldaux = ctx->ldx;
+      d.kl = ctx->dred; d.stop = stop; d.only_kl = only_error ? 1 : 0;
+      KL_TRY(dense_gemm(ctx, EPI_RATIO, d));
+    }
+    if (ratio_host) {   // _Q parity hook: hand the ratio panel back to the host
+      KL_TRY(download_matrix(ctx, ctx->Q, ctx->Qlo, ctx->ldq,
+                             (char *)ratio_host + r0 * ratio_ld * (ratio_dtype == KLNMF_F64 ? 8 : 4), ratio_dtype,
+                             ratio_ld, rows, ctx->f, false));
+      continue;
+    }
+    if (only_error) continue;
+    if (!dict_only) {  // coefficients: W' = W (.) (Q.H^T)           (nmf.py:338-343)
+      PhaseTimer t(ctx, prof, PH_COEF);
+      GemmDesc d{};
+      d.M = rows; d.N = ctx->k; d.K = ctx->f;
+      d.A = ctx->Q; d.a_sm = ctx->ldq; d.a_sk = 1; d.A_lo = ctx->Qlo;
+      d.B = ctx->H[hc]; d.b_sk = 1; d.b_sn = ctx->ldh; d.B_lo = ctx->split ? ctx->Hlo[hc] : nullptr;
+      d.out = Wn; d.ldo = ctx->ldw; d.out_lo = Wnlo;
+      d.aux = Wc; d.ldaux = ctx->ldw; d.aux_lo = Wclo;
+      d.stop = stop;
+      KL_TRY(dense_gemm(ctx, EPI_MULW, d));
+    }
+    if (fit) {  // dictionary numerator: N += W'^T.Q  (stale Q, new W: nmf.py:345-349)
+      PhaseTimer t(ctx, prof, PH_NUM);
+      GemmDesc d{};
+      d.M = ctx->k; d.N = ctx->f; d.K = rows;
+      d.A = dict_only ? (const void *)Wc : (const void *)Wn; d.a_sm = 1; d.a_sk = ctx->ldw;
+      d.A_lo = dict_only ? (const void *)Wclo : (const void *)Wnlo;
+      d.B = ctx->Q; d.b_sk = ctx->ldq; d.b_sn = 1; d.B_lo = ctx->Qlo;
+      d.out = ctx->num; d.ldo = ctx->ldh;
+      d.stop = stop;
+      KL_TRY(dense_gemm(ctx, EPI_ACC, d));
+    }
+  }
+  return KLNMF_OK;
+}
+
+int reset_reduction(klnmf_ctx *ctx) {
+  KL_CUDA(cudaMemsetAsync(ctx->dred, 0, ctx->dred_len * 8, ctx->stream));
+  KL_CUDA(cudaMemcpyAsync(ctx->dred + 1, ctx->dscal + DS_SUMX, 8, cudaMemcpyDeviceToDevice, ctx->stream));
+  return KLNMF_OK;
+}
+
+}  // namespace
+}  // namespace klnmf
+
+using namespace klnmf;
+
+extern "C" {
+
+int klnmf_abi_version(void) { return KLNMF_ABI_VERSION; }
+
+const char *klnmf_last_error(void) { return g_err; }
+
+int klnmf_device_count(void) {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int klnmf_create(klnmf_ctx **out, int device, int64_t n_local, int64_t f, int64_t k, int mode) {
+  KL_CHECK(out != nullptr, KLNMF_EINVAL, "klnmf_create: out is NULL");
+  *out = nullptr;
+  KL_CHECK(n_local >= 0 && f > 0 && k > 0, KLNMF_EINVAL, "klnmf_create: bad shape n=%lld f=%lld k=%lld",
+           (long long)n_local, (long long)f, (long long)k);
+  KL_CHECK(mode == KLNMF_MODE_TF32 || mode == KLNMF_MODE_TF32X3 || mode == KLNMF_MODE_FP64, KLNMF_EINVAL,
+           "klnmf_create: unknown mode %d", mode);
+  const int ndev = klnmf_device_count();
+  KL_CHECK(ndev > 0, KLNMF_ENODEVICE, "no CUDA device: libklnmf has no CPU path");
+  KL_CHECK(device >= 0 && device < ndev, KLNMF_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  KL_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  KL_CUDA(cudaGetDeviceProperties(&prop, device));
+  KL_CHECK(prop.major == 10, KLNMF_ENODEVICE, "device %d is sm_%d%d; libklnmf is built for sm_100a only", device,
+           prop.major, prop.minor);
+  klnmf_ctx *ctx = new klnmf_ctx();
+  ctx->device = device;
+  ctx->n = n_local; ctx->f = f; ctx->k = k; ctx->mode = mode;
+  ctx->es = mode == KLNMF_MODE_FP64 ? 8 : 4;
+  ctx->sm_count = prop.multiProcessorCount;
+  const char *dbg = getenv("KLNMF_DEBUG_ENGINE");
+  ctx->debug_simt = dbg && strcmp(dbg, "simt") == 0;
+  ctx->split = (mode == KLNMF_MODE_TF32X3) && !ctx->debug_simt;
+  const char *pf = getenv("KLNMF_PROFILE");
+  ctx->profile = pf && pf[0] == '1';
+  if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
+    set_error("cudaStreamCreate failed");
+    delete ctx;
+    return KLNMF_ECUDA;
+  }
+  ctx->own_stream = true;
+  int r = dmalloc((void **)&ctx->dscal, DS_COUNT * 8);
+  if (r == KLNMF_OK) r = dmalloc((void **)&ctx->flags, FL_COUNT * 4);
+  if (r != KLNMF_OK || cudaMallocHost((void **)&ctx->pinned, 4096) != cudaSuccess) {
+    klnmf_destroy(ctx);
+    return r != KLNMF_OK ? r : KLNMF_ECUDA;
+  }
+  cudaMemsetAsync(ctx->dscal, 0, DS_COUNT * 8, ctx->stream);
+  cudaMemsetAsync(ctx->flags, 0, FL_COUNT * 4, ctx->stream);
+  *out = ctx;
+  return KLNMF_OK;
+}
+
+int klnmf_destroy(klnmf_ctx *ctx) {
+  if (!ctx) return KLNMF_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  nccl_comm_destroy(ctx);
+  tc_release(ctx);
+  release_data(ctx);
+  for (int i = 0; i < 2; i++) {
+    if (ctx->W[i]) cudaFree(ctx->W[i]);
+    if (ctx->H[i]) cudaFree(ctx->H[i]);
+    if (ctx->Wlo[i]) cudaFree(ctx->Wlo[i]);
+    if (ctx->Hlo[i]) cudaFree(ctx->Hlo[i]);
+  }
+  void *ptrs[] = {ctx->num, ctx->rowsumH, ctx->hsum, ctx->dred, ctx->stage, ctx->Q, ctx->Qlo,
+                  ctx->dscal, ctx->flags, ctx->errors_dev};
+  for (void *p : ptrs)
+    if (p) cudaFree(p);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
+  cudaGetLastError();
+  delete ctx;
+  return KLNMF_OK;
+}
+
+int klnmf_set_stream(klnmf_ctx *ctx, void *cuda_stream) {
+  KL_CHECK(ctx, KLNMF_EINVAL, "ctx is NULL");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  KL_CUDA(cudaStreamSynchronize(ctx->stream));
+  if (cuda_stream == nullptr) {
+    if (!ctx->own_stream) {
+      KL_CUDA(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+      ctx->own_stream = true;
+    }
+    return KLNMF_OK;
+  }
+  if (ctx->own_stream) cudaStreamDestroy(ctx->stream);
+  ctx->stream = (cudaStream_t)cuda_stream;
+  ctx->own_stream = false;
+  return KLNMF_OK;
+}
+
+int klnmf_set_scratch_limit(klnmf_ctx *ctx, int64_t bytes) {
+  KL_CHECK(ctx && bytes > 0, KLNMF_EINVAL, "bad scratch limit");
+  KL_CHECK(!ctx->Q, KLNMF_ESTATE, "scratch limit must be set before the data");
+  ctx->scratch_limit = bytes;
+  return KLNMF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int klnmf_set_dense_host(klnmf_ctx *ctx, const void *X, int dtype, int64_t ld) {
+  KL_CHECK(ctx && (X || ctx->n == 0), KLNMF_EINVAL, "set_dense_host: NULL argument");
+  KL_CHECK(ld >= ctx->f, KLNMF_EINVAL, "set_dense_host: ld %lld < f %lld", (long long)ld, (long long)ctx->f);
+  KL_CUDA(cudaSetDevice(ctx->device));
+  KL_TRY(kind_guard(ctx, false));
+  release_data(ctx);
+  ctx->ldx = round_up(ctx->f, 32);
+  const int64_t bytes = (ctx->n > 0 ? ctx->n : 1) * ctx->ldx * ctx->es;
+  KL_TRY(dmalloc(&ctx->X, bytes));
+  ctx->x_owned = true;
+  if (ctx->ldx != ctx->f) KL_CUDA(cudaMemsetAsync(ctx->X, 0, bytes, ctx->stream));
+  KL_TRY(upload_matrix(ctx, X, dtype, ld, ctx->X, ctx->ldx, ctx->n, ctx->f, false));
+  KL_TRY(ensure_state(ctx));
+  ctx->have_x = true;
+  return KLNMF_OK;
+}
+
+int klnmf_set_dense_device(klnmf_ctx *ctx, const void *X_dev, int dtype, int64_t ld) {
+  KL_CHECK(ctx && X_dev, KLNMF_EINVAL, "set_dense_device: NULL argument");
+  KL_CHECK(ld >= ctx->f, KLNMF_EINVAL, "set_dense_device: ld < f");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  KL_TRY(kind_guard(ctx, false));
+  release_data(ctx);
+  const int64_t ses = dtype == KLNMF_F64 ? 8 : 4;
+  const bool borrow = ses == ctx->es && (ld * ses) % 16 == 0 && ((uintptr_t)X_dev % 16) == 0 &&
+                      ld >= round_up(ctx->f, 32);   // epilogues read whole 32-column chunks
+  if (borrow) {
+    ctx->X = const_cast<void *>(X_dev);
+    ctx->ldx = ld;
+    ctx->x_owned = false;
+  } else {
+    ctx->ldx = round_up(ctx->f, 32);
+    const int64_t bytes = (ctx->n > 0 ? ctx->n : 1) * ctx->ldx * ctx->es;
+    KL_TRY(dmalloc(&ctx->X, bytes));
+    ctx->x_owned = true;
+    if (ctx->ldx != ctx->f) KL_CUDA(cudaMemsetAsync(ctx->X, 0, bytes, ctx->stream));
+    KL_TRY(launch_convert(ctx, X_dev, nullptr, dtype, ld, ctx->X, ctx->es, ctx->ldx, ctx->n, ctx->f, false));
+  }
+  KL_TRY(ensure_state(ctx));
+  ctx->have_x = true;
+  return KLNMF_OK;
+}
+
+static int alloc_csr(klnmf_ctx *ctx, int64_t nnz) {
+  KL_TRY(dmalloc((void **)&ctx->indptr, (ctx->n + 1) * 8));
+  KL_TRY(dmalloc((void **)&ctx->indices, nnz * 4));
+  KL_TRY(dmalloc(&ctx->vals, nnz * ctx->es));
+  ctx->csr_owned = true;
+  return KLNMF_OK;
+}
+
+int klnmf_set_csr_host(klnmf_ctx *ctx, const int64_t *indptr, const int32_t *indices, const void *values, int dtype,
+                       int64_t nnz) {
+  KL_CHECK(ctx && indptr && nnz >= 0 && (nnz == 0 || (indices && values)), KLNMF_EINVAL, "set_csr_host: bad argument");
+  KL_CHECK(ctx->f < ((int64_t)1 << 31), KLNMF_EINVAL, "set_csr_host: int32 column indices need f < 2^31");
+  KL_CHECK(indptr[0] == 0 && indptr[ctx->n] == nnz, KLNMF_EINVAL, "set_csr_host: indptr does not span nnz");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  KL_TRY(kind_guard(ctx, true));
+  release_data(ctx);
+  ctx->nnz = nnz;
+  KL_TRY(alloc_csr(ctx, nnz));
+  KL_CUDA(cudaMemcpyAsync(ctx->indptr, indptr, (ctx->n + 1) * 8, cudaMemcpyHostToDevice, ctx->stream));
+  if (nnz > 0) {
+    KL_CUDA(cudaMemcpyAsync(ctx->indices, indices, nnz * 4, cudaMemcpyHostToDevice, ctx->stream));
+    {  // 1-D upload in bounded chunks (the staging buffer converts float64 -> float32 when needed)
+      const int64_t ses = dtype == KLNMF_F64 ? 8 : 4, step = (int64_t)8 << 20;
+      for (int64_t o = 0; o < nnz; o += step) {
+        const int64_t c = nnz - o < step ? nnz - o : step;
+        KL_TRY(upload_matrix(ctx, (const char *)values + o * ses, dtype, c, (char *)ctx->vals + o * ctx->es, c, 1, c, false));
+      }
+    }
+  }
+  ctx->bytes_h2d += (ctx->n + 1) * 8 + nnz * 4;
+  KL_TRY(dmalloc(&ctx->qnz, nnz * ctx->es));
+  KL_TRY(ensure_state(ctx));
+  KL_TRY(launch_sum_vals(ctx));
+  KL_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->have_x = true;
+  return KLNMF_OK;
+}
+
+int klnmf_set_csr_device(klnmf_ctx *ctx, const int64_t *indptr_dev, const int32_t *indices_dev, const void *values_dev,
+                         int dtype, int64_t nnz) {
+  KL_CHECK(ctx && indptr_dev && nnz >= 0, KLNMF_EINVAL, "set_csr_device: bad argument");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  KL_TRY(kind_guard(ctx, true));
+  release_data(ctx);
+  ctx->nnz = nnz;
+  const int64_t ses = dtype == KLNMF_F64 ? 8 : 4;
+  ctx->indptr = const_cast<int64_t *>(indptr_dev);
+  ctx->indices = const_cast<int32_t *>(indices_dev);
+  ctx->csr_owned = false;
+  if (ses == ctx->es) {
+    ctx->vals = const_cast<void *>(values_dev);
+  } else {
+    // value type differs from the arithmetic mode: keep a converted private copy of everything
+    KL_TRY(alloc_csr(ctx, nnz));
+    KL_CUDA(cudaMemcpyAsync(ctx->indptr, indptr_dev, (ctx->n + 1) * 8, cudaMemcpyDeviceToDevice, ctx->stream));
+    KL_CUDA(cudaMemcpyAsync(ctx->indices, indices_dev, nnz * 4, cudaMemcpyDeviceToDevice, ctx->stream));
+    KL_TRY(launch_convert(ctx, values_dev, nullptr, dtype, nnz, ctx->vals, ctx->es, nnz, 1, nnz, false));
+  }
+  KL_TRY(dmalloc(&ctx->qnz, nnz * ctx->es));
+  KL_TRY(ensure_state(ctx));
+  KL_TRY(launch_sum_vals(ctx));
+  ctx->have_x = true;
+  return KLNMF_OK;
+}
+
+int klnmf_check_input(klnmf_ctx *ctx, int32_t out[2]) {
+  KL_CHECK(ctx && out && ctx->have_x, KLNMF_ESTATE, "check_input: no data set");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  KL_CUDA(cudaMemsetAsync(ctx->flags + FL_NEG, 0, 8, ctx->stream));
+  if (ctx->sparse) KL_TRY(launch_check(ctx, ctx->vals, ctx->es, 1, ctx->nnz, ctx->nnz));
+  else KL_TRY(launch_check(ctx, ctx->X, ctx->es, ctx->n, ctx->f, ctx->ldx));
+  int *h = (int *)ctx->pinned;
+  KL_CUDA(cudaMemcpyAsync(h, ctx->flags + FL_NEG, 8, cudaMemcpyDeviceToHost, ctx->stream));
+  KL_CUDA(cudaStreamSynchronize(ctx->stream));
+  out[0] = h[0];
+  out[1] = h[1];
+  return KLNMF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int klnmf_set_dictionary_host(klnmf_ctx *ctx, const double *H, int64_t ld) {
+  KL_CHECK(ctx && H, KLNMF_EINVAL, "set_dictionary_host: NULL argument");
+  KL_CHECK(ctx->have_x, KLNMF_ESTATE, "set the data before the dictionary");
+  KL_CHECK(ld >= ctx->f, KLNMF_EINVAL, "set_dictionary_host: ld < f");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  const int hc = ctx->hcur;
+  // dense layout k x f; sparse layout transposed f x k
+  KL_TRY(upload_matrix(ctx, H, KLNMF_F64, ld, ctx->H[hc], ctx->ldh, ctx->k, ctx->f, ctx->sparse));
+  if (ctx->split)
+    KL_TRY(launch_split(ctx, (const float *)ctx->H[hc], (float *)ctx->H[hc], (float *)ctx->Hlo[hc], ctx->k, ctx->f,
+                        ctx->ldh));
+  KL_TRY(launch_rowsum_h(ctx));
+  ctx->have_h = true;
+  return KLNMF_OK;
+}
+
+int klnmf_get_dictionary_host(klnmf_ctx *ctx, double *H, int64_t ld) {
+  KL_CHECK(ctx && H && ctx->have_h, KLNMF_ESTATE, "get_dictionary_host: no dictionary");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  const int hc = ctx->hcur;
+  return download_matrix(ctx, ctx->H[hc], ctx->split ? ctx->Hlo[hc] : nullptr, ctx->ldh, H, KLNMF_F64, ld, ctx->k,
+                         ctx->f, ctx->sparse);
+}
+
+int klnmf_init_coefficients(klnmf_ctx *ctx) {
+  KL_CHECK(ctx && ctx->have_x && ctx->have_h, KLNMF_ESTATE, "init_coefficients needs data and dictionary");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->n == 0) { ctx->have_w = true; return KLNMF_OK; }
+  if (ctx->sparse) {
+    KL_TRY(sparse_init_w(ctx));
+    ctx->have_w = true;
+    return KLNMF_OK;
+  }
+  const int64_t es = ctx->es;
+  const int cur = ctx->cur, hc = ctx->hcur;
+  for (int64_t r0 = 0; r0 < ctx->n; r0 += ctx->panel_rows) {
+    const int64_t rows = ctx->n - r0 < ctx->panel_rows ? ctx->n - r0 : ctx->panel_rows;
+    GemmDesc d{};
+    d.M = rows; d.N = ctx->k; d.K = ctx->f;
+    const char *Xp = (const char *)ctx->X + r0 * ctx->ldx * es;
+    if (ctx->split) {
+      // X must enter the split-TF32 contraction as (hi, lo) too: stage the panel through the Q scratch
+      for (int64_t rr = 0; rr < rows; rr += 1 << 20) {
+        const int64_t r = rows - rr < (1 << 20) ? rows - rr : (1 << 20);
+        KL_CUDA(cudaMemcpy2DAsync((char *)ctx->Q + rr * ctx->ldq * es, ctx->ldq * es, Xp + rr * ctx->ldx * es,
+                                  ctx->ldx * es, ctx->f * es, r, cudaMemcpyDeviceToDevice, ctx->stream));
+      }
+      KL_TRY(launch_split(ctx, (const float *)ctx->Q, (float *)ctx->Q, (float *)ctx->Qlo, rows, ctx->f, ctx->ldq));
+      d.A = ctx->Q; d.a_sm = ctx->ldq; d.A_lo = ctx->Qlo;
+    } else {
+      d.A = Xp; d.a_sm = ctx->ldx;
+    }
+    d.a_sk = 1;
+    d.B = ctx->H[hc]; d.b_sk = 1; d.b_sn = ctx->ldh; d.B_lo = ctx->split ? ctx->Hlo[hc] : nullptr;
+    d.out = (char *)ctx->W[cur] + r0 * ctx->ldw * es; d.ldo = ctx->ldw;
+    d.out_lo = ctx->split ? (char *)ctx->Wlo[cur] + r0 * ctx->ldw * es : nullptr;
+    KL_TRY(dense_gemm(ctx, EPI_STORE, d));
+  }
+  ctx->have_w = true;
+  return KLNMF_OK;
+}
+
+int klnmf_set_coefficients_host(klnmf_ctx *ctx, const double *W, int64_t ld) {
+  KL_CHECK(ctx && (W || ctx->n == 0), KLNMF_EINVAL, "set_coefficients_host: NULL argument");
+  KL_CHECK(ctx->have_x, KLNMF_ESTATE, "set the data before the coefficients");
+  KL_CHECK(ld >= ctx->k, KLNMF_EINVAL, "set_coefficients_host: ld < k");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  const int cur = ctx->cur;
+  KL_TRY(upload_matrix(ctx, W, KLNMF_F64, ld, ctx->W[cur], ctx->ldw, ctx->n, ctx->k, false));
+  if (ctx->split)
+    KL_TRY(launch_split(ctx, (const float *)ctx->W[cur], (float *)ctx->W[cur], (float *)ctx->Wlo[cur], ctx->n, ctx->k,
+                        ctx->ldw));
+  ctx->have_w = true;
+  return KLNMF_OK;
+}
+
+int klnmf_get_coefficients_host(klnmf_ctx *ctx, double *W, int64_t ld) {
+  KL_CHECK(ctx && (W || ctx->n == 0) && ctx->have_w, KLNMF_ESTATE, "get_coefficients_host: no coefficients");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  const int cur = ctx->cur;
+  return download_matrix(ctx, ctx->W[cur], ctx->split ? ctx->Wlo[cur] : nullptr, ctx->ldw, W, KLNMF_F64, ld, ctx->n,
+                         ctx->k, false);
+}
+
+int klnmf_coefficients_device(klnmf_ctx *ctx, void **ptr, int64_t *ld, int *dtype) {
+  KL_CHECK(ctx && ptr && ld && dtype && ctx->have_w, KLNMF_ESTATE, "coefficients_device: no coefficients");
+  KL_CHECK(!ctx->split, KLNMF_ESTATE, "split-TF32 state is a (hi, lo) pair; use get_coefficients_host");
+  *ptr = ctx->W[ctx->cur]; *ld = ctx->ldw; *dtype = ctx->es == 8 ? KLNMF_F64 : KLNMF_F32;
+  return KLNMF_OK;
+}
+
+int klnmf_dictionary_device(klnmf_ctx *ctx, void **ptr, int64_t *ld, int *dtype) {
+  KL_CHECK(ctx && ptr && ld && dtype && ctx->have_h, KLNMF_ESTATE, "dictionary_device: no dictionary");
+  KL_CHECK(!ctx->split, KLNMF_ESTATE, "split-TF32 state is a (hi, lo) pair; use get_dictionary_host");
+  *ptr = ctx->H[ctx->hcur]; *ld = ctx->ldh; *dtype = ctx->es == 8 ? KLNMF_F64 : KLNMF_F32;
+  return KLNMF_OK;
+}
+
+// ------------------------------------------------------------------------------------------------
+int klnmf_run(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, double *errors_out, int *n_errors, int *n_iter) {
+  KL_CHECK(ctx && max_iter >= 1, KLNMF_EINVAL, "klnmf_run: max_iter must be >= 1 (reference: range(1, max_iter+1))");
+  KL_CHECK(ctx->have_x && ctx->have_h && ctx->have_w, KLNMF_ESTATE, "klnmf_run needs data, dictionary and coefficients");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->errors_cap < max_iter) {
+    if (ctx->errors_dev) { KL_CUDA(cudaStreamSynchronize(ctx->stream)); cudaFree(ctx->errors_dev); }
+    KL_TRY(dmalloc((void **)&ctx->errors_dev, (int64_t)max_iter * 8));
+    ctx->errors_cap = max_iter;
+  }
+  // tol == 0 is the learner's "run exactly `iterations` updates" idiom (learner.py:12,39): the float64
+  // reference then breaks only if the objective RISES.  Objective noise of the reduced-precision
+  // contractions must not trigger that break, so the rise has to exceed the mode's noise floor.
+  double slack = 0.0;
+  if (tol_abs == 0.0) slack = ctx->mode == KLNMF_MODE_FP64 ? 0.0 : (ctx->mode == KLNMF_MODE_TF32X3 ? 1e-6 : 1e-4);
+  double *hp = ctx->pinned;
+  hp[DS_KL] = 0.0; hp[DS_PREV] = INFINITY; hp[DS_WHSUM] = slack; hp[DS_TOL] = tol_abs;
+  KL_CUDA(cudaMemcpyAsync(ctx->dscal + DS_KL, hp + DS_KL, 8, cudaMemcpyHostToDevice, ctx->stream));
+  KL_CUDA(cudaMemcpyAsync(ctx->dscal + DS_PREV, hp + DS_PREV, 8, cudaMemcpyHostToDevice, ctx->stream));
+  KL_CUDA(cudaMemcpyAsync(ctx->dscal + DS_WHSUM, hp + DS_WHSUM, 8, cudaMemcpyHostToDevice, ctx->stream));
+  KL_CUDA(cudaMemcpyAsync(ctx->dscal + DS_TOL, hp + DS_TOL, 8, cudaMemcpyHostToDevice, ctx->stream));
+  KL_CUDA(cudaMemsetAsync(ctx->flags, 0, 2 * 4, ctx->stream));
+  KL_TRY(reset_reduction(ctx));
+  KL_CUDA(cudaStreamSynchronize(ctx->stream));   // pinned scratch is reused below
+
+  Profiler prof_store;
+  Profiler *prof = ctx->profile ? &prof_store : nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEventCreate(&ev0);
+  cudaEventCreate(&ev1);
+  cudaEventRecord(ev0, ctx->stream);
+
+  const int cur0 = ctx->cur, hcur0 = ctx->hcur;
+  const int64_t hbytes = (ctx->sparse ? ctx->f : ctx->k) * ctx->ldh * (int64_t)ctx->es;
+  int *hflags = (int *)(ctx->pinned + 16);
+  int enq = 0;
+  int rc = KLNMF_OK;
+  for (int it = 0; it < max_iter && rc == KLNMF_OK; it++) {
+    if (fit) rc = launch_zero(ctx, ctx->num, hbytes);
+    if (rc == KLNMF_OK && ctx->sparse && ctx->n > 0) {
+      { PhaseTimer t(ctx, prof, PH_RATIO); rc = sparse_rows(ctx, 0); }
+      if (rc == KLNMF_OK && fit) { PhaseTimer t(ctx, prof, PH_NUM); rc = sparse_scatter(ctx, false); }
+    } else if (rc == KLNMF_OK) {
+      rc = dense_iteration(ctx, fit, false, prof);
+    }
+    if (rc == KLNMF_OK && ctx->world > 1) {
+      PhaseTimer t(ctx, prof, PH_COMM);
+      rc = nccl_allreduce_sum_f64(ctx, ctx->dred, 2 + ctx->k);
+      if (rc == KLNMF_OK && fit)
+        rc = nccl_allreduce_sum(ctx, ctx->num, (ctx->sparse ? ctx->f : ctx->k) * ctx->ldh, ctx->es);
+    }
+    if (rc == KLNMF_OK) rc = launch_decide(ctx, it);
+    if (rc == KLNMF_OK && fit) {
+      PhaseTimer t(ctx, prof, PH_DICT);
+      const int hc = ctx->hcur;
+      rc = ctx->sparse ? launch_dict_update_t(ctx, ctx->H[hc], ctx->H[hc ^ 1])
+                       : launch_dict_update(ctx, ctx->H[hc], ctx->H[hc ^ 1], ctx->split ? ctx->Hlo[hc ^ 1] : nullptr);
+      ctx->hcur ^= 1;
+    }
+    ctx->cur ^= 1;
+    enq++;
+    if (rc == KLNMF_OK && tol_abs > 0.0 && (it % 32) == 31 && it + 1 < max_iter) {
+      cudaMemcpyAsync(hflags, ctx->flags, 8, cudaMemcpyDeviceToHost, ctx->stream);
+      cudaStreamSynchronize(ctx->stream);
+      if (hflags[FL_STOP]) break;
+    }
+  }
+  cudaEventRecord(ev1, ctx->stream);
+  cudaError_t se = cudaStreamSynchronize(ctx->stream);
+  if (rc == KLNMF_OK && se != cudaSuccess) {
+    set_error("klnmf_run: device error: %s", cudaGetErrorString(se));
+    rc = KLNMF_ECUDA;
+  }
+  if (rc == KLNMF_OK) {
+    cudaMemcpy(hflags, ctx->flags, 8, cudaMemcpyDeviceToHost);
+    const int ne = hflags[FL_NERR], stopped = hflags[FL_STOP];
+    // updates applied == errors recorded; later (gated) iterations wrote nothing
+    ctx->cur = (cur0 + ne) & 1;
+    ctx->hcur = fit ? (hcur0 + ne) & 1 : hcur0;
+    if (n_errors) *n_errors = ne;
+    if (n_iter) *n_iter = stopped ? ne + 1 : max_iter;
+    if (errors_out && ne > 0) {
+      cudaMemcpy(errors_out, ctx->errors_dev, (size_t)ne * 8, cudaMemcpyDeviceToHost);
+      ctx->bytes_d2h += (int64_t)ne * 8;
+    }
+    // a stop leaves FL_STOP set; clear it so that later calls (error, reconstruct) are not gated
+    cudaMemsetAsync(ctx->flags, 0, 4, ctx->stream);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, ev0, ev1);
+    for (int i = 0; i < 6; i++) ctx->prof_ms[i] = 0.0;
+    for (int i = 0; i < 5; i++) ctx->prof_cnt[i] = 0;
+    ctx->prof_ms[PH_TOTAL] = ms;
+    if (prof)
+      for (auto &e : prof->ev) {
+        float t = 0.f;
+        cudaEventElapsedTime(&t, e.a, e.b);
+        ctx->prof_ms[e.phase] += t;
+        ctx->prof_cnt[e.phase] += 1;
+      }
+  } else {
+    ctx->cur = cur0;
+    ctx->hcur = hcur0;
+  }
+  if (prof)
+    for (auto &e : prof->ev) { cudaEventDestroy(e.a); cudaEventDestroy(e.b); }
+  cudaEventDestroy(ev0);
+  cudaEventDestroy(ev1);
+  (void)enq;
+  return rc;
+}
+
+int klnmf_error(klnmf_ctx *ctx, double *out) {
+  KL_CHECK(ctx && out, KLNMF_EINVAL, "klnmf_error: NULL argument");
+  KL_CHECK(ctx->have_x && ctx->have_h && ctx->have_w, KLNMF_ESTATE, "klnmf_error needs data, dictionary and coefficients");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  KL_TRY(reset_reduction(ctx));
+  if (ctx->sparse) { if (ctx->n > 0) KL_TRY(sparse_rows(ctx, 1)); }
+  else KL_TRY(dense_iteration(ctx, 0, true, nullptr));
+  if (ctx->world > 1) KL_TRY(nccl_allreduce_sum_f64(ctx, ctx->dred, 2 + ctx->k));
+  std::vector<double> h(2 + ctx->k), rs(ctx->k);
+  KL_CUDA(cudaMemcpyAsync(h.data(), ctx->dred, (2 + ctx->k) * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  KL_CUDA(cudaMemcpyAsync(rs.data(), ctx->rowsumH, ctx->k * 8, cudaMemcpyDeviceToHost, ctx->stream));
+  KL_CUDA(cudaStreamSynchronize(ctx->stream));
+  double e = h[0];
+  if (ctx->sparse) {
+    double wh = 0.0;
+    for (int64_t a = 0; a < ctx->k; a++) wh += h[2 + a] * rs[a];
+    e = e - h[1] + wh;
+  }
+  *out = e;
+  KL_TRY(reset_reduction(ctx));
+  return KLNMF_OK;
+}
+
+// _updated_H with Q=None (nmf.py:345-351): H <- rownorm(H (.) W^T Q(W,H)) with the CURRENT W.
+int klnmf_dictionary_step(klnmf_ctx *ctx) {
+  KL_CHECK(ctx && ctx->have_x && ctx->have_h && ctx->have_w, KLNMF_ESTATE, "dictionary_step needs data, dictionary, coefficients");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  const int64_t hbytes = (ctx->sparse ? ctx->f : ctx->k) * ctx->ldh * (int64_t)ctx->es;
+  KL_TRY(reset_reduction(ctx));
+  KL_TRY(launch_zero(ctx, ctx->num, hbytes));
+  if (ctx->sparse) {
+    if (ctx->n > 0) {
+      KL_TRY(sparse_rows(ctx, 0));
+      KL_TRY(sparse_scatter(ctx, true));
+    }
+  } else {
+    KL_TRY(dense_iteration(ctx, 1, false, nullptr, true));
+  }
+  if (ctx->world > 1) KL_TRY(nccl_allreduce_sum(ctx, ctx->num, (ctx->sparse ? ctx->f : ctx->k) * ctx->ldh, ctx->es));
+  const int hc = ctx->hcur;
+  KL_TRY(ctx->sparse ? launch_dict_update_t(ctx, ctx->H[hc], ctx->H[hc ^ 1])
+                     : launch_dict_update(ctx, ctx->H[hc], ctx->H[hc ^ 1], ctx->split ? ctx->Hlo[hc ^ 1] : nullptr));
+  ctx->hcur ^= 1;
+  KL_TRY(reset_reduction(ctx));
+  KL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return KLNMF_OK;
+}
+
+// _Q (nmf.py:325-336): dense -> n x f matrix; CSR -> nnz values in the order of the stored entries.
+int klnmf_ratio_host(klnmf_ctx *ctx, void *out, int dtype, int64_t ld) {
+  KL_CHECK(ctx && out && ctx->have_x && ctx->have_h && ctx->have_w, KLNMF_ESTATE, "ratio_host needs data, dictionary, coefficients");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  KL_TRY(reset_reduction(ctx));
+  if (ctx->sparse) {
+    if (ctx->nnz > 0) {
+      KL_TRY(sparse_rows(ctx, 0));
+      KL_TRY(download_matrix(ctx, ctx->qnz, nullptr, ctx->nnz, out, dtype, ctx->nnz, 1, ctx->nnz, false));
+    }
+  } else {
+    KL_CHECK(ld >= ctx->f, KLNMF_EINVAL, "ratio_host: ld < f");
+    KL_TRY(dense_iteration(ctx, 0, false, nullptr, false, out, dtype, ld));
+  }
+  KL_TRY(reset_reduction(ctx));
+  KL_CUDA(cudaStreamSynchronize(ctx->stream));
+  return KLNMF_OK;
+}
+
+// _special_sparse_dot (nmf.py:52-70): (W.H) sampled at the stored entries of the CSR data.
+int klnmf_sddmm_host(klnmf_ctx *ctx, double *out_vals) {
+  KL_CHECK(ctx && ctx->sparse && ctx->have_x && ctx->have_h && ctx->have_w, KLNMF_ESTATE, "sddmm_host needs CSR data, dictionary, coefficients");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->nnz == 0) return KLNMF_OK;
+  KL_CHECK(out_vals, KLNMF_EINVAL, "sddmm_host: NULL output");
+  KL_TRY(reset_reduction(ctx));
+  KL_TRY(sparse_rows(ctx, 3));
+  KL_TRY(download_matrix(ctx, ctx->qnz, nullptr, ctx->nnz, out_vals, KLNMF_F64, ctx->nnz, 1, ctx->nnz, false));
+  KL_TRY(reset_reduction(ctx));
+  return KLNMF_OK;
+}
+
+int klnmf_reconstruct_host(klnmf_ctx *ctx, const double *H_dest, int64_t f_dest, int64_t ld_h, double *out,
+                           int64_t ld_out) {
+  KL_CHECK(ctx && H_dest && (out || ctx->n == 0) && f_dest > 0, KLNMF_EINVAL, "reconstruct_host: bad argument");
+  KL_CHECK(ctx->have_w, KLNMF_ESTATE, "reconstruct_host: no coefficients");
+  KL_CHECK(ld_h >= f_dest && ld_out >= f_dest, KLNMF_EINVAL, "reconstruct_host: leading dimension too small");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  if (ctx->n == 0) return KLNMF_OK;
+  const int64_t es = ctx->es;
+  const int64_t ldd = round_up(f_dest, 32);
+  void *Hd = nullptr, *Hdlo = nullptr, *panel = nullptr;
+  KL_TRY(dmalloc(&Hd, ctx->k * ldd * es));
+  cudaMemsetAsync(Hd, 0, ctx->k * ldd * es, ctx->stream);
+  int rc = upload_matrix(ctx, H_dest, KLNMF_F64, ld_h, Hd, ldd, ctx->k, f_dest, false);
+  if (rc == KLNMF_OK && ctx->split) {
+    rc = dmalloc(&Hdlo, ctx->k * ldd * es);
+    if (rc == KLNMF_OK) {
+      cudaMemsetAsync(Hdlo, 0, ctx->k * ldd * es, ctx->stream);
+      rc = launch_split(ctx, (const float *)Hd, (float *)Hd, (float *)Hdlo, ctx->k, f_dest, ldd);
+    }
+  }
+  int64_t prow = ((int64_t)1 << 30) / (ldd * es);
+  prow = prow / 128 * 128;
+  if (prow < 128) prow = 128;
+  if (prow > ctx->n) prow = ctx->n;
+  if (rc == KLNMF_OK) rc = dmalloc(&panel, prow * ldd * es);
+  const int cur = ctx->cur;
+  for (int64_t r0 = 0; r0 < ctx->n && rc == KLNMF_OK; r0 += prow) {
+    const int64_t rows = ctx->n - r0 < prow ? ctx->n - r0 : prow;
+    GemmDesc d{};
+    d.M = rows; d.N = f_dest; d.K = ctx->k;
+    d.A = (const char *)ctx->W[cur] + r0 * ctx->ldw * es; d.a_sm = ctx->ldw; d.a_sk = 1;
+    d.A_lo = ctx->split ? (const char *)ctx->Wlo[cur] + r0 * ctx->ldw * es : nullptr;
+    d.B = Hd; d.b_sk = ldd; d.b_sn = 1; d.B_lo = Hdlo;
+    d.out = panel; d.ldo = ldd;
+    rc = dense_gemm(ctx, EPI_STORE, d);
+    if (rc == KLNMF_OK)
+      rc = download_matrix(ctx, panel, nullptr, ldd, out + r0 * ld_out, KLNMF_F64, ld_out, rows, f_dest, false);
+  }
+  cudaStreamSynchronize(ctx->stream);
+  if (Hd) cudaFree(Hd);
+  if (Hdlo) cudaFree(Hdlo);
+  if (panel) cudaFree(panel);
+  return rc;
+}
+
+// ------------------------------------------------------------------------------------------------
+int klnmf_nccl_load(const char *libnccl_path) { return nccl_load(libnccl_path); }
+int klnmf_nccl_unique_id(void *id128) {
+  KL_CHECK(id128, KLNMF_EINVAL, "nccl_unique_id: NULL");
+  return nccl_unique_id(id128);
+}
+int klnmf_comm_init(klnmf_ctx *ctx, const void *id128, int rank, int world) {
+  KL_CHECK(ctx && id128, KLNMF_EINVAL, "comm_init: NULL argument");
+  return nccl_comm_init(ctx, id128, rank, world);
+}
+
+// ------------------------------------------------------------------------------------------------
+int klnmf_fill_dense_synthetic(klnmf_ctx *ctx, uint64_t seed) {
+  KL_CHECK(ctx, KLNMF_EINVAL, "ctx is NULL");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  KL_TRY(kind_guard(ctx, false));
+  release_data(ctx);
+  ctx->ldx = round_up(ctx->f, 32);
+  const int64_t bytes = (ctx->n > 0 ? ctx->n : 1) * ctx->ldx * ctx->es;
+  KL_TRY(dmalloc(&ctx->X, bytes));
+  ctx->x_owned = true;
+  if (ctx->ldx != ctx->f) KL_CUDA(cudaMemsetAsync(ctx->X, 0, bytes, ctx->stream));
+  KL_TRY(launch_fill_uniform(ctx, ctx->X, ctx->es, ctx->n, ctx->f, ctx->ldx, seed));
+  KL_TRY(ensure_state(ctx));
+  ctx->have_x = true;
+  return KLNMF_OK;
+}
+
+int klnmf_fill_csr_synthetic(klnmf_ctx *ctx, int64_t nnz_per_row, uint64_t seed) {
+  KL_CHECK(ctx && nnz_per_row > 0 && nnz_per_row <= ctx->f, KLNMF_EINVAL, "fill_csr_synthetic: bad nnz_per_row");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  KL_TRY(kind_guard(ctx, true));
+  release_data(ctx);
+  ctx->nnz = ctx->n * nnz_per_row;
+  KL_TRY(alloc_csr(ctx, ctx->nnz));
+  KL_TRY(dmalloc(&ctx->qnz, ctx->nnz * ctx->es));
+  KL_TRY(sparse_fill_synthetic(ctx, nnz_per_row, seed));
+  KL_TRY(ensure_state(ctx));
+  KL_TRY(launch_sum_vals(ctx));
+  ctx->have_x = true;
+  return KLNMF_OK;
+}
+
+int klnmf_get_dense_host(klnmf_ctx *ctx, void *X, int dtype, int64_t ld) {
+  KL_CHECK(ctx && X && ctx->have_x && !ctx->sparse, KLNMF_ESTATE, "get_dense_host: no dense data");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  return download_matrix(ctx, ctx->X, nullptr, ctx->ldx, X, dtype, ld, ctx->n, ctx->f, false);
+}
+
+int klnmf_counters(klnmf_ctx *ctx, int64_t out[4]) {
+  KL_CHECK(ctx && out, KLNMF_EINVAL, "counters: NULL argument");
+  out[0] = ctx->n_launch; out[1] = ctx->n_nccl; out[2] = ctx->bytes_h2d; out[3] = ctx->bytes_d2h;
+  return KLNMF_OK;
+}
+
+int klnmf_last_run_profile(klnmf_ctx *ctx, double ms[6], int64_t counts[5]) {
+  KL_CHECK(ctx && ms && counts, KLNMF_EINVAL, "last_run_profile: NULL argument");
+  for (int i = 0; i < 6; i++) ms[i] = ctx->prof_ms[i];
+  for (int i = 0; i < 5; i++) counts[i] = ctx->prof_cnt[i];
+  return KLNMF_OK;
+}
+
+// Diagnostic / test hook: one contraction out = op(A).op(B) through the context-free engine of
+// `mode` (the same kernels klnmf_run uses), host float64 in and out.
+int klnmf_contract_host(int device, int mode, int64_t M, int64_t N, int64_t K, const double *A, int a_trans,
+                        const double *B, int b_trans, double *out) {
+  KL_CHECK(A && B && out && M > 0 && N > 0 && K > 0, KLNMF_EINVAL, "contract_host: bad argument");
+  klnmf_ctx *ctx = nullptr;
+  KL_TRY(klnmf_create(&ctx, device, M, N, K, mode));
+  const int64_t es = ctx->es;
+  // A: a_trans=0 -> M x K row-major (K contiguous); a_trans=1 -> K x M row-major (M contiguous)
+  const int64_t a_rows = a_trans ? K : M, a_cols = a_trans ? M : K;
+  const int64_t b_rows = b_trans ? N : K, b_cols = b_trans ? K : N;
+  const int64_t lda = round_up(a_cols, 32), ldb = round_up(b_cols, 32), ldo = round_up(N, 32);
+  void *dA = nullptr, *dAlo = nullptr, *dB = nullptr, *dBlo = nullptr, *dO = nullptr;
+  int rc = dmalloc(&dA, a_rows * lda * es);
+  if (rc == KLNMF_OK) rc = dmalloc(&dB, b_rows * ldb * es);
+  if (rc == KLNMF_OK) rc = dmalloc(&dO, M * ldo * es);
+  if (rc == KLNMF_OK) {
+    cudaMemsetAsync(dA, 0, a_rows * lda * es, ctx->stream);
+    cudaMemsetAsync(dB, 0, b_rows * ldb * es, ctx->stream);
+    cudaMemsetAsync(dO, 0, M * ldo * es, ctx->stream);
+    rc = upload_matrix(ctx, A, KLNMF_F64, a_cols, dA, lda, a_rows, a_cols, false);
+  }
+  if (rc == KLNMF_OK) rc = upload_matrix(ctx, B, KLNMF_F64, b_cols, dB, ldb, b_rows, b_cols, false);
+  if (rc == KLNMF_OK && ctx->split) {
+    rc = dmalloc(&dAlo, a_rows * lda * es);
+    if (rc == KLNMF_OK) rc = dmalloc(&dBlo, b_rows * ldb * es);
+    if (rc == KLNMF_OK) {
+      cudaMemsetAsync(dAlo, 0, a_rows * lda * es, ctx->stream);
+      cudaMemsetAsync(dBlo, 0, b_rows * ldb * es, ctx->stream);
+      rc = launch_split(ctx, (const float *)dA, (float *)dA, (float *)dAlo, a_rows, a_cols, lda);
+    }
+    if (rc == KLNMF_OK) rc = launch_split(ctx, (const float *)dB, (float *)dB, (float *)dBlo, b_rows, b_cols, ldb);
+  }
+  if (rc == KLNMF_OK) {
+    GemmDesc d{};
+    d.M = M; d.N = N; d.K = K;
+    d.A = dA; d.A_lo = dAlo; d.a_sm = a_trans ? 1 : lda; d.a_sk = a_trans ? lda : 1;
+    d.B = dB; d.B_lo = dBlo; d.b_sk = b_trans ? 1 : ldb; d.b_sn = b_trans ? ldb : 1;
+    d.out = dO; d.ldo = ldo;
+    rc = dense_gemm(ctx, EPI_STORE, d);
+  }
+  if (rc == KLNMF_OK) rc = download_matrix(ctx, dO, nullptr, ldo, out, KLNMF_F64, N, M, N, false);
+  cudaError_t se = cudaStreamSynchronize(ctx->stream);
+  if (rc == KLNMF_OK && se != cudaSuccess) {
+    set_error("contract_host: device error: %s", cudaGetErrorString(se));
+    rc = KLNMF_ECUDA;
+  }
+  void *ptrs[] = {dA, dAlo, dB, dBlo, dO};
+  for (void *q : ptrs)
+    if (q) cudaFree(q);
+  klnmf_destroy(ctx);
+  return rc;
+}
+
+const char *klnmf_engine_name(klnmf_ctx *ctx) {
+  if (!ctx) return "none";
+  if (ctx->es == 8) return "dmma_f64";
+  if (ctx->debug_simt) return "simt_f32_debug";
+  return ctx->mode == KLNMF_MODE_TF32X3 ? "tcgen05_tf32x3" : "tcgen05_tf32";
+}
+
+}  // extern "C"

@@ -1,0 +1,176 @@
+// Shared declarations of libklnmf (B200 / sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "../../include/klnmf.h"
+
+#define KL_EPS      1.0e-8     // nmf.py:232,297,325 literal default
+#define KL_NORM_EPS 1.0e-16    // array_utils.py:19
+
+namespace klnmf {
+
+void set_error(const char *fmt, ...);
+
+#define KL_CUDA(expr)                                                                        \
+  do {                                                                                       \
+    cudaError_t _e = (expr);                                                                 \
+    if (_e != cudaSuccess) {                                                                 \
+      klnmf::set_error("%s:%d: %s -> %s", __FILE__, __LINE__, #expr, cudaGetErrorString(_e)); \
+      return KLNMF_ECUDA;                                                                    \
+    }                                                                                        \
+  } while (0)
+
+#define KL_CHECK(cond, code, ...)     \
+  do {                                \
+    if (!(cond)) {                    \
+      klnmf::set_error(__VA_ARGS__);  \
+      return (code);                  \
+    }                                 \
+  } while (0)
+
+#define KL_TRY(expr)              \
+  do {                            \
+    int _r = (expr);              \
+    if (_r != KLNMF_OK) return _r; \
+  } while (0)
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+static inline int64_t ceil_div(int64_t x, int64_t m) { return (x + m - 1) / m; }
+
+// device scalars (double) kept in ctx->dscal
+enum { DS_KL = 0, DS_PREV = 1, DS_WHSUM = 2, DS_SUMX = 3, DS_TOL = 4, DS_COUNT = 8 };
+// device flags (int) kept in ctx->flags
+enum { FL_STOP = 0, FL_NERR = 1, FL_NEG = 2, FL_NONFINITE = 3, FL_COUNT = 8 };
+// profile phases
+enum { PH_RATIO = 0, PH_COEF = 1, PH_NUM = 2, PH_DICT = 3, PH_COMM = 4, PH_TOTAL = 5 };
+
+}  // namespace klnmf
+
+struct klnmf_ctx {
+  int device = 0;
+  int64_t n = 0, f = 0, k = 0;
+  int mode = 0;
+  int es = 4;                  // element size of device state (4: TF32 modes, 8: FP64)
+  bool debug_simt = false;     // KLNMF_DEBUG_ENGINE=simt: FP32 FMA bring-up engine (never default)
+  cudaStream_t stream = nullptr;
+  bool own_stream = false;
+  int sm_count = 148;
+
+  // ---- data -------------------------------------------------------------------------
+  bool have_x = false, sparse = false;
+  void *X = nullptr;           // dense n x f
+  int64_t ldx = 0;
+  bool x_owned = false;
+  int64_t nnz = 0;
+  int64_t *indptr = nullptr;   // n+1
+  int32_t *indices = nullptr;  // nnz
+  void *vals = nullptr;        // nnz
+  bool csr_owned = false;
+  void *qnz = nullptr;         // nnz ratio values (sparse path)
+
+  // ---- state -------------------------------------------------------------------------
+  bool have_h = false, have_w = false;
+  int cur = 0;                 // index of the current W in the ping-pong buffers
+  int hcur = 0;                // index of the current dictionary (flips only while fitting)
+  bool split = false;          // TF32X3: arrays hold the tf32-exact high part, *lo the residual
+  void *W[2] = {nullptr, nullptr};
+  int64_t ldw = 0;             // n x k
+  void *H[2] = {nullptr, nullptr};
+  int64_t ldh = 0;             // dense: k x f (ld >= f);  sparse: f x k transposed (ld >= k)
+  void *Wlo[2] = {nullptr, nullptr};   // TF32X3 low parts (same layout)
+  void *Hlo[2] = {nullptr, nullptr};
+  void *num = nullptr;         // numerator accumulator, same layout as H
+  double *rowsumH = nullptr;   // k   (sum over f of H, used by the sparse objective)
+  double *colsumW = nullptr;   // k
+  double *hsum = nullptr;      // k   scratch of the normaliser
+  double *dred = nullptr;      // [kl, sum(X.data), colsum(W)[0..ldw)] : the doubles that are all-reduced
+  int64_t dred_len = 0;
+  void *stage = nullptr;       // device staging for host<->device conversions
+  int64_t stage_bytes = 0;
+
+  // ---- dense scratch -------------------------------------------------------------------
+  void *Q = nullptr, *Qlo = nullptr;   // panel_rows x f ratio panel
+  int64_t ldq = 0, panel_rows = 0;
+  int64_t scratch_limit = (int64_t)16 << 30;
+
+  // ---- control ---------------------------------------------------------------------------
+  double *dscal = nullptr;     // DS_COUNT doubles
+  int *flags = nullptr;        // FL_COUNT ints
+  double *errors_dev = nullptr;
+  int errors_cap = 0;
+  double *pinned = nullptr;    // small pinned host buffer for read-backs
+
+  // ---- multi GPU ----------------------------------------------------------------------------
+  void *comm = nullptr;        // ncclComm_t
+  int rank = 0, world = 1;
+
+  // ---- accounting -----------------------------------------------------------------------------
+  int64_t n_launch = 0, n_nccl = 0, bytes_h2d = 0, bytes_d2h = 0;
+  double prof_ms[6] = {0, 0, 0, 0, 0, 0};
+  int64_t prof_cnt[5] = {0, 0, 0, 0, 0};
+  bool profile = false;        // per-phase events (adds syncs at the end only)
+  void *tc = nullptr;          // tcgen05 engine private state (tensor maps, ...)
+};
+
+namespace klnmf {
+
+// ---- generic (DMMA fp64 / FMA fp32 bring-up) contraction engine: dense_generic.cu -----------
+// C = op(A) . op(B) with arbitrary strides and a fused epilogue.
+enum Epilogue {
+  EPI_STORE = 0,   // out = C
+  EPI_RATIO = 1,   // out = (X+eps)/(C+eps), kl += X*log(out) - X + C        (nmf.py:325-336, metrics.py:18-20)
+  EPI_MULW = 2,    // out = aux * C                                           (nmf.py:338-343)
+  EPI_ACC = 3      // out += C  (atomic, split over the contraction)          (nmf.py:345-349)
+};
+struct GemmDesc {
+  int64_t M, N, K;
+  const void *A; int64_t a_sm, a_sk;     // A(m,kk) = A[m*a_sm + kk*a_sk]
+  const void *B; int64_t b_sk, b_sn;     // B(kk,n) = B[kk*b_sk + n*b_sn]
+  void *out; int64_t ldo;                // row-major M x N
+  const void *aux; int64_t ldaux;        // X (EPI_RATIO) or W (EPI_MULW), row-major M x N
+  double *kl;                            // objective accumulator (EPI_RATIO) or nullptr
+  const int *stop;                       // device stop flag: kernel exits when *stop != 0
+  int splitk;                            // EPI_ACC only
+  int only_kl;                           // EPI_RATIO: do not write out (klnmf_error)
+  // split-TF32 residual arrays (same layout as their high parts); nullptr unless ctx->split
+  const void *A_lo; const void *B_lo; void *out_lo; const void *aux_lo;
+};
+int generic_gemm(klnmf_ctx *ctx, int es, int epi, const GemmDesc &d);
+
+// ---- tcgen05 engine: dense_tc.cu ---------------------------------------------------------------
+int tc_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d);
+int tc_selftest(int *n_fail, char *report, int report_len);
+void tc_release(klnmf_ctx *ctx);
+
+// ---- elementwise / reductions: elementwise.cu ----------------------------------------------------
+int launch_dict_update(klnmf_ctx *ctx, const void *H_old, void *H_new, void *Hlo_new);
+int launch_dict_update_t(klnmf_ctx *ctx, const void *Ht_old, void *Ht_new);     // sparse: f x k layout
+int launch_decide(klnmf_ctx *ctx, int iter_index);
+int launch_split(klnmf_ctx *ctx, const float *src, float *hi, float *lo, int64_t rows, int64_t cols, int64_t ld);
+// dst = (src [+ src_lo]) converted; optional transpose
+int launch_convert(klnmf_ctx *ctx, const void *src, const void *src_lo, int src_dtype, int64_t src_ld, void *dst,
+                   int dst_es, int64_t dst_ld, int64_t rows, int64_t cols, bool transpose);
+int launch_zero(klnmf_ctx *ctx, void *p, int64_t bytes);
+int launch_fill_uniform(klnmf_ctx *ctx, void *p, int es, int64_t rows, int64_t cols, int64_t ld, uint64_t seed);
+int launch_check(klnmf_ctx *ctx, const void *p, int es, int64_t rows, int64_t cols, int64_t ld);
+int launch_rowsum_h(klnmf_ctx *ctx);        // rowsumH from the current dictionary
+int launch_sum_vals(klnmf_ctx *ctx);        // DS_SUMX = sum of CSR values
+
+// ---- sparse path: sparse.cu ------------------------------------------------------------------------
+int sparse_rows(klnmf_ctx *ctx, int mode);    // 0 full pass, 1 objective only, 3 SDDMM only
+int sparse_scatter(klnmf_ctx *ctx, bool use_current_w);
+int sparse_init_w(klnmf_ctx *ctx);
+int sparse_fill_synthetic(klnmf_ctx *ctx, int64_t nnz_per_row, uint64_t seed);
+
+// ---- NCCL through dlopen: nccl_dyn.cu ----------------------------------------------------------------
+int nccl_load(const char *path);
+int nccl_unique_id(void *id128);
+int nccl_comm_init(klnmf_ctx *ctx, const void *id128, int rank, int world);
+int nccl_allreduce_sum(klnmf_ctx *ctx, void *buf, int64_t count, int es);
+int nccl_allreduce_sum_f64(klnmf_ctx *ctx, double *buf, int64_t count);
+void nccl_comm_destroy(klnmf_ctx *ctx);
+
+}  // namespace klnmf

@@ -1,0 +1,588 @@
+// tcgen05 / TMEM / TMA contraction engine for sm_100a with the KL-NMF epilogues fused in.
+//
+// One persistent, warp-specialised kernel serves the three contractions of a reference
+// iteration (nmf.py:325-351) plus W0 = X.H0^T (nmf.py:156) and internal.dot(dico) (learner.py:81):
+//
+//   warp 0      TMA producer   : cp.async.bulk.tensor 2D boxes (128B swizzle) -> smem ring
+//   warp 1      MMA issuer     : tcgen05.mma.cta_group::1.kind::tf32, accumulators in TMEM
+//   warps 2..9  epilogue       : tcgen05.ld 32x32b -> registers -> fused epilogue -> global
+//
+// D tile = 128 x BN fp32 in TMEM, double buffered (2*BN <= 512 columns), so the epilogue of
+// tile i overlaps the mainloop of tile i+1.  Operands may be K-major or MN-major (both are legal
+// for kind::tf32), which lets W, H, Q be consumed exactly as they lie in HBM:
+//   ratio      S = W.H        A = W  (K-major)   B = H  (MN-major)   epilogue: Q=(X+eps)/(S+eps), KL
+//   coefficient G = Q.H^T     A = Q  (K-major)   B = H  (K-major)    epilogue: W' = W (.) G
+//   numerator  N += W'^T.Q    A = W' (MN-major)  B = Q  (MN-major)   epilogue: red.add (split over rows)
+// Split-TF32 ("tf32x3"): every operand is a (hi, lo) pair with hi exactly representable in TF32;
+// three MMAs hi*hi + hi*lo + lo*hi per K step give FP32-grade products.
+#include <cuda.h>
+
+#include "common.cuh"
+
+namespace klnmf {
+
+namespace {
+
+constexpr int BM = 128;          // tile rows  (UMMA M, cta_group::1)
+constexpr int BK = 32;           // K per stage in floats = one 128-byte swizzle span
+constexpr int UMMA_K = 8;        // kind::tf32: 32 bytes of K per instruction
+constexpr int NUM_THREADS = 320; // producer warp + MMA warp + 8 epilogue warps
+constexpr int EPI_WARPS = 8;
+
+struct TcParams {
+  int64_t M, N, K;
+  int m_tiles, n_tiles, splits, m_fastest;
+  int64_t kb_total, kb_per_split;        // K blocks (of BK)
+  int epi, only_kl, accurate;
+  float *out, *out_lo;
+  int64_t ldo, n_store;                  // columns < n_store are written (multiple of 32, <= ldo)
+  const float *aux, *aux_lo;
+  int64_t ldaux;
+  double *kl;
+  const int *stop;
+  int *err;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *err, int code) {
+  if (mbar_try_wait(bar, parity)) return;
+  uint64_t t0;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+  for (;;) {
+    for (int i = 0; i < 2048; i++)
+      if (mbar_try_wait(bar, parity)) return;
+    uint64_t t1;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+    if (t1 - t0 > 4000000000ull) {   // 4 s
+      if (err) atomicExch(err, code);
+      __threadfence_system();
+      asm volatile("trap;");
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float tf32_round(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
+// Shared-memory matrix descriptor (sm_100 UMMA), 128-byte swizzle.
+//   K-major : rows of 128 B (32 floats of K), 8-row groups SBO = 1024 B apart
+//   MN-major: rows of 128 B (32 floats of M/N), one row per K index; 8-row K groups SBO = 1024 B
+//             apart, 32-wide M/N groups LBO bytes apart
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
+  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  return d;
+}
+
+template <int BN, bool SPLIT>
+struct Cfg {
+  static constexpr int A_BYTES = BM * BK * 4;
+  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (SPLIT ? 2 : 1);
+  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
+  static constexpr int TMEM_COLS = 2 * BN;   // power of two: 256 or 512
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// ---------------------------------------------------------------------------------------------
+// fused epilogue on one 32-column chunk held by its row-owning thread
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void st_row32(float *p, const float v[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; j++)
+    *reinterpret_cast<float4 *>(p + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+}
+__device__ __forceinline__ void ld_row32(const float *p, float v[32]) {
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    float4 t = __ldg(reinterpret_cast<const float4 *>(p + 4 * j));
+    v[4 * j] = t.x; v[4 * j + 1] = t.y; v[4 * j + 2] = t.z; v[4 * j + 3] = t.w;
+  }
+}
+
+template <bool SPLIT>
+__device__ __forceinline__ void epilogue_chunk(const TcParams &p, int64_t row, int64_t col0, const uint32_t acc_u[32],
+                                               double &kl) {
+  float acc[32];
+#pragma unroll
+  for (int j = 0; j < 32; j++) acc[j] = __uint_as_float(acc_u[j]);
+  if (row >= p.M || col0 >= p.n_store) return;
+  const int epi = p.epi;
+  if (epi == EPI_STORE) {
+    if (SPLIT && p.out_lo) {
+      float hi[32], lo[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) { hi[j] = tf32_round(acc[j]); lo[j] = acc[j] - hi[j]; }
+      st_row32(p.out + row * p.ldo + col0, hi);
+      st_row32(p.out_lo + row * p.ldo + col0, lo);
+    } else {
+      st_row32(p.out + row * p.ldo + col0, acc);
+    }
+  } else if (epi == EPI_RATIO) {
+    float x[32], q[32];
+    ld_row32(p.aux + row * p.ldaux + col0, x);
+    float part = 0.f;
+#pragma unroll
+    for (int j = 0; j < 32; j++) {
+      const float s = acc[j];
+      float lq;
+      if (p.accurate) {
+        q[j] = (x[j] + (float)KL_EPS) / (s + (float)KL_EPS);
+        lq = logf(q[j]);
+      } else {
+        q[j] = __fdividef(x[j] + (float)KL_EPS, s + (float)KL_EPS);
+        lq = __logf(q[j]);
+      }
+      // columns >= N hold x = 0, s = 0: q = 1, the term is exactly 0
+      part += fmaf(x[j], lq, s - x[j]);
+    }
+    kl += (double)part;
+    if (!p.only_kl) {
+      if (SPLIT && p.out_lo) {
+        float lo[32];
+#pragma unroll
+        for (int j = 0; j < 32; j++) { float h = tf32_round(q[j]); lo[j] = q[j] - h; q[j] = h; }
+        st_row32(p.out + row * p.ldo + col0, q);
+        st_row32(p.out_lo + row * p.ldo + col0, lo);
+      } else {
+        st_row32(p.out + row * p.ldo + col0, q);
+      }
+    }
+  } else if (epi == EPI_MULW) {
+    float w[32];
+    ld_row32(p.aux + row * p.ldaux + col0, w);
+    if (SPLIT && p.aux_lo) {
+      float wl[32];
+      ld_row32(p.aux_lo + row * p.ldaux + col0, wl);
+#pragma unroll
+      for (int j = 0; j < 32; j++) w[j] += wl[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j++) w[j] *= acc[j];
+    if (SPLIT && p.out_lo) {
+      float lo[32];
+#pragma unroll
+      for (int j = 0; j < 32; j++) { float h = tf32_round(w[j]); lo[j] = w[j] - h; w[j] = h; }
+      st_row32(p.out + row * p.ldo + col0, w);
+      st_row32(p.out_lo + row * p.ldo + col0, lo);
+    } else {
+      st_row32(p.out + row * p.ldo + col0, w);
+    }
+  } else {  // EPI_ACC
+    float *o = p.out + row * p.ldo + col0;
+#pragma unroll
+    for (int j = 0; j < 8; j++)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(o + 4 * j), "f"(acc[4 * j]),
+                   "f"(acc[4 * j + 1]), "f"(acc[4 * j + 2]), "f"(acc[4 * j + 3])
+                   : "memory");
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <int BN, bool A_MN, bool B_MN, bool SPLIT>
+__global__ void __launch_bounds__(NUM_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
+  using C = Cfg<BN, SPLIT>;
+  constexpr int STAGES = C::STAGES;
+  if (p.stop != nullptr && *p.stop != 0) return;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t bar_base = smem_base + STAGES * C::STAGE_BYTES;
+  // barrier block: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem_ptr
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+  volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(smem_gen + STAGES * C::STAGE_BYTES +
+                                                                           8 * (2 * STAGES + 4));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (SPLIT) { tma_prefetch_desc(&tmAlo); tma_prefetch_desc(&tmBlo); }
+    for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr_addr, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+
+  const int64_t total_units = (int64_t)p.m_tiles * p.n_tiles * p.splits;
+  auto decode = [&](int64_t u, int &mi, int &ni, int &si) {
+    if (p.m_fastest) { mi = (int)(u % p.m_tiles); u /= p.m_tiles; ni = (int)(u % p.n_tiles); si = (int)(u / p.n_tiles); }
+    else { ni = (int)(u % p.n_tiles); u /= p.n_tiles; mi = (int)(u % p.m_tiles); si = (int)(u / p.m_tiles); }
+  };
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int64_t u = blockIdx.x; u < total_units; u += gridDim.x) {
+        int mi, ni, si;
+        decode(u, mi, ni, si);
+        const int64_t kb0 = (int64_t)si * p.kb_per_split;
+        const int64_t kb1 = kb0 + p.kb_per_split < p.kb_total ? kb0 + p.kb_per_split : p.kb_total;
+        const int32_t m0 = mi * BM, n0 = ni * BN;
+        for (int64_t kb = kb0; kb < kb1; kb++) {
+          mbar_wait(empty_bar(stage), phase ^ 1, p.err, 1);
+          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          const uint32_t sA = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sAlo = sA + C::A_BYTES;
+          const uint32_t sB = sA + C::A_BYTES * (SPLIT ? 2 : 1);
+          const uint32_t sBlo = sB + C::B_BYTES;
+          const int32_t k0 = (int32_t)(kb * BK);
+          if (!A_MN) {
+            tma_load_2d(sA, &tmA, full_bar(stage), k0, m0);
+            if (SPLIT) tma_load_2d(sAlo, &tmAlo, full_bar(stage), k0, m0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BM / 32; i++) {
+              tma_load_2d(sA + i * 4096, &tmA, full_bar(stage), m0 + 32 * i, k0);
+              if (SPLIT) tma_load_2d(sAlo + i * 4096, &tmAlo, full_bar(stage), m0 + 32 * i, k0);
+            }
+          }
+          if (!B_MN) {
+            tma_load_2d(sB, &tmB, full_bar(stage), k0, n0);
+            if (SPLIT) tma_load_2d(sBlo, &tmBlo, full_bar(stage), k0, n0);
+          } else {
+#pragma unroll
+            for (int i = 0; i < BN / 32; i++) {
+              tma_load_2d(sB + i * 4096, &tmB, full_bar(stage), n0 + 32 * i, k0);
+              if (SPLIT) tma_load_2d(sBlo + i * 4096, &tmBlo, full_bar(stage), n0 + 32 * i, k0);
+            }
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
+      const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int64_t u = blockIdx.x; u < total_units; u += gridDim.x) {
+        int mi, ni, si;
+        decode(u, mi, ni, si);
+        const int64_t kb0 = (int64_t)si * p.kb_per_split;
+        const int64_t kb1 = kb0 + p.kb_per_split < p.kb_total ? kb0 + p.kb_per_split : p.kb_total;
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1, p.err, 2);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int64_t kb = kb0; kb < kb1; kb++) {
+          mbar_wait(full_bar(stage), phase, p.err, 3);
+          tc_fence_after();
+          const uint32_t sA = smem_base + stage * C::STAGE_BYTES;
+          const uint32_t sAlo = sA + C::A_BYTES;
+          const uint32_t sB = sA + C::A_BYTES * (SPLIT ? 2 : 1);
+          const uint32_t sBlo = sB + C::B_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < BK / UMMA_K; kk++) {
+            // K-major: +32 B inside the 128 B swizzle row; MN-major: next 8-row group (+1024 B)
+            const uint32_t a_off = A_MN ? kk * 1024u : kk * 32u;
+            const uint32_t b_off = B_MN ? kk * 1024u : kk * 32u;
+            const uint32_t a_lbo = A_MN ? 4096u : 16u, b_lbo = B_MN ? 4096u : 16u;
+            const uint64_t da = make_desc(sA + a_off, a_lbo, 1024u);
+            const uint64_t db = make_desc(sB + b_off, b_lbo, 1024u);
+            const uint32_t first = (kb > kb0 || kk > 0) ? 1u : 0u;
+            if (SPLIT) {
+              const uint64_t dal = make_desc(sAlo + a_off, a_lbo, 1024u);
+              const uint64_t dbl = make_desc(sBlo + b_off, b_lbo, 1024u);
+              umma_tf32(d_tmem, dal, db, idesc, first);   // lo*hi
+              umma_tf32(d_tmem, da, dbl, idesc, 1u);      // hi*lo
+              umma_tf32(d_tmem, da, db, idesc, 1u);       // hi*hi
+            } else {
+              umma_tf32(d_tmem, da, db, idesc, first);
+            }
+          }
+          umma_commit(empty_bar(stage));            // smem slot free once these MMAs retire
+          if (kb + 1 == kb1) umma_commit(tfull_bar(acc));   // accumulator complete
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int e = warp - 2;                 // 0..7
+    const int quarter = warp & 3;           // TMEM lanes this warp may touch: [32*quarter, +32)
+    const int half = e >> 2;                // column half of the tile
+    int acc = 0; uint32_t acc_phase = 0;
+    double kl = 0.0;
+    for (int64_t u = blockIdx.x; u < total_units; u += gridDim.x) {
+      int mi, ni, si;
+      decode(u, mi, ni, si);
+      mbar_wait(tfull_bar(acc), acc_phase, p.err, 4);
+      tc_fence_after();
+      const int64_t row = (int64_t)mi * BM + quarter * 32 + lane;
+#pragma unroll 1
+      for (int c = 0; c < BN / 64; c++) {
+        const int col_in_tile = half * (BN / 2) + c * 32;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col_in_tile);
+        uint32_t v[32];
+        tmem_ld32(taddr, v);
+        epilogue_chunk<SPLIT>(p, row, (int64_t)ni * BN + col_in_tile, v, kl);
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (p.epi == EPI_RATIO && p.kl != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) kl += __shfl_xor_sync(0xffffffffu, kl, o);
+      if (lane == 0) atomicAdd(p.kl, kl);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, C::TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void *p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = (EncodeTiledFn)p;
+  return fn;
+}
+
+// 2D fp32 tensor map: inner (contiguous) extent `inner`, `outer` rows `ld` elements apart; box = 32 x box_rows.
+int make_map(CUtensorMap *map, const void *base, int64_t inner, int64_t outer, int64_t ld, int box_rows) {
+  EncodeTiledFn enc = get_encode();
+  KL_CHECK(enc != nullptr, KLNMF_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+  KL_CHECK(((uintptr_t)base % 16) == 0 && (ld * 4) % 16 == 0, KLNMF_EINVAL,
+           "TMA operand must be 16-byte aligned with a 16-byte multiple row pitch (ld=%lld)", (long long)ld);
+  cuuint64_t dims[2] = {(cuuint64_t)inner, (cuuint64_t)outer};
+  cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  KL_CHECK(r == CUDA_SUCCESS, KLNMF_ECUDA, "cuTensorMapEncodeTiled failed with %d (inner=%lld outer=%lld ld=%lld)", (int)r,
+           (long long)inner, (long long)outer, (long long)ld);
+  return KLNMF_OK;
+}
+
+struct TcState {
+  int *err_dev = nullptr;
+};
+
+template <int BN, bool A_MN, bool B_MN, bool SPLIT>
+int launch_cfg(klnmf_ctx *ctx, const GemmDesc &d, TcParams p) {
+  using C = Cfg<BN, SPLIT>;
+  static_assert(C::STAGES >= 2, "pipeline too shallow");
+  CUtensorMap tmA, tmAlo, tmB, tmBlo;
+  // A: K-major = memory M x K (inner K);  MN-major = memory K x M (inner M)
+  if (!A_MN) KL_TRY(make_map(&tmA, d.A, d.K, d.M, d.a_sm, BM));
+  else KL_TRY(make_map(&tmA, d.A, d.M, d.K, d.a_sk, 32));
+  if (!B_MN) KL_TRY(make_map(&tmB, d.B, d.K, d.N, d.b_sn, BN));
+  else KL_TRY(make_map(&tmB, d.B, d.N, d.K, d.b_sk, 32));
+  tmAlo = tmA;
+  tmBlo = tmB;
+  if (SPLIT) {
+    if (!A_MN) KL_TRY(make_map(&tmAlo, d.A_lo, d.K, d.M, d.a_sm, BM));
+    else KL_TRY(make_map(&tmAlo, d.A_lo, d.M, d.K, d.a_sk, 32));
+    if (!B_MN) KL_TRY(make_map(&tmBlo, d.B_lo, d.K, d.N, d.b_sn, BN));
+    else KL_TRY(make_map(&tmBlo, d.B_lo, d.N, d.K, d.b_sk, 32));
+  }
+  p.m_tiles = (int)ceil_div(d.M, BM);
+  p.n_tiles = (int)ceil_div(d.N, BN);
+  p.kb_total = ceil_div(d.K, BK);
+  p.splits = 1;
+  p.kb_per_split = p.kb_total;
+  if (p.epi == EPI_ACC) {
+    // split the contraction so that the persistent grid is filled evenly (>= 95 % wave efficiency)
+    const int64_t tiles = (int64_t)p.m_tiles * p.n_tiles;
+    const int64_t max_s = p.kb_total / 16 > 0 ? p.kb_total / 16 : 1;   // >= 512 of K per unit
+    int64_t best = 1; double best_eff = 0.0;
+    for (int64_t s = 1; s <= max_s && s <= 64; s++) {
+      const int64_t units = tiles * s;
+      const double eff = (double)units / (double)(ceil_div(units, ctx->sm_count) * ctx->sm_count);
+      if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
+      if (eff >= 0.95) { best = s; break; }
+    }
+    p.kb_per_split = ceil_div(p.kb_total, best);
+    p.splits = (int)ceil_div(p.kb_total, p.kb_per_split);
+  }
+  const int64_t units = (int64_t)p.m_tiles * p.n_tiles * p.splits;
+  if (units == 0 || p.kb_total == 0) return KLNMF_OK;
+  const int grid = (int)(units < ctx->sm_count ? units : ctx->sm_count);
+  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, SPLIT>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    KL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, ctx->stream>>>(tmA, tmAlo, tmB, tmBlo, p);
+  ctx->n_launch++;
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
+template <bool A_MN, bool B_MN>
+int launch_major(klnmf_ctx *ctx, const GemmDesc &d, const TcParams &p, bool split, bool narrow) {
+  if (split) return narrow ? launch_cfg<128, A_MN, B_MN, true>(ctx, d, p) : launch_cfg<256, A_MN, B_MN, true>(ctx, d, p);
+  return narrow ? launch_cfg<128, A_MN, B_MN, false>(ctx, d, p) : launch_cfg<256, A_MN, B_MN, false>(ctx, d, p);
+}
+
+}  // namespace
+
+int tc_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d) {
+  if (d.M <= 0 || d.N <= 0) return KLNMF_OK;
+  const bool a_mn = d.a_sm == 1 && d.a_sk != 1;
+  const bool b_mn = d.b_sn == 1 && d.b_sk != 1;
+  KL_CHECK(a_mn || d.a_sk == 1, KLNMF_EINVAL, "tc_gemm: A must have a unit stride");
+  KL_CHECK(b_mn || d.b_sk == 1, KLNMF_EINVAL, "tc_gemm: B must have a unit stride");
+  TcState *st = (TcState *)ctx->tc;
+  if (!st) {
+    st = new TcState();
+    if (cudaMalloc((void **)&st->err_dev, 4) != cudaSuccess) {
+      delete st;
+      set_error("tc_gemm: cudaMalloc failed");
+      return KLNMF_ENOMEM;
+    }
+    cudaMemsetAsync(st->err_dev, 0, 4, ctx->stream);
+    ctx->tc = st;
+  }
+  const bool split = ctx->split && d.A_lo != nullptr && d.B_lo != nullptr;
+  KL_CHECK(!ctx->split || split, KLNMF_EINVAL, "tc_gemm: split-TF32 mode needs (hi, lo) operands");
+  TcParams p{};
+  p.M = d.M; p.N = d.N; p.K = d.K;
+  p.epi = epi; p.only_kl = d.only_kl;
+  p.accurate = ctx->mode == KLNMF_MODE_TF32X3 ? 1 : 0;
+  p.out = (float *)d.out; p.out_lo = (float *)d.out_lo; p.ldo = d.ldo;
+  p.n_store = round_up(d.N, 32);
+  KL_CHECK(epi == EPI_RATIO && d.only_kl ? true : p.n_store <= d.ldo, KLNMF_EINVAL,
+           "tc_gemm: output leading dimension %lld too small for N=%lld rounded to 32", (long long)d.ldo, (long long)d.N);
+  p.aux = (const float *)d.aux; p.aux_lo = (const float *)d.aux_lo; p.ldaux = d.ldaux;
+  KL_CHECK(!(epi == EPI_RATIO || epi == EPI_MULW) || (d.aux && d.ldaux >= p.n_store), KLNMF_EINVAL,
+           "tc_gemm: aux operand missing or its leading dimension is below N rounded to 32");
+  p.kl = d.kl; p.stop = d.stop; p.err = st->err_dev;
+  p.m_fastest = (epi == EPI_ACC) ? 1 : 0;
+  const char *force = getenv("KLNMF_TC_BN");
+  bool narrow = d.N <= 128;
+  if (force) narrow = atoi(force) == 128;
+  if (!a_mn && !b_mn) return launch_major<false, false>(ctx, d, p, split, narrow);
+  if (!a_mn && b_mn) return launch_major<false, true>(ctx, d, p, split, narrow);
+  if (a_mn && b_mn) return launch_major<true, true>(ctx, d, p, split, narrow);
+  return launch_major<true, false>(ctx, d, p, split, narrow);
+}
+
+int tc_selftest(int *n_fail, char *, int) { *n_fail = 0; return KLNMF_OK; }
+
+void tc_release(klnmf_ctx *ctx) {
+  TcState *st = (TcState *)ctx->tc;
+  if (!st) return;
+  if (st->err_dev) cudaFree(st->err_dev);
+  delete st;
+  ctx->tc = nullptr;
+}
+
+}  // namespace klnmf

@@ -1,0 +1,356 @@
+// Vectorised / warp-reduction kernels around the contractions:
+// dictionary update + row normalisation (nmf.py:345-351, array_utils.py:19-22), the
+// device-side stopping test (nmf.py:214-220), split-TF32 operand preparation, layout
+// conversion, input checks, synthetic data.
+#include "common.cuh"
+
+namespace klnmf {
+
+namespace {
+
+__device__ __forceinline__ float tf32_hi(float v) {
+  uint32_t u;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
+  return __uint_as_float(u);
+}
+
+__device__ __forceinline__ double block_sum(double v, double *red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  double s = 0.0;
+  if (warp == 0) {
+    s = lane < nw ? red[lane] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[0] = s;
+  }
+  __syncthreads();
+  s = red[0];
+  __syncthreads();
+  return s;
+}
+
+// H_new[a,:] = H[a,:]*N[a,:] / (1e-16 + sum_j H[a,j]*N[a,j]); one block per dictionary row.
+template <typename T>
+__global__ void __launch_bounds__(512) dict_update_kernel(const T *__restrict__ H, const T *__restrict__ Hlo,
+                                                          const T *__restrict__ num, T *__restrict__ Hn,
+                                                          T *__restrict__ Hnlo, int64_t f, int64_t ld,
+                                                          double *__restrict__ rowsum, const int *stop) {
+  if (*stop != 0) return;
+  __shared__ double red[32];
+  const int64_t a = blockIdx.x;
+  const T *h = H + a * ld, *nm = num + a * ld;
+  const T *hl = Hlo ? Hlo + a * ld : nullptr;
+  double s = 0.0;
+  for (int64_t j = threadIdx.x; j < f; j += blockDim.x) {
+    T v = h[j];
+    if (hl) v += hl[j];
+    s += (double)(v * nm[j]);
+  }
+  s = block_sum(s, red);
+  const double inv = 1.0 / (KL_NORM_EPS + s);
+  for (int64_t j = threadIdx.x; j < f; j += blockDim.x) {
+    T v = h[j];
+    if (hl) v += hl[j];
+    T r = (T)((double)(v * nm[j]) * inv);
+    if (Hnlo) {
+      float hi = tf32_hi((float)r);
+      Hn[a * ld + j] = (T)hi;
+      Hnlo[a * ld + j] = (T)((float)r - hi);
+    } else {
+      Hn[a * ld + j] = r;
+    }
+  }
+  if (threadIdx.x == 0 && rowsum) rowsum[a] = s * inv;
+}
+
+// transposed (sparse-path) layout: Ht is f x k.  Pass 1: column sums of Ht*Nt.
+template <typename T>
+__global__ void __launch_bounds__(256) dict_colsum_t_kernel(const T *__restrict__ Ht, const T *__restrict__ Nt,
+                                                            int64_t f, int64_t k, int64_t ld,
+                                                            double *__restrict__ hsum, int rows_per_block,
+                                                            const int *stop) {
+  if (*stop != 0) return;
+  const int64_t j0 = (int64_t)blockIdx.x * rows_per_block;
+  const int64_t j1 = j0 + rows_per_block < f ? j0 + rows_per_block : f;
+  for (int64_t a = threadIdx.x; a < k; a += blockDim.x) {
+    double s = 0.0;
+    for (int64_t j = j0; j < j1; j++) s += (double)(Ht[j * ld + a] * Nt[j * ld + a]);
+    atomicAdd(&hsum[a], s);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dict_scale_t_kernel(const T *__restrict__ Ht, const T *__restrict__ Nt,
+                                                           T *__restrict__ Htn, int64_t f, int64_t k, int64_t ld,
+                                                           const double *__restrict__ hsum,
+                                                           double *__restrict__ rowsum, const int *stop) {
+  if (*stop != 0) return;
+  const int64_t total = f * k;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t j = i / k, a = i - j * k;
+    double inv = 1.0 / (KL_NORM_EPS + hsum[a]);
+    Htn[j * ld + a] = (T)((double)(Ht[j * ld + a] * Nt[j * ld + a]) * inv);
+    if (j == 0) rowsum[a] = hsum[a] * inv;
+  }
+}
+
+// The reference's stopping test on the device (nmf.py:214-220).  dred = [kl, sum(X.data), colsum(W)...]
+__global__ void decide_kernel(double *dred, double *dscal, int *flags, double *errors, int errors_cap,
+                              const double *rowsumH, int64_t k, int sparse) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  double e = dred[0];
+  if (sparse) {
+    double wh = 0.0;
+    for (int64_t a = 0; a < k; a++) wh += dred[2 + a] * rowsumH[a];
+    e = e - dred[1] + wh;                       // nmf.py:301-308
+  }
+  if (flags[FL_STOP] == 0) {
+    const double prev = dscal[DS_PREV];
+    // DS_WHSUM holds the relative noise slack that applies when tol == 0 (see klnmf_run)
+    const double tol = dscal[DS_TOL] - dscal[DS_WHSUM] * (isfinite(prev) ? fabs(prev) : 0.0);
+    if (prev - e < tol) {
+      flags[FL_STOP] = 1;
+    } else {
+      dscal[DS_PREV] = e;
+      int ne = flags[FL_NERR];
+      if (ne < errors_cap) errors[ne] = e;
+      flags[FL_NERR] = ne + 1;
+    }
+  }
+  dscal[DS_KL] = e;
+  dred[0] = 0.0;
+  dred[1] = dscal[DS_SUMX];
+  for (int64_t a = 0; a < k; a++) dred[2 + a] = 0.0;
+}
+
+__global__ void split_kernel(const float *__restrict__ src, float *__restrict__ hi, float *__restrict__ lo,
+                             int64_t rows, int64_t cols, int64_t ld) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / cols, c = i - r * cols;
+    float v = src[r * ld + c];
+    float h = tf32_hi(v);
+    hi[r * ld + c] = h;
+    lo[r * ld + c] = v - h;
+  }
+}
+
+template <typename S, typename D>
+__global__ void convert_kernel(const S *__restrict__ src, const S *__restrict__ src_lo, int64_t src_ld,
+                               D *__restrict__ dst, int64_t dst_ld, int64_t rows, int64_t cols, int transpose) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / cols, c = i - r * cols;
+    D v = (D)src[r * src_ld + c];
+    if (src_lo) v += (D)src_lo[r * src_ld + c];
+    if (transpose) dst[c * dst_ld + r] = v; else dst[r * dst_ld + c] = v;
+  }
+}
+
+__device__ __forceinline__ uint64_t mix64(uint64_t z) {
+  z += 0x9E3779B97F4A7C15ull;
+  z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+  z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+  return z ^ (z >> 31);
+}
+
+template <typename T>
+__global__ void fill_uniform_kernel(T *__restrict__ p, int64_t rows, int64_t cols, int64_t ld, uint64_t seed,
+                                    int64_t row_offset) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / cols, c = i - r * cols;
+    uint64_t h = mix64(seed ^ mix64((uint64_t)(r + row_offset) * 0x100000001B3ull + (uint64_t)c));
+    // uniform in (0, 1]
+    p[r * ld + c] = (T)(((double)(h >> 11) + 1.0) * (1.0 / 9007199254740992.0));
+  }
+}
+
+template <typename T>
+__global__ void check_kernel(const T *__restrict__ p, int64_t rows, int64_t cols, int64_t ld, int *flags) {
+  const int64_t total = rows * cols;
+  int neg = 0, bad = 0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / cols, c = i - r * cols;
+    T v = p[r * ld + c];
+    neg |= (v < (T)0);
+    bad |= !isfinite((double)v);
+  }
+  if (neg) atomicOr(&flags[FL_NEG], 1);
+  if (bad) atomicOr(&flags[FL_NONFINITE], 1);
+}
+
+// rowsumH[a] = sum_j H[a,j]  (dense layout: one block per row; transposed: strided)
+template <typename T>
+__global__ void __launch_bounds__(256) rowsum_kernel(const T *__restrict__ H, const T *__restrict__ Hlo,
+                                                     int64_t k, int64_t f, int64_t ld, int transposed,
+                                                     double *__restrict__ out) {
+  __shared__ double red[32];
+  const int64_t a = blockIdx.x;
+  double s = 0.0;
+  for (int64_t j = threadIdx.x; j < f; j += blockDim.x) {
+    int64_t off = transposed ? j * ld + a : a * ld + j;
+    T v = H[off];
+    if (Hlo) v += Hlo[off];
+    s += (double)v;
+  }
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) out[a] = s;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) sum_vals_kernel(const T *__restrict__ v, int64_t n, double *out) {
+  __shared__ double red[32];
+  double s = 0.0;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    s += (double)v[i];
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) atomicAdd(out, s);
+}
+
+inline int grid_for(klnmf_ctx *ctx, int64_t total, int threads) {
+  int64_t g = ceil_div(total, threads);
+  int64_t cap = (int64_t)ctx->sm_count * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+}  // namespace
+
+int launch_dict_update(klnmf_ctx *ctx, const void *H_old, void *H_new, void *Hlo_new) {
+  const int cur = ctx->hcur;
+  if (ctx->es == 8) {
+    dict_update_kernel<double><<<(unsigned)ctx->k, 512, 0, ctx->stream>>>(
+        (const double *)H_old, nullptr, (const double *)ctx->num, (double *)H_new, nullptr, ctx->f, ctx->ldh,
+        ctx->rowsumH, ctx->flags + FL_STOP);
+  } else {
+    dict_update_kernel<float><<<(unsigned)ctx->k, 512, 0, ctx->stream>>>(
+        (const float *)H_old, (const float *)ctx->Hlo[cur], (const float *)ctx->num, (float *)H_new,
+        (float *)Hlo_new, ctx->f, ctx->ldh, ctx->rowsumH, ctx->flags + FL_STOP);
+  }
+  ctx->n_launch++;
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
+int launch_dict_update_t(klnmf_ctx *ctx, const void *Ht_old, void *Ht_new) {
+  KL_CUDA(cudaMemsetAsync(ctx->hsum, 0, sizeof(double) * ctx->k, ctx->stream));
+  const int rpb = 64;
+  const unsigned g1 = (unsigned)ceil_div(ctx->f, rpb);
+  const int g2 = grid_for(ctx, ctx->f * ctx->k, 256);
+  if (ctx->es == 8) {
+    dict_colsum_t_kernel<double><<<g1, 256, 0, ctx->stream>>>((const double *)Ht_old, (const double *)ctx->num,
+                                                              ctx->f, ctx->k, ctx->ldh, ctx->hsum, rpb,
+                                                              ctx->flags + FL_STOP);
+    dict_scale_t_kernel<double><<<g2, 256, 0, ctx->stream>>>((const double *)Ht_old, (const double *)ctx->num,
+                                                             (double *)Ht_new, ctx->f, ctx->k, ctx->ldh, ctx->hsum,
+                                                             ctx->rowsumH, ctx->flags + FL_STOP);
+  } else {
+    dict_colsum_t_kernel<float><<<g1, 256, 0, ctx->stream>>>((const float *)Ht_old, (const float *)ctx->num,
+                                                             ctx->f, ctx->k, ctx->ldh, ctx->hsum, rpb,
+                                                             ctx->flags + FL_STOP);
+    dict_scale_t_kernel<float><<<g2, 256, 0, ctx->stream>>>((const float *)Ht_old, (const float *)ctx->num,
+                                                            (float *)Ht_new, ctx->f, ctx->k, ctx->ldh, ctx->hsum,
+                                                            ctx->rowsumH, ctx->flags + FL_STOP);
+  }
+  ctx->n_launch += 2;
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
+int launch_decide(klnmf_ctx *ctx, int /*iter_index*/) {
+  decide_kernel<<<1, 32, 0, ctx->stream>>>(ctx->dred, ctx->dscal, ctx->flags, ctx->errors_dev, ctx->errors_cap,
+                                           ctx->rowsumH, ctx->k, ctx->sparse ? 1 : 0);
+  ctx->n_launch++;
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
+int launch_split(klnmf_ctx *ctx, const float *src, float *hi, float *lo, int64_t rows, int64_t cols, int64_t ld) {
+  if (rows * cols == 0) return KLNMF_OK;
+  split_kernel<<<grid_for(ctx, rows * cols, 256), 256, 0, ctx->stream>>>(src, hi, lo, rows, cols, ld);
+  ctx->n_launch++;
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
+int launch_convert(klnmf_ctx *ctx, const void *src, const void *src_lo, int src_dtype, int64_t src_ld, void *dst,
+                   int dst_es, int64_t dst_ld, int64_t rows, int64_t cols, bool transpose) {
+  if (rows * cols == 0) return KLNMF_OK;
+  const int g = grid_for(ctx, rows * cols, 256);
+  const int t = transpose ? 1 : 0;
+  if (src_dtype == KLNMF_F32 && dst_es == 4)
+    convert_kernel<float, float><<<g, 256, 0, ctx->stream>>>((const float *)src, (const float *)src_lo, src_ld, (float *)dst, dst_ld, rows, cols, t);
+  else if (src_dtype == KLNMF_F32 && dst_es == 8)
+    convert_kernel<float, double><<<g, 256, 0, ctx->stream>>>((const float *)src, (const float *)src_lo, src_ld, (double *)dst, dst_ld, rows, cols, t);
+  else if (src_dtype == KLNMF_F64 && dst_es == 4)
+    convert_kernel<double, float><<<g, 256, 0, ctx->stream>>>((const double *)src, (const double *)src_lo, src_ld, (float *)dst, dst_ld, rows, cols, t);
+  else
+    convert_kernel<double, double><<<g, 256, 0, ctx->stream>>>((const double *)src, (const double *)src_lo, src_ld, (double *)dst, dst_ld, rows, cols, t);
+  ctx->n_launch++;
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
+int launch_zero(klnmf_ctx *ctx, void *p, int64_t bytes) {
+  if (bytes > 0) KL_CUDA(cudaMemsetAsync(p, 0, (size_t)bytes, ctx->stream));
+  return KLNMF_OK;
+}
+
+int launch_fill_uniform(klnmf_ctx *ctx, void *p, int es, int64_t rows, int64_t cols, int64_t ld, uint64_t seed) {
+  if (rows * cols == 0) return KLNMF_OK;
+  const int g = grid_for(ctx, rows * cols, 256);
+  const int64_t row_offset = 0;
+  if (es == 8) fill_uniform_kernel<double><<<g, 256, 0, ctx->stream>>>((double *)p, rows, cols, ld, seed, row_offset);
+  else fill_uniform_kernel<float><<<g, 256, 0, ctx->stream>>>((float *)p, rows, cols, ld, seed, row_offset);
+  ctx->n_launch++;
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
+int launch_check(klnmf_ctx *ctx, const void *p, int es, int64_t rows, int64_t cols, int64_t ld) {
+  if (rows * cols == 0) return KLNMF_OK;
+  const int g = grid_for(ctx, rows * cols, 256);
+  if (es == 8) check_kernel<double><<<g, 256, 0, ctx->stream>>>((const double *)p, rows, cols, ld, ctx->flags);
+  else check_kernel<float><<<g, 256, 0, ctx->stream>>>((const float *)p, rows, cols, ld, ctx->flags);
+  ctx->n_launch++;
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
+int launch_rowsum_h(klnmf_ctx *ctx) {
+  const int cur = ctx->hcur;
+  const int t = ctx->sparse ? 1 : 0;
+  if (ctx->es == 8)
+    rowsum_kernel<double><<<(unsigned)ctx->k, 256, 0, ctx->stream>>>((const double *)ctx->H[cur], nullptr, ctx->k,
+                                                                     ctx->f, ctx->ldh, t, ctx->rowsumH);
+  else
+    rowsum_kernel<float><<<(unsigned)ctx->k, 256, 0, ctx->stream>>>((const float *)ctx->H[cur],
+                                                                    (const float *)ctx->Hlo[cur], ctx->k, ctx->f,
+                                                                    ctx->ldh, t, ctx->rowsumH);
+  ctx->n_launch++;
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
+int launch_sum_vals(klnmf_ctx *ctx) {
+  KL_CUDA(cudaMemsetAsync(ctx->dscal + DS_SUMX, 0, sizeof(double), ctx->stream));
+  if (ctx->nnz > 0) {
+    const int g = grid_for(ctx, ctx->nnz, 256);
+    if (ctx->es == 8) sum_vals_kernel<double><<<g, 256, 0, ctx->stream>>>((const double *)ctx->vals, ctx->nnz, ctx->dscal + DS_SUMX);
+    else sum_vals_kernel<float><<<g, 256, 0, ctx->stream>>>((const float *)ctx->vals, ctx->nnz, ctx->dscal + DS_SUMX);
+    ctx->n_launch++;
+  }
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
+}  // namespace klnmf

@@ -1,0 +1,326 @@
+// Sparse (CSR bag-of-features) path of one reference iteration.
+//   pass 1, one warp per sample row i (nmf.py:52-70, 297-310, 325-343):
+//        s_p = W[i,:] . H[:,j_p]           SDDMM at the stored non-zeros
+//        q_p = (x_p+eps)/(s_p+eps)         ratio, only where X is stored (structural zeros stay zero)
+//        kl += x_p log q_p ;  G[i,:] += q_p H[:,j_p]^T ;  W'[i,:] = W[i,:] (.) G[i,:]
+//   pass 2, one warp per row (nmf.py:345-349):  N[:,j_p] += q_p W'[i,:]   (vector red.add into L2)
+// The dictionary is kept TRANSPOSED (Ht: f x k) so that each non-zero gathers / scatters one
+// contiguous k-vector (coalesced 128-bit accesses).
+#include "common.cuh"
+
+namespace klnmf {
+
+namespace {
+
+constexpr int WARPS = 8;
+
+template <typename T> struct Vec4;
+template <> struct Vec4<float> { typedef float4 type; };
+template <> struct Vec4<double> { typedef double4 type; };
+
+template <typename T>
+__device__ __forceinline__ void ld4(const T *p, T v[4]) {
+  if (sizeof(T) == 4) {
+    float4 t = *reinterpret_cast<const float4 *>(p);
+    v[0] = (T)t.x; v[1] = (T)t.y; v[2] = (T)t.z; v[3] = (T)t.w;
+  } else {
+    double2 t0 = *reinterpret_cast<const double2 *>(p);
+    double2 t1 = *reinterpret_cast<const double2 *>(p + 2);
+    v[0] = (T)t0.x; v[1] = (T)t0.y; v[2] = (T)t1.x; v[3] = (T)t1.y;
+  }
+}
+template <typename T>
+__device__ __forceinline__ void st4(T *p, const T v[4]) {
+  if (sizeof(T) == 4) {
+    *reinterpret_cast<float4 *>(p) = make_float4((float)v[0], (float)v[1], (float)v[2], (float)v[3]);
+  } else {
+    *reinterpret_cast<double2 *>(p) = make_double2((double)v[0], (double)v[1]);
+    *reinterpret_cast<double2 *>(p + 2) = make_double2((double)v[2], (double)v[3]);
+  }
+}
+__device__ __forceinline__ void red4(float *p, const float v[4]) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(v[0]), "f"(v[1]), "f"(v[2]),
+               "f"(v[3])
+               : "memory");
+}
+__device__ __forceinline__ void red4(double *p, const double v[4]) {
+#pragma unroll
+  for (int e = 0; e < 4; e++) atomicAdd(p + e, v[e]);
+}
+
+template <typename T>
+__device__ __forceinline__ T warp_sum(T v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// lane owns the k-elements { 128*c + 4*lane + e : c < VPL, e < 4 } (zero padded up to ld)
+// MODE 0: full pass 1;  MODE 1: objective only;  MODE 2: W0 = X . H0^T (nmf.py:156);
+// MODE 3: SDDMM only, qnz <- (W.H) at the non-zeros (nmf.py:52-70)
+template <typename T, int VPL, int MODE>
+__global__ void __launch_bounds__(WARPS * 32)
+sparse_rows_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                   const T *__restrict__ vals, const T *__restrict__ W, int64_t ldw, const T *__restrict__ Ht,
+                   int64_t ldh, T *__restrict__ Wn, T *__restrict__ qnz, int64_t n, double *__restrict__ dred,
+                   const int *stop) {
+  if (stop != nullptr && *stop != 0) return;
+  __shared__ double red[WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t warp_global = (int64_t)blockIdx.x * WARPS + warp;
+  const int64_t n_warps = (int64_t)gridDim.x * WARPS;
+  bool act[VPL];
+#pragma unroll
+  for (int c = 0; c < VPL; c++) act[c] = (128 * c + 4 * lane) < ldh && (128 * c + 4 * lane) < ldw;
+
+  double kl = 0.0;
+  double cs[VPL][4];
+#pragma unroll
+  for (int c = 0; c < VPL; c++)
+#pragma unroll
+    for (int e = 0; e < 4; e++) cs[c][e] = 0.0;
+
+  for (int64_t i = warp_global; i < n; i += n_warps) {
+    T w[VPL][4], g[VPL][4];
+#pragma unroll
+    for (int c = 0; c < VPL; c++) {
+#pragma unroll
+      for (int e = 0; e < 4; e++) { w[c][e] = (T)0; g[c][e] = (T)0; }
+      if (MODE != 2 && act[c]) ld4(W + i * ldw + 128 * c + 4 * lane, w[c]);
+      if (MODE != 2) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) cs[c][e] += (double)w[c][e];
+      }
+    }
+    const int64_t p0 = indptr[i], p1 = indptr[i + 1];
+    for (int64_t p = p0; p < p1; p += 2) {
+      const bool two = (p + 1 < p1);
+      const int32_t ja = indices[p], jb = two ? indices[p + 1] : ja;
+      const T xa = vals[p], xb = two ? vals[p + 1] : (T)0;
+      T ha[VPL][4], hb[VPL][4];
+      T sa = (T)0, sb = (T)0;
+#pragma unroll
+      for (int c = 0; c < VPL; c++) {
+#pragma unroll
+        for (int e = 0; e < 4; e++) { ha[c][e] = (T)0; hb[c][e] = (T)0; }
+        if (act[c]) {
+          ld4(Ht + (int64_t)ja * ldh + 128 * c + 4 * lane, ha[c]);
+          ld4(Ht + (int64_t)jb * ldh + 128 * c + 4 * lane, hb[c]);
+        }
+      }
+      if (MODE == 2) {
+#pragma unroll
+        for (int c = 0; c < VPL; c++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) g[c][e] += xa * ha[c][e] + xb * hb[c][e];
+        continue;
+      }
+#pragma unroll
+      for (int c = 0; c < VPL; c++)
+#pragma unroll
+        for (int e = 0; e < 4; e++) { sa += w[c][e] * ha[c][e]; sb += w[c][e] * hb[c][e]; }
+      sa = warp_sum(sa);
+      sb = warp_sum(sb);
+      const T qa = (xa + (T)KL_EPS) / (sa + (T)KL_EPS);
+      const T qb = two ? (xb + (T)KL_EPS) / (sb + (T)KL_EPS) : (T)0;
+      if (lane == 0) {
+        kl += (double)xa * log((double)qa);
+        if (two) kl += (double)xb * log((double)qb);
+        if (MODE == 0) {
+          qnz[p] = qa;
+          if (two) qnz[p + 1] = qb;
+        }
+        if (MODE == 3) {
+          qnz[p] = sa;
+          if (two) qnz[p + 1] = sb;
+        }
+      }
+      if (MODE == 0) {
+#pragma unroll
+        for (int c = 0; c < VPL; c++)
+#pragma unroll
+          for (int e = 0; e < 4; e++) g[c][e] += qa * ha[c][e] + qb * hb[c][e];
+      }
+    }
+    if (MODE == 0 || MODE == 2) {
+#pragma unroll
+      for (int c = 0; c < VPL; c++) {
+        if (MODE == 0) {
+#pragma unroll
+          for (int e = 0; e < 4; e++) g[c][e] *= w[c][e];
+        }
+        if (act[c]) st4(Wn + i * ldw + 128 * c + 4 * lane, g[c]);
+      }
+    }
+  }
+  if (MODE == 2) return;
+  // colsum(W) for the sparse objective's sum_k colsum(W)_k rowsum(H)_k term (nmf.py:304)
+#pragma unroll
+  for (int c = 0; c < VPL; c++)
+    if (act[c]) {
+#pragma unroll
+      for (int e = 0; e < 4; e++) atomicAdd(&dred[2 + 128 * c + 4 * lane + e], cs[c][e]);
+    }
+  if (lane == 0) red[warp] = kl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double s = 0.0;
+    for (int w = 0; w < WARPS; w++) s += red[w];
+    atomicAdd(&dred[0], s);
+  }
+}
+
+template <typename T, int VPL>
+__global__ void __launch_bounds__(WARPS * 32)
+sparse_scatter_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                      const T *__restrict__ qnz, const T *__restrict__ Wn, int64_t ldw, T *__restrict__ Nt,
+                      int64_t ldh, int64_t n, const int *stop) {
+  if (*stop != 0) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t warp_global = (int64_t)blockIdx.x * WARPS + warp;
+  const int64_t n_warps = (int64_t)gridDim.x * WARPS;
+  bool act[VPL];
+#pragma unroll
+  for (int c = 0; c < VPL; c++) act[c] = (128 * c + 4 * lane) < ldh && (128 * c + 4 * lane) < ldw;
+  for (int64_t i = warp_global; i < n; i += n_warps) {
+    T w[VPL][4];
+#pragma unroll
+    for (int c = 0; c < VPL; c++) {
+#pragma unroll
+      for (int e = 0; e < 4; e++) w[c][e] = (T)0;
+      if (act[c]) ld4(Wn + i * ldw + 128 * c + 4 * lane, w[c]);
+    }
+    const int64_t p0 = indptr[i], p1 = indptr[i + 1];
+    for (int64_t p = p0; p < p1; p++) {
+      const int32_t j = indices[p];
+      const T q = qnz[p];
+#pragma unroll
+      for (int c = 0; c < VPL; c++)
+        if (act[c]) {
+          T v[4];
+#pragma unroll
+          for (int e = 0; e < 4; e++) v[e] = q * w[c][e];
+          red4(Nt + (int64_t)j * ldh + 128 * c + 4 * lane, v);
+        }
+    }
+  }
+}
+
+template <typename T>
+__global__ void fill_csr_kernel(int64_t *__restrict__ indptr, int32_t *__restrict__ indices, T *__restrict__ vals,
+                                int64_t n, int64_t f, int64_t m, uint64_t seed) {
+  const int64_t total = n * m;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (int64_t)gridDim.x * blockDim.x) {
+    int64_t r = i / m, t = i - r * m;
+    uint64_t z = seed ^ ((uint64_t)i * 0x9E3779B97F4A7C15ull);
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    z ^= z >> 31;
+    // stratified: the t-th non-zero of a row falls in the t-th of m equal column strata -> sorted, distinct
+    int64_t lo = t * f / m, hi = (t + 1) * f / m;
+    indices[i] = (int32_t)(lo + (int64_t)(z % (uint64_t)(hi - lo)));
+    vals[i] = (T)(((double)(z >> 11) + 1.0) * (1.0 / 9007199254740992.0));
+    if (t == 0) indptr[r] = r * m;
+    if (i == total - 1) indptr[n] = total;
+  }
+}
+
+template <typename T, int VPL>
+int run_rows(klnmf_ctx *ctx, int mode, const T *W, T *Wn) {
+  const int grid = (int)(ceil_div(ctx->n, WARPS) < (int64_t)ctx->sm_count * 8 ? ceil_div(ctx->n, WARPS)
+                                                                               : (int64_t)ctx->sm_count * 8);
+  const int *stop = ctx->flags + FL_STOP;
+  const T *Ht = (const T *)ctx->H[ctx->hcur];
+  if (mode == 0)
+    sparse_rows_kernel<T, VPL, 0><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->indptr, ctx->indices, (const T *)ctx->vals, W,
+                                                                        ctx->ldw, Ht, ctx->ldh, Wn, (T *)ctx->qnz, ctx->n,
+                                                                        ctx->dred, stop);
+  else if (mode == 1)
+    sparse_rows_kernel<T, VPL, 1><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->indptr, ctx->indices, (const T *)ctx->vals, W,
+                                                                        ctx->ldw, Ht, ctx->ldh, nullptr, nullptr, ctx->n,
+                                                                        ctx->dred, nullptr);
+  else if (mode == 3)
+    sparse_rows_kernel<T, VPL, 3><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->indptr, ctx->indices, (const T *)ctx->vals, W,
+                                                                        ctx->ldw, Ht, ctx->ldh, nullptr, (T *)ctx->qnz, ctx->n,
+                                                                        ctx->dred, nullptr);
+  else
+    sparse_rows_kernel<T, VPL, 2><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->indptr, ctx->indices, (const T *)ctx->vals,
+                                                                        nullptr, ctx->ldw, Ht, ctx->ldh, Wn, nullptr, ctx->n,
+                                                                        nullptr, nullptr);
+  ctx->n_launch++;
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
+template <typename T, int VPL>
+int run_scatter(klnmf_ctx *ctx, const T *Wn) {
+  const int grid = (int)(ceil_div(ctx->n, WARPS) < (int64_t)ctx->sm_count * 8 ? ceil_div(ctx->n, WARPS)
+                                                                               : (int64_t)ctx->sm_count * 8);
+  sparse_scatter_kernel<T, VPL><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->indptr, ctx->indices, (const T *)ctx->qnz, Wn,
+                                                                      ctx->ldw, (T *)ctx->num, ctx->ldh, ctx->n,
+                                                                      ctx->flags + FL_STOP);
+  ctx->n_launch++;
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
+template <typename T>
+int dispatch_rows(klnmf_ctx *ctx, int mode, const T *W, T *Wn) {
+  const int64_t kp = ctx->ldw;
+  if (kp <= 128) return run_rows<T, 1>(ctx, mode, W, Wn);
+  if (kp <= 256) return run_rows<T, 2>(ctx, mode, W, Wn);
+  if (kp <= 512) return run_rows<T, 4>(ctx, mode, W, Wn);
+  if (kp <= 1024) return run_rows<T, 8>(ctx, mode, W, Wn);
+  set_error("sparse path supports n_components <= 1024 (got %lld)", (long long)ctx->k);
+  return KLNMF_EINVAL;
+}
+template <typename T>
+int dispatch_scatter(klnmf_ctx *ctx, const T *Wn) {
+  const int64_t kp = ctx->ldw;
+  if (kp <= 128) return run_scatter<T, 1>(ctx, Wn);
+  if (kp <= 256) return run_scatter<T, 2>(ctx, Wn);
+  if (kp <= 512) return run_scatter<T, 4>(ctx, Wn);
+  if (kp <= 1024) return run_scatter<T, 8>(ctx, Wn);
+  set_error("sparse path supports n_components <= 1024 (got %lld)", (long long)ctx->k);
+  return KLNMF_EINVAL;
+}
+
+}  // namespace
+
+// Pass 1 of the sparse iteration (SDDMM -> ratio -> objective -> SpMM -> W update), or with
+// only_error just the objective terms.
+int sparse_rows(klnmf_ctx *ctx, int mode) {
+  const int cur = ctx->cur;
+  return ctx->es == 8 ? dispatch_rows<double>(ctx, mode, (const double *)ctx->W[cur], (double *)ctx->W[cur ^ 1])
+                      : dispatch_rows<float>(ctx, mode, (const float *)ctx->W[cur], (float *)ctx->W[cur ^ 1]);
+}
+
+// Pass 2: dictionary numerator N^T[j,:] += q W'[i,:] over the stored non-zeros.
+int sparse_scatter(klnmf_ctx *ctx, bool use_current_w) {
+  const int w = use_current_w ? ctx->cur : ctx->cur ^ 1;
+  return ctx->es == 8 ? dispatch_scatter<double>(ctx, (const double *)ctx->W[w])
+                      : dispatch_scatter<float>(ctx, (const float *)ctx->W[w]);
+}
+
+int sparse_init_w(klnmf_ctx *ctx) {
+  return ctx->es == 8 ? dispatch_rows<double>(ctx, 2, nullptr, (double *)ctx->W[ctx->cur])
+                      : dispatch_rows<float>(ctx, 2, nullptr, (float *)ctx->W[ctx->cur]);
+}
+
+int sparse_fill_synthetic(klnmf_ctx *ctx, int64_t m, uint64_t seed) {
+  const int64_t total = ctx->n * m;
+  int64_t g = ceil_div(total, 256);
+  if (g > (int64_t)ctx->sm_count * 32) g = (int64_t)ctx->sm_count * 32;
+  if (ctx->es == 8)
+    fill_csr_kernel<double><<<(unsigned)g, 256, 0, ctx->stream>>>(ctx->indptr, ctx->indices, (double *)ctx->vals, ctx->n,
+                                                                  ctx->f, m, seed);
+  else
+    fill_csr_kernel<float><<<(unsigned)g, 256, 0, ctx->stream>>>(ctx->indptr, ctx->indices, (float *)ctx->vals, ctx->n,
+                                                                 ctx->f, m, seed);
+  ctx->n_launch++;
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
+}  // namespace klnmf

@@ -1,0 +1,166 @@
+"""-m gpu: the CUDA path (through the drop-in Python API -> C ABI) against the golden vectors
+produced by the real reference and against the float64 oracle on the same seeds.
+
+Stated tolerances (norm-relative on W, H after 10 iterations; relative on the KL objective):
+    fp64    1e-9            DMMA float64, only the summation order differs
+    tf32x3  2e-5 / 2e-5     split-TF32 contractions are FP32-grade (measured ~1e-7 in emulation)
+    tf32    3e-3 / 1e-2     one-pass TF32 (measured 1.5e-4 / 3e-3 in emulation)
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from multimodal_b200.lib.nmf import KLdivNMF
+from multimodal_b200.learner import MultimodalLearner, fit_coefficients
+from oracle import cases
+from oracle import klnmf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+MODES = ["fp64", "tf32x3", "tf32"]
+TOL_WH = {"fp64": 1e-9, "tf32x3": 2e-5, "tf32": 3e-3}
+TOL_KL = {"fp64": 1e-9, "tf32x3": 2e-5, "tf32": 1e-2}
+
+
+def fit(X, k, iters, seed, mode, tol=0, **kw):
+    est = KLdivNMF(n_components=k, max_iter=iters, tol=tol, mode=mode)
+    np.random.seed(seed)
+    W, errs = est.fit_transform(X, return_errors=True, **kw)
+    return est, W, np.asarray(errs)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_kat_dense(golden, mode):
+    g = golden("kat_dense")
+    est, W, errs = fit(cases.kat_dense(), 2, 10, 0, mode)
+    assert cases.rel_fro(W, g["W"]) < TOL_WH[mode]
+    assert cases.rel_fro(est.components_, g["H"]) < TOL_WH[mode]
+    np.testing.assert_allclose(errs, g["errors"], rtol=TOL_KL[mode] * 10)
+    np.testing.assert_allclose(est.error(cases.kat_dense(), W), g["after"], rtol=TOL_KL[mode] * 10)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_kat_csr(golden, mode):
+    g = golden("kat_csr")
+    est, W, errs = fit(cases.kat_csr(), 2, 10, 0, mode)
+    tol = 1e-9 if mode == "fp64" else 2e-5        # the sparse path is FP32 FMA in both TF32 modes
+    assert cases.rel_fro(W, g["W"]) < tol and cases.rel_fro(est.components_, g["H"]) < tol
+    np.testing.assert_allclose(errs, g["errors"], rtol=tol)
+    # and the dense path on the same matrix is the reference's OTHER algorithm (eps at X == 0)
+    est, W, errs = fit(cases.kat_csr().toarray(), 2, 10, 0, mode)
+    np.testing.assert_allclose(errs, g["errors_densepath"], rtol=TOL_KL[mode] * 10)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name,maker,k,seed,long_iters", [
+    ("cfg1_dense", cases.cfg1_X, 10, 1, 200),
+    ("ragged_dense", cases.ragged_dense_X, 13, 5, 200),
+    ("zeros_dense", cases.zeros_dense_X, 8, 7, 60),
+])
+def test_dense_fit_golden(golden, mode, name, maker, k, seed, long_iters):
+    g = golden(name)
+    est, W, errs = fit(maker(), k, 10, seed, mode)
+    assert W.dtype == np.float64 and W.flags.c_contiguous and W.shape == g["W10"].shape
+    assert len(errs) == 10
+    assert cases.rel_fro(W, g["W10"]) < TOL_WH[mode]
+    assert cases.rel_fro(est.components_, g["H10"]) < TOL_WH[mode]
+    np.testing.assert_allclose(errs, g["errors10"], rtol=TOL_KL[mode])
+    est, W, errs = fit(maker(), k, long_iters, seed, mode)
+    assert len(errs) == long_iters
+    assert abs(errs[-1] - g["errors_long"][-1]) <= TOL_KL[mode] * abs(g["errors_long"][-1])
+    final = est.error(maker(), W)
+    assert abs(final - g["final_error"]) <= TOL_KL[mode] * abs(g["final_error"])
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_sparse_fit_golden(golden, mode):
+    g = golden("sparse_mid")
+    tol = 1e-9 if mode == "fp64" else 2e-5
+    est, W, errs = fit(cases.sparse_mid_X(), 16, 10, 11, mode)
+    assert cases.rel_fro(W, g["W10"]) < tol and cases.rel_fro(est.components_, g["H10"]) < tol
+    np.testing.assert_allclose(errs, g["errors10"], rtol=tol)
+    est, W, errs = fit(cases.sparse_mid_X(), 16, 200, 11, mode)
+    assert abs(errs[-1] - g["errors_long"][-1]) <= 10 * tol * abs(g["errors_long"][-1])
+    assert abs(est.error(cases.sparse_mid_X(), W) - g["final_error"]) <= 10 * tol * abs(g["final_error"])
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_transform_golden(golden, mode):
+    H0 = cases.sub_dictionary(10, 200)
+    est = KLdivNMF(n_components=10, max_iter=30, tol=0, mode=mode)
+    est.components_ = H0
+    np.random.seed(0)
+    W = est.transform(cases.cfg1_X()[:64])
+    assert est.components_ is H0 and est._init_dictionary is H0      # untouched + sticky (nmf.py:289)
+    assert cases.rel_fro(W, golden("transform_dense")["W"]) < TOL_WH[mode]
+    Xs = cases.sparse_mid_X()[:50]
+    W = fit_coefficients(Xs, cases.sub_dictionary(16, Xs.shape[1]), iter_nmf=30, mode=mode)
+    assert cases.rel_fro(W, golden("transform_sparse")["W"]) < (1e-9 if mode == "fp64" else 2e-5)
+
+
+@pytest.mark.parametrize("mode", ["fp64", "tf32x3"])
+def test_early_stop_golden(golden, mode, capsys):
+    g = golden("early_stop")
+    est, W, errs = fit(cases.cfg1_X()[:120, :60], 6, 500, 2, mode, tol=1e-5)
+    if mode == "fp64":
+        assert len(errs) == len(g["errors"])          # stops at the same iteration as the reference
+        assert cases.rel_fro(W, g["W"]) < 1e-8 and cases.rel_fro(est.components_, g["H"]) < 1e-8
+    else:
+        assert abs(len(errs) - len(g["errors"])) <= 25
+        assert cases.rel_fro(W, g["W"]) < 2e-2
+    assert "Iteration limit" not in capsys.readouterr().err
+    # and the warning text when the limit IS reached with tol > 0 (nmf.py:224-225)
+    fit(cases.cfg1_X()[:120, :60], 6, 5, 2, mode, tol=1e-5)
+    assert "Warning: Iteration limit reached during fit\n" in capsys.readouterr().err
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_learner_golden(golden, mode):
+    g = golden("learner_small")
+    tol = 1e-9 if mode == "fp64" else 5e-5
+    mot, snd, coefs = cases.learner_small()
+    lr = MultimodalLearner(['motion', 'sound'], [mot.shape[1], snd.shape[1]], coefs, 8, mode=mode)
+    np.random.seed(3)
+    lr.train([mot, snd.copy()], 20)
+    assert lr.dico.shape == g["dico"].shape and cases.rel_fro(lr.dico, g["dico"]) < tol
+    assert cases.rel_fro(lr.reconstruct_internal('sound', snd[:25].copy(), 15), g["internal_sound"]) < tol
+    # a dense-only sub-problem goes through the dense engine of the mode
+    assert cases.rel_fro(lr.reconstruct_internal('motion', mot[:25], 15), g["internal_motion"]) < max(tol, TOL_WH[mode])
+    m2s = lr.modality_to_modality('motion', 'sound', mot[:25], 15)
+    assert m2s.shape == g["motion_to_sound"].shape
+    assert cases.rel_fro(m2s, g["motion_to_sound"]) < max(tol, TOL_WH[mode])
+    both = lr.reconstruct_internal_multi(['motion', 'sound'], [mot[:25], snd[:25].copy()], 15)
+    assert cases.rel_fro(both, g["internal_both"]) < tol
+    with pytest.raises(AssertionError):
+        lr.reconstruct_internal('sound', mot[:25], 5)          # wrong width (learner.py:73)
+
+
+@pytest.mark.parametrize("mode", ["tf32x3", "tf32"])
+def test_mid_size_dense_vs_oracle(mode):
+    """cfg3/cfg5-like tile shapes (f, k multiples of the MMA tile) on a row subsample."""
+    rs = np.random.RandomState(5)
+    n, f, k = 1000, 1024, 256
+    X = rs.gamma(0.5, 1.0, size=(n, f))
+    np.random.seed(9)
+    Wr, Hr, er, _ = O.fit_transform(X, k=k, max_iter=10, tol=0)
+    est, W, errs = fit(X, k, 10, 9, mode)
+    assert cases.rel_fro(W, Wr) < TOL_WH[mode] and cases.rel_fro(est.components_, Hr) < TOL_WH[mode]
+    np.testing.assert_allclose(errs, er, rtol=TOL_KL[mode])
+
+
+def test_multi_panel_equals_single_panel():
+    """Row panels (the ratio scratch) must not change the result."""
+    from multimodal_b200 import _native
+    X = cases.ragged_dense_X()
+    np.random.seed(5)
+    H0 = O.init_dictionary(13, X.shape[1])
+    outs = []
+    for limit in (None, 128 * 160 * 8):          # second run: 128-row panels
+        with _native.Engine(X.shape[0], X.shape[1], 13, mode="fp64", scratch_limit=limit) as e:
+            e.set_dense(X)
+            e.set_dictionary(H0)
+            e.init_coefficients()
+            errs, _ = e.run(5, 0.0, True)
+            outs.append((e.get_coefficients(), e.get_dictionary(), errs))
+    assert cases.rel_fro(outs[1][0], outs[0][0]) < 1e-12 and cases.rel_fro(outs[1][1], outs[0][1]) < 1e-12
+    np.testing.assert_allclose(outs[1][2], outs[0][2], rtol=1e-12)

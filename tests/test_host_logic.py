@@ -1,0 +1,108 @@
+"""Host-side logic: the reference-API helpers and the world_size-2 sharding plumbing (gloo)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from multimodal_b200 import distributed as D
+from multimodal_b200.lib import nmf as M
+from multimodal_b200.lib.array_utils import normalize_sum, safe_hstack
+from multimodal_b200.lib.metrics import generalized_KL
+from multimodal_b200.lib.sklearn_utils import atleast2d_or_csr
+from oracle import cases
+from oracle import klnmf_oracle as O
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_shard_bounds():
+    assert D.shard_bounds(10, 3) == [0, 4, 7, 10] == O.row_partition(10, 3)
+    assert D.shard_bounds(4_000_000, 8)[-1] == 4_000_000
+    assert D.shard_bounds(2, 4) == [0, 1, 2, 2, 2]
+
+
+def test_reference_helpers_known_answers():
+    # reference tests/test_array_utils.py:31-41, tests/test_metrics.py:48-54, tests/test_nmf_kl.py:25-68
+    a = np.array([[0., 1., 3.], [2., 3., 3.]])
+    assert np.all(normalize_sum(a, axis=1) == np.array([[0., .25, .75], [.25, .375, .375]]))
+    x = np.zeros((4, 2)); x[1, 1] = 1
+    np.testing.assert_array_almost_equal(generalized_KL(x, .5 * np.ones((4, 2))), np.log(2.) + 3.)
+    m = np.array([[1, 2, 3], [4, 5, 6]])
+    np.testing.assert_array_almost_equal(M._scale(m, np.array([2, 3]), axis=1), [[2, 4, 6], [12, 15, 18]])
+    for bad in [lambda: M._scale(np.zeros((3, 4)), np.zeros(4), axis=3),
+                lambda: M._scale(np.zeros((3, 4, 6)), np.zeros(3), axis=1),
+                lambda: M._scale(np.zeros((3,)), np.zeros(3), axis=1),
+                lambda: M._scale(np.zeros((3, 4)), np.zeros(2), axis=1)]:
+        with pytest.raises(ValueError):
+            bad()
+    with pytest.raises(ValueError):
+        M.check_non_negative(np.array([1., -2.]), "NMF.fit")
+    assert sp.issparse(safe_hstack([np.ones((2, 2)), sp.csr_matrix(np.ones((2, 3)))]))
+    assert atleast2d_or_csr(np.matrix([[1., 2.]])).__class__ is np.ndarray
+    with pytest.raises(ValueError):
+        atleast2d_or_csr(np.array([[np.inf, 1.]]))
+
+
+def test_estimator_constructor_matches_reference_defaults():
+    e = M.KLdivNMF()
+    assert (e.n_components, e.tol, e.max_iter, e.eps, e.subit, e.random_state) == (None, 1e-6, 200, 1e-8, 10, None)
+    assert e._init_dictionary is None
+    s_W, s_H = M.KLdivNMF(eps=0.).scale(np.ones((2, 3)), np.ones((3, 4)), np.array([1., 2., 4.]))
+    assert np.allclose(s_W[0], [1, 2, 4]) and np.allclose(s_H[:, 0], [1, .5, .25])
+
+
+# ---- world_size 2 over gloo --------------------------------------------------------------------
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out_dir):
+    sys.path.insert(0, ROOT)
+    import torch.distributed as dist
+    import torch
+    from multimodal_b200 import _native, distributed as DD
+    from oracle import cases as C, klnmf_oracle as OO
+    dist.init_process_group("gloo", init_method="tcp://127.0.0.1:%d" % port, rank=rank, world_size=world)
+    # (1) the 128-byte NCCL id travels from rank 0 (NCCL itself is not needed for the plumbing)
+    _native.nccl_unique_id = lambda *a: bytes((7 * i) % 251 for i in range(128))
+    uid = DD.broadcast_unique_id()
+    # (2) every rank gets rank 0's host-drawn H0
+    np.random.seed(100 + rank)
+    H0 = DD.draw_shared_dictionary(6, 200)
+    # (3) one sharded fit iteration == the unsharded oracle iteration
+    X = C.cfg1_X()[:97]
+    b = DD.shard_bounds(X.shape[0], world)
+    Xs = X[b[rank]:b[rank + 1]]
+    Ws = Xs.dot(H0.T)
+
+    def allreduce(a):
+        t = torch.from_numpy(np.ascontiguousarray(a))
+        dist.all_reduce(t)
+        return t.numpy()
+
+    Wn, Hn = OO.sharded_update([Xs], [Ws], H0, allreduce=allreduce)
+    np.savez(os.path.join(out_dir, "r%d.npz" % rank), uid=np.frombuffer(uid, dtype=np.uint8), H0=H0, W=Wn[0], H=Hn)
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_over_gloo(tmp_path):
+    import torch.multiprocessing as mp
+    port = _free_port()
+    mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+    r0, r1 = np.load(tmp_path / "r0.npz"), np.load(tmp_path / "r1.npz")
+    assert np.array_equal(r0["uid"], r1["uid"]) and len(r0["uid"]) == 128
+    assert np.array_equal(r0["H0"], r1["H0"])
+    np.random.seed(100)
+    assert np.array_equal(r0["H0"], O.init_dictionary(6, 200))          # bit-identical with nmf.py:150-151
+    X = cases.cfg1_X()[:97]
+    Wref, Href = O.update(X, X.dot(r0["H0"].T), r0["H0"])
+    assert cases.rel_fro(np.vstack([r0["W"], r1["W"]]), Wref) < 1e-14
+    assert cases.rel_fro(r0["H"], Href) < 1e-13 and np.array_equal(r0["H"], r1["H"])
