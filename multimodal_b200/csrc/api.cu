@@ -124,6 +124,7 @@ int kind_guard(klnmf_ctx *ctx, bool sparse) {
   KL_CHECK(!ctx->W[0] || ctx->sparse == sparse, KLNMF_ESTATE,
            "a context serves either dense or CSR data for its whole life; create a new one");
   ctx->sparse = sparse;
+  if (sparse) ctx->split = false;   // the CSR path is FP32 FMA: no (hi, lo) operand pairs
   return KLNMF_OK;
 }
 

@@ -41,6 +41,7 @@ struct TcParams {
   double *kl;
   const int *stop;
   int *err;
+  uint32_t mn_lt, mn_lbo, mn_sbo, mn_kadv;   // MN-major descriptor parameters (bring-up overridable)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -137,17 +138,19 @@ __device__ __forceinline__ float tf32_round(float v) {
   return __uint_as_float(u);
 }
 
-// Shared-memory matrix descriptor (sm_100 UMMA), 128-byte swizzle.
-//   K-major : rows of 128 B (32 floats of K), 8-row groups SBO = 1024 B apart
-//   MN-major: rows of 128 B (32 floats of M/N), one row per K index; 8-row K groups SBO = 1024 B
-//             apart, 32-wide M/N groups LBO bytes apart
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+// Shared-memory matrix descriptor (sm_100 UMMA).
+//   K-major : SWIZZLE_128B (type 2, 16-byte swizzle atoms): rows of 128 B (32 floats of K),
+//             8-row groups SBO = 1024 B apart.
+//   MN-major: 32-bit operands only exist as SWIZZLE_128B_BASE32B (type 1, 32-byte swizzle atoms,
+//             TMA mode 128B_ATOM_32B): rows of 128 B (32 floats of M/N), one row per K index;
+//             4-row K groups SBO = 512 B apart, 32-wide M/N groups LBO bytes apart.
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout_type) {
   uint64_t d = 0;
   d |= (uint64_t)((saddr >> 4) & 0x3FFF);
   d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
   d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
   d |= (uint64_t)1 << 46;   // descriptor version (Blackwell)
-  d |= (uint64_t)2 << 61;   // SWIZZLE_128B
+  d |= (uint64_t)layout_type << 61;
   return d;
 }
 
@@ -369,15 +372,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
           for (int kk = 0; kk < BK / UMMA_K; kk++) {
             // K-major: +32 B inside the 128 B swizzle row; MN-major: next 8-row group (+1024 B)
-            const uint32_t a_off = A_MN ? kk * 1024u : kk * 32u;
-            const uint32_t b_off = B_MN ? kk * 1024u : kk * 32u;
-            const uint32_t a_lbo = A_MN ? 4096u : 16u, b_lbo = B_MN ? 4096u : 16u;
-            const uint64_t da = make_desc(sA + a_off, a_lbo, 1024u);
-            const uint64_t db = make_desc(sB + b_off, b_lbo, 1024u);
+            const uint32_t a_off = A_MN ? kk * p.mn_kadv : kk * 32u;
+            const uint32_t b_off = B_MN ? kk * p.mn_kadv : kk * 32u;
+            const uint32_t a_lbo = A_MN ? p.mn_lbo : 16u, b_lbo = B_MN ? p.mn_lbo : 16u;
+            const uint32_t a_sbo = A_MN ? p.mn_sbo : 1024u, b_sbo = B_MN ? p.mn_sbo : 1024u;
+            const uint32_t a_lt = A_MN ? p.mn_lt : 2u, b_lt = B_MN ? p.mn_lt : 2u;
+            const uint64_t da = make_desc(sA + a_off, a_lbo, a_sbo, a_lt);
+            const uint64_t db = make_desc(sB + b_off, b_lbo, b_sbo, b_lt);
             const uint32_t first = (kb > kb0 || kk > 0) ? 1u : 0u;
             if (SPLIT) {
-              const uint64_t dal = make_desc(sAlo + a_off, a_lbo, 1024u);
-              const uint64_t dbl = make_desc(sBlo + b_off, b_lbo, 1024u);
+              const uint64_t dal = make_desc(sAlo + a_off, a_lbo, a_sbo, a_lt);
+              const uint64_t dbl = make_desc(sBlo + b_off, b_lbo, b_sbo, b_lt);
               umma_tf32(d_tmem, dal, db, idesc, first);   // lo*hi
               umma_tf32(d_tmem, da, dbl, idesc, 1u);      // hi*lo
               umma_tf32(d_tmem, da, db, idesc, 1u);       // hi*hi
@@ -453,7 +458,7 @@ EncodeTiledFn get_encode() {
 }
 
 // 2D fp32 tensor map: inner (contiguous) extent `inner`, `outer` rows `ld` elements apart; box = 32 x box_rows.
-int make_map(CUtensorMap *map, const void *base, int64_t inner, int64_t outer, int64_t ld, int box_rows) {
+int make_map(CUtensorMap *map, const void *base, int64_t inner, int64_t outer, int64_t ld, int box_rows, bool mn_major) {
   EncodeTiledFn enc = get_encode();
   KL_CHECK(enc != nullptr, KLNMF_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
   KL_CHECK(((uintptr_t)base % 16) == 0 && (ld * 4) % 16 == 0, KLNMF_EINVAL,
@@ -462,8 +467,15 @@ int make_map(CUtensorMap *map, const void *base, int64_t inner, int64_t outer, i
   cuuint64_t strides[1] = {(cuuint64_t)ld * 4};
   cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
   cuuint32_t estr[2] = {1u, 1u};
+  CUtensorMapSwizzle swz = mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B;
+  if (mn_major) {
+    const char *o = getenv("KLNMF_TC_MN_TMA");
+    if (o) swz = (CUtensorMapSwizzle)atoi(o);
+  }
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   swz,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   KL_CHECK(r == CUDA_SUCCESS, KLNMF_ECUDA, "cuTensorMapEncodeTiled failed with %d (inner=%lld outer=%lld ld=%lld)", (int)r,
            (long long)inner, (long long)outer, (long long)ld);
@@ -480,17 +492,17 @@ int launch_cfg(klnmf_ctx *ctx, const GemmDesc &d, TcParams p) {
   static_assert(C::STAGES >= 2, "pipeline too shallow");
   CUtensorMap tmA, tmAlo, tmB, tmBlo;
   // A: K-major = memory M x K (inner K);  MN-major = memory K x M (inner M)
-  if (!A_MN) KL_TRY(make_map(&tmA, d.A, d.K, d.M, d.a_sm, BM));
-  else KL_TRY(make_map(&tmA, d.A, d.M, d.K, d.a_sk, 32));
-  if (!B_MN) KL_TRY(make_map(&tmB, d.B, d.K, d.N, d.b_sn, BN));
-  else KL_TRY(make_map(&tmB, d.B, d.N, d.K, d.b_sk, 32));
+  if (!A_MN) KL_TRY(make_map(&tmA, d.A, d.K, d.M, d.a_sm, BM, false));
+  else KL_TRY(make_map(&tmA, d.A, d.M, d.K, d.a_sk, 32, true));
+  if (!B_MN) KL_TRY(make_map(&tmB, d.B, d.K, d.N, d.b_sn, BN, false));
+  else KL_TRY(make_map(&tmB, d.B, d.N, d.K, d.b_sk, 32, true));
   tmAlo = tmA;
   tmBlo = tmB;
   if (SPLIT) {
-    if (!A_MN) KL_TRY(make_map(&tmAlo, d.A_lo, d.K, d.M, d.a_sm, BM));
-    else KL_TRY(make_map(&tmAlo, d.A_lo, d.M, d.K, d.a_sk, 32));
-    if (!B_MN) KL_TRY(make_map(&tmBlo, d.B_lo, d.K, d.N, d.b_sn, BN));
-    else KL_TRY(make_map(&tmBlo, d.B_lo, d.N, d.K, d.b_sk, 32));
+    if (!A_MN) KL_TRY(make_map(&tmAlo, d.A_lo, d.K, d.M, d.a_sm, BM, false));
+    else KL_TRY(make_map(&tmAlo, d.A_lo, d.M, d.K, d.a_sk, 32, true));
+    if (!B_MN) KL_TRY(make_map(&tmBlo, d.B_lo, d.K, d.N, d.b_sn, BN, false));
+    else KL_TRY(make_map(&tmBlo, d.B_lo, d.N, d.K, d.b_sk, 32, true));
   }
   p.m_tiles = (int)ceil_div(d.M, BM);
   p.n_tiles = (int)ceil_div(d.N, BN);
@@ -566,6 +578,11 @@ int tc_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d) {
            "tc_gemm: aux operand missing or its leading dimension is below N rounded to 32");
   p.kl = d.kl; p.stop = d.stop; p.err = st->err_dev;
   p.m_fastest = (epi == EPI_ACC) ? 1 : 0;
+  p.mn_lt = 1; p.mn_lbo = 4096; p.mn_sbo = 512; p.mn_kadv = 1024;
+  if (const char *o = getenv("KLNMF_TC_MN")) {   // "layout_type,lbo,sbo,kadv" (bring-up only)
+    unsigned a, b, c, e;
+    if (sscanf(o, "%u,%u,%u,%u", &a, &b, &c, &e) == 4) { p.mn_lt = a; p.mn_lbo = b; p.mn_sbo = c; p.mn_kadv = e; }
+  }
   const char *force = getenv("KLNMF_TC_BN");
   bool narrow = d.N <= 128;
   if (force) narrow = atoi(force) == 128;
