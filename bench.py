@@ -43,12 +43,12 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("KLNMF_BENCH_MODE", "tf32x3"))
+    ap.add_argument("--mode", default=os.environ.get("KLNMF_BENCH_MODE", "tf32"))
     ap.add_argument("--workload", default=os.environ.get("KLNMF_BENCH_WORKLOAD", "cfg5"), choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="override the total sample count (development only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--alt-mode", default=os.environ.get("KLNMF_BENCH_ALT", "tf32"),
+    ap.add_argument("--alt-mode", default=os.environ.get("KLNMF_BENCH_ALT", "tf32x3"),
                     help="second arithmetic mode reported under alt_modes ('' to skip)")
     return ap.parse_args()
 

@@ -147,6 +147,9 @@ int klnmf_last_run_profile(klnmf_ctx *ctx, double ms[6], int64_t counts[5]);
  * a_trans=1: A is stored K x M; b_trans=0: B is K x N row-major, b_trans=1: B is stored N x K. */
 int klnmf_contract_host(int device, int mode, int64_t M, int64_t N, int64_t K, const double *A, int a_trans,
                         const double *B, int b_trans, double *out);
+/* diagnostic: average device milliseconds of one such contraction on synthetic device-resident operands */
+int klnmf_contract_bench(int device, int mode, int64_t M, int64_t N, int64_t K, int a_trans, int b_trans, int iters,
+                         double *ms_out);
 /* name of the kernel family that serves the dense contractions in this context
  * ("tcgen05_tf32", "tcgen05_tf32x3", "dmma_f64") -- lets tests assert the native path. */
 const char *klnmf_engine_name(klnmf_ctx *ctx);

@@ -61,6 +61,8 @@ PROTOTYPES = {
     "klnmf_counters": (_c_int, [_c_vp, ctypes.POINTER(_c_i64)]),
     "klnmf_last_run_profile": (_c_int, [_c_vp, ctypes.POINTER(_c_dbl), ctypes.POINTER(_c_i64)]),
     "klnmf_contract_host": (_c_int, [_c_int, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_vp, _c_int, _c_vp]),
+    "klnmf_contract_bench": (_c_int, [_c_int, _c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_int,
+                                      ctypes.POINTER(_c_dbl)]),
     "klnmf_engine_name": (ctypes.c_char_p, [_c_vp]),
 }
 
@@ -328,3 +330,12 @@ def contract(A, B, mode, a_trans=False, b_trans=False, device=0):
     _check(lib.klnmf_contract_host(int(device), resolve_mode(mode), M, N, K, _ptr(A), 1 if a_trans else 0,
                                    _ptr(B), 1 if b_trans else 0, _ptr(out)))
     return out
+
+
+def contract_bench(M, N, K, mode, a_trans=False, b_trans=False, iters=10, device=0):
+    """Diagnostic: average device ms of one M x N x K contraction (see klnmf_contract_bench)."""
+    lib = load()
+    ms = _c_dbl(0.0)
+    _check(lib.klnmf_contract_bench(int(device), resolve_mode(mode), int(M), int(N), int(K), 1 if a_trans else 0,
+                                    1 if b_trans else 0, int(iters), ctypes.byref(ms)))
+    return ms.value

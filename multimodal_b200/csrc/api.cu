@@ -957,6 +957,58 @@ int klnmf_contract_host(int device, int mode, int64_t M, int64_t N, int64_t K, c
   return rc;
 }
 
+// Diagnostic: device time of `iters` back-to-back contractions of the given shape and operand majors
+// on synthetic device data (no host copies); ms_out = average milliseconds per contraction.
+int klnmf_contract_bench(int device, int mode, int64_t M, int64_t N, int64_t K, int a_trans, int b_trans, int iters,
+                         double *ms_out) {
+  KL_CHECK(ms_out && M > 0 && N > 0 && K > 0 && iters > 0, KLNMF_EINVAL, "contract_bench: bad argument");
+  klnmf_ctx *ctx = nullptr;
+  KL_TRY(klnmf_create(&ctx, device, M, N, K, mode));
+  const int64_t es = ctx->es;
+  const int64_t a_rows = a_trans ? K : M, a_cols = a_trans ? M : K;
+  const int64_t b_rows = b_trans ? N : K, b_cols = b_trans ? K : N;
+  const int64_t lda = round_up(a_cols, 32), ldb = round_up(b_cols, 32), ldo = round_up(N, 32);
+  void *dA = nullptr, *dAlo = nullptr, *dB = nullptr, *dBlo = nullptr, *dO = nullptr;
+  int rc = dmalloc(&dA, a_rows * lda * es);
+  if (rc == KLNMF_OK) rc = dmalloc(&dB, b_rows * ldb * es);
+  if (rc == KLNMF_OK) rc = dmalloc(&dO, M * ldo * es);
+  if (rc == KLNMF_OK) rc = launch_fill_uniform(ctx, dA, (int)es, a_rows, a_cols, lda, 1);
+  if (rc == KLNMF_OK) rc = launch_fill_uniform(ctx, dB, (int)es, b_rows, b_cols, ldb, 2);
+  if (rc == KLNMF_OK && ctx->split) {
+    rc = dmalloc(&dAlo, a_rows * lda * es);
+    if (rc == KLNMF_OK) rc = dmalloc(&dBlo, b_rows * ldb * es);
+    if (rc == KLNMF_OK) rc = launch_split(ctx, (const float *)dA, (float *)dA, (float *)dAlo, a_rows, a_cols, lda);
+    if (rc == KLNMF_OK) rc = launch_split(ctx, (const float *)dB, (float *)dB, (float *)dBlo, b_rows, b_cols, ldb);
+  }
+  GemmDesc d{};
+  d.M = M; d.N = N; d.K = K;
+  d.A = dA; d.A_lo = dAlo; d.a_sm = a_trans ? 1 : lda; d.a_sk = a_trans ? lda : 1;
+  d.B = dB; d.B_lo = dBlo; d.b_sk = b_trans ? 1 : ldb; d.b_sn = b_trans ? ldb : 1;
+  d.out = dO; d.ldo = ldo;
+  cudaEvent_t e0 = nullptr, e1 = nullptr;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  for (int i = 0; i < 2 && rc == KLNMF_OK; i++) rc = dense_gemm(ctx, EPI_STORE, d);
+  cudaEventRecord(e0, ctx->stream);
+  for (int i = 0; i < iters && rc == KLNMF_OK; i++) rc = dense_gemm(ctx, EPI_STORE, d);
+  cudaEventRecord(e1, ctx->stream);
+  cudaError_t se = cudaStreamSynchronize(ctx->stream);
+  if (rc == KLNMF_OK && se != cudaSuccess) {
+    set_error("contract_bench: device error: %s", cudaGetErrorString(se));
+    rc = KLNMF_ECUDA;
+  }
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  *ms_out = (double)ms / iters;
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  void *ptrs[] = {dA, dAlo, dB, dBlo, dO};
+  for (void *q : ptrs)
+    if (q) cudaFree(q);
+  klnmf_destroy(ctx);
+  return rc;
+}
+
 const char *klnmf_engine_name(klnmf_ctx *ctx) {
   if (!ctx) return "none";
   if (ctx->es == 8) return "dmma_f64";

@@ -27,7 +27,10 @@ constexpr int BM = 128;          // tile rows  (UMMA M, cta_group::1)
 constexpr int BK = 32;           // K per stage in floats = one 128-byte swizzle span
 constexpr int UMMA_K = 8;        // kind::tf32: 32 bytes of K per instruction
 constexpr int NUM_THREADS = 320; // producer warp + MMA warp + 8 epilogue warps
+constexpr int NUM_THREADS_XT = 352; // + one warp that streams X chunks by TMA (ratio epilogue)
 constexpr int EPI_WARPS = 8;
+constexpr int XCHUNK_BYTES = BM * 32 * 4;   // one 128-row x 32-column fp32 chunk of X or Q (128B-swizzled)
+constexpr int XBUFS = 3;                    // X chunks in flight per CTA
 
 struct TcParams {
   int64_t M, N, K;
@@ -97,6 +100,17 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
       "l"(map), "r"(bar), "r"(c0), "r"(c1)
       : "memory");
 }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t src, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src),
+               "r"(c0), "r"(c1)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
 __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
@@ -132,6 +146,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
+// MUFU approximations (flush-to-zero forms: no denormal range fix-up code, so 32 independent
+// chains per thread interleave freely).  Arguments here are >= eps = 1e-8, far from denormals.
+__device__ __forceinline__ float rcp_approx(float v) {
+  float r;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+__device__ __forceinline__ float lg2_approx(float v) {
+  float r;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v));
+  return r;
+}
+// one element of the ratio epilogue (nmf.py:325-336 + metrics.py:18-20): q = (x+eps)/(s+eps),
+// returns x*log(q) + s - x
+template <bool ACCURATE>
+__device__ __forceinline__ float ratio_term(float x, float s, float &q) {
+  if (ACCURATE) {
+    q = (x + (float)KL_EPS) / (s + (float)KL_EPS);
+    return fmaf(x, logf(q), s - x);
+  }
+  q = (x + (float)KL_EPS) * rcp_approx(s + (float)KL_EPS);
+  return fmaf(x * 0.69314718055994531f, lg2_approx(q), s - x);
+}
 __device__ __forceinline__ float tf32_round(float v) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
@@ -154,14 +191,17 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   return d;
 }
 
-template <int BN, bool SPLIT>
+// XT = the ratio epilogue with TMA-staged X and Q: three operand stages instead of four make
+// room for XBUFS X chunks plus one Q staging chunk per epilogue half.
+template <int BN, bool SPLIT, bool XT = false>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = BN * BK * 4;
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (SPLIT ? 2 : 1);
-  static constexpr int STAGES = (192 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = ((XT ? 144 : 192) * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;   // power of two: 256 or 512
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int XQ_BYTES = XT ? (XBUFS + 2) * XCHUNK_BYTES : 0;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + XQ_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -202,20 +242,10 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams &p, int64_t row, i
     float x[32], q[32];
     ld_row32(p.aux + row * p.ldaux + col0, x);
     float part = 0.f;
+    // split-TF32 contractions are FP32-grade, so their epilogue uses IEEE division and logf
 #pragma unroll
-    for (int j = 0; j < 32; j++) {
-      const float s = acc[j];
-      float lq;
-      if (p.accurate) {
-        q[j] = (x[j] + (float)KL_EPS) / (s + (float)KL_EPS);
-        lq = logf(q[j]);
-      } else {
-        q[j] = __fdividef(x[j] + (float)KL_EPS, s + (float)KL_EPS);
-        lq = __logf(q[j]);
-      }
-      // columns >= N hold x = 0, s = 0: q = 1, the term is exactly 0
-      part += fmaf(x[j], lq, s - x[j]);
-    }
+    for (int j = 0; j < 32; j++) part += ratio_term<SPLIT>(x[j], acc[j], q[j]);
+    // columns >= N hold x = 0, s = 0: q = 1, the term is exactly 0
     kl += (double)part;
     if (!p.only_kl) {
       if (SPLIT && p.out_lo) {
@@ -261,26 +291,33 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams &p, int64_t row, i
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <int BN, bool A_MN, bool B_MN, bool SPLIT>
-__global__ void __launch_bounds__(NUM_THREADS, 1)
+// XT = true: the ratio contraction (EPI_RATIO, A K-major, B MN-major) with X streamed into a
+// 128B-swizzled smem ring by TMA (warp 10) and Q leaving through smem + TMA store, so that both
+// cross HBM as full 128-byte lines instead of one 16-byte piece per thread and row.
+template <int BN, bool A_MN, bool B_MN, bool SPLIT, bool XT>
+__global__ void __launch_bounds__(XT ? NUM_THREADS_XT : NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
-               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo, const TcParams p) {
-  using C = Cfg<BN, SPLIT>;
+               const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
+               const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQ, const TcParams p) {
+  using C = Cfg<BN, SPLIT, XT>;
   constexpr int STAGES = C::STAGES;
   if (p.stop != nullptr && *p.stop != 0) return;
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
-  const uint32_t bar_base = smem_base + STAGES * C::STAGE_BYTES;
-  // barrier block: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem_ptr
+  const uint32_t xq_base = smem_base + STAGES * C::STAGE_BYTES;          // X ring, then Q staging (XT only)
+  const uint32_t bar_base = xq_base + C::XQ_BYTES;
+  // barrier block: full[STAGES] | empty[STAGES] | tmem_full[2] | tmem_empty[2] | tmem_ptr | xfull[XBUFS] | xempty[XBUFS]
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
   auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
   const uint32_t tmem_ptr_addr = bar_base + 8u * (2 * STAGES + 4);
+  auto xfull_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 5 + b); };
+  auto xempty_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 5 + XBUFS + b); };
   volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(smem_gen + STAGES * C::STAGE_BYTES +
-                                                                           8 * (2 * STAGES + 4));
+                                                                           C::XQ_BYTES + 8 * (2 * STAGES + 4));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -288,8 +325,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
     if (SPLIT) { tma_prefetch_desc(&tmAlo); tma_prefetch_desc(&tmBlo); }
+    if (XT) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmQ); }
     for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
     for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+    if (XT)
+      for (int b = 0; b < XBUFS; b++) { mbar_init(xfull_bar(b), 1); mbar_init(xempty_bar(b), EPI_WARPS / 2); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_ptr_addr, C::TMEM_COLS);
@@ -306,41 +346,37 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
   if (warp == 0) {
     // =============================== TMA producer ===============================
-    if (lane == 0) {
+    // MN-major operands need one 32 x 32 box per 32-wide M/N group (up to 4 + 8 boxes per stage, twice
+    // that for split-TF32): every lane issues at most one box, so a stage costs one issue slot of the
+    // warp instead of a dozen serial UTMALDGs on one thread.
+    {
+      constexpr int NA = A_MN ? BM / 32 : 1, NB = B_MN ? BN / 32 : 1;
+      static_assert(NA + NB <= 16, "lo operands use lanes 16..31");
+      const int l = lane & 15;
+      const bool is_lo = lane >= 16;
+      const bool is_a = l < NA;
+      const int grp = is_a ? l : l - NA;
+      const bool active = l < NA + NB && (SPLIT || !is_lo);
+      const CUtensorMap *map = is_a ? (is_lo ? &tmAlo : &tmA) : (is_lo ? &tmBlo : &tmB);
+      const uint32_t dst_off = (is_a ? 0u : (uint32_t)C::A_BYTES * (SPLIT ? 2 : 1)) +
+                               (is_lo ? (uint32_t)(is_a ? C::A_BYTES : C::B_BYTES) : 0u) + (uint32_t)grp * 4096u;
+      const bool mn = is_a ? A_MN : B_MN;
       int stage = 0; uint32_t phase = 0;
       for (int64_t u = blockIdx.x; u < total_units; u += gridDim.x) {
         int mi, ni, si;
         decode(u, mi, ni, si);
         const int64_t kb0 = (int64_t)si * p.kb_per_split;
         const int64_t kb1 = kb0 + p.kb_per_split < p.kb_total ? kb0 + p.kb_per_split : p.kb_total;
-        const int32_t m0 = mi * BM, n0 = ni * BN;
+        const int32_t mn0 = (is_a ? mi * BM : ni * BN) + (mn ? 32 * grp : 0);
         for (int64_t kb = kb0; kb < kb1; kb++) {
           mbar_wait(empty_bar(stage), phase ^ 1, p.err, 1);
-          mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
-          const uint32_t sA = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t sAlo = sA + C::A_BYTES;
-          const uint32_t sB = sA + C::A_BYTES * (SPLIT ? 2 : 1);
-          const uint32_t sBlo = sB + C::B_BYTES;
-          const int32_t k0 = (int32_t)(kb * BK);
-          if (!A_MN) {
-            tma_load_2d(sA, &tmA, full_bar(stage), k0, m0);
-            if (SPLIT) tma_load_2d(sAlo, &tmAlo, full_bar(stage), k0, m0);
-          } else {
-#pragma unroll
-            for (int i = 0; i < BM / 32; i++) {
-              tma_load_2d(sA + i * 4096, &tmA, full_bar(stage), m0 + 32 * i, k0);
-              if (SPLIT) tma_load_2d(sAlo + i * 4096, &tmAlo, full_bar(stage), m0 + 32 * i, k0);
-            }
-          }
-          if (!B_MN) {
-            tma_load_2d(sB, &tmB, full_bar(stage), k0, n0);
-            if (SPLIT) tma_load_2d(sBlo, &tmBlo, full_bar(stage), k0, n0);
-          } else {
-#pragma unroll
-            for (int i = 0; i < BN / 32; i++) {
-              tma_load_2d(sB + i * 4096, &tmB, full_bar(stage), n0 + 32 * i, k0);
-              if (SPLIT) tma_load_2d(sBlo + i * 4096, &tmBlo, full_bar(stage), n0 + 32 * i, k0);
-            }
+          if (lane == 0) mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          __syncwarp();
+          if (active) {
+            const int32_t k0 = (int32_t)(kb * BK);
+            const uint32_t dst = smem_base + stage * C::STAGE_BYTES + dst_off;
+            if (mn) tma_load_2d(dst, map, full_bar(stage), mn0, k0);
+            else tma_load_2d(dst, map, full_bar(stage), k0, mn0);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -397,7 +433,97 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
       }
     }
-  } else {
+  } else if (XT && warp == 10) {
+    // =============================== X loader (ratio epilogue) ===============================
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int64_t u = blockIdx.x; u < total_units; u += gridDim.x) {
+        int mi, ni, si;
+        decode(u, mi, ni, si);
+        const int32_t m0 = mi * BM, n0 = ni * BN;
+        const int64_t left = (p.n_store - (int64_t)n0) / 32;
+        const int nch = (int)(left < BN / 32 ? left : BN / 32);
+        for (int c = 0; c < nch; c++, g++) {
+          const uint32_t b = g % XBUFS, ph = (g / XBUFS) & 1u;
+          mbar_wait(xempty_bar(b), ph ^ 1u, p.err, 5);
+          mbar_expect_tx(xfull_bar(b), XCHUNK_BYTES);
+          tma_load_2d(xq_base + b * XCHUNK_BYTES, &tmX, xfull_bar(b), n0 + 32 * c, m0);
+        }
+      }
+    }
+  } else if (XT) {
+    // =============================== ratio epilogue, X and Q through shared memory ===============================
+    const int e = warp - 2;                 // 0..7
+    const int quarter = warp & 3;           // TMEM lanes this warp may touch: [32*quarter, +32)
+    const int half = e >> 2;                // chunks c with (c & 1) == half belong to this half
+    const bool elected = (e & 3) == 0 && lane == 0;
+    const int r = quarter * 32 + lane;      // row inside the tile = TMEM lane
+    const uint32_t sw = (uint32_t)(r & 7);
+    uint8_t *xq_gen = smem_gen + STAGES * C::STAGE_BYTES;
+    uint8_t *qst_gen = xq_gen + (XBUFS + half) * XCHUNK_BYTES + r * 128;
+    const uint32_t qst = xq_base + (XBUFS + half) * XCHUNK_BYTES;
+    int acc = 0; uint32_t acc_phase = 0;
+    uint32_t gbase = 0;
+    double kl = 0.0;
+    for (int64_t u = blockIdx.x; u < total_units; u += gridDim.x) {
+      int mi, ni, si;
+      decode(u, mi, ni, si);
+      const int32_t m0 = mi * BM, n0 = ni * BN;
+      const int64_t left = (p.n_store - (int64_t)n0) / 32;
+      const int nch = (int)(left < BN / 32 ? left : BN / 32);
+      mbar_wait(tfull_bar(acc), acc_phase, p.err, 4);
+      tc_fence_after();
+#pragma unroll 1
+      for (int c = half; c < nch; c += 2) {
+        const uint32_t g = gbase + c, b = g % XBUFS, ph = (g / XBUFS) & 1u;
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32);
+        uint32_t v[32];
+        tmem_ld32(taddr, v);
+        mbar_wait(xfull_bar(b), ph, p.err, 6);
+        float x[32];
+        const uint8_t *xrow = xq_gen + b * XCHUNK_BYTES + r * 128;
+#pragma unroll
+        for (int j = 0; j < 8; j++) {
+          const float4 t = *reinterpret_cast<const float4 *>(xrow + ((j ^ sw) << 4));
+          x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(xempty_bar(b));
+        // rows >= M and columns >= N hold x = 0, s = 0 (TMA zero fill): q = 1, the term is exactly 0
+        float part0 = 0.f, part1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 32; j += 2) {
+          float q0, q1;
+          part0 += ratio_term<false>(x[j], __uint_as_float(v[j]), q0);
+          part1 += ratio_term<false>(x[j + 1], __uint_as_float(v[j + 1]), q1);
+          x[j] = q0; x[j + 1] = q1;
+        }
+        const float part = part0 + part1;
+        kl += (double)part;
+        if (!p.only_kl) {
+          if (elected) bulk_wait_read0();           // the previous store has finished reading the staging chunk
+          named_bar(1 + half, 128);
+#pragma unroll
+          for (int j = 0; j < 8; j++)
+            *reinterpret_cast<float4 *>(qst_gen + ((j ^ sw) << 4)) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+          fence_proxy_async();
+          named_bar(1 + half, 128);
+          if (elected) tma_store_2d(&tmQ, qst, n0 + 32 * c, m0);
+        }
+      }
+      gbase += (uint32_t)nch;
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+    if (elected) bulk_wait_all();
+    if (p.kl != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) kl += __shfl_xor_sync(0xffffffffu, kl, o);
+      if (lane == 0) atomicAdd(p.kl, kl);
+    }
+  } else if (warp < 10) {
     // =============================== epilogue ===============================
     const int e = warp - 2;                 // 0..7
     const int quarter = warp & 3;           // TMEM lanes this warp may touch: [32*quarter, +32)
@@ -486,11 +612,12 @@ struct TcState {
   int *err_dev = nullptr;
 };
 
-template <int BN, bool A_MN, bool B_MN, bool SPLIT>
+template <int BN, bool A_MN, bool B_MN, bool SPLIT, bool XT = false>
 int launch_cfg(klnmf_ctx *ctx, const GemmDesc &d, TcParams p) {
-  using C = Cfg<BN, SPLIT>;
+  using C = Cfg<BN, SPLIT, XT>;
   static_assert(C::STAGES >= 2, "pipeline too shallow");
-  CUtensorMap tmA, tmAlo, tmB, tmBlo;
+  static_assert(C::SMEM_BYTES <= 232448, "shared memory budget exceeded");
+  CUtensorMap tmA, tmAlo, tmB, tmBlo, tmX, tmQ;
   // A: K-major = memory M x K (inner K);  MN-major = memory K x M (inner M)
   if (!A_MN) KL_TRY(make_map(&tmA, d.A, d.K, d.M, d.a_sm, BM, false));
   else KL_TRY(make_map(&tmA, d.A, d.M, d.K, d.a_sk, 32, true));
@@ -503,6 +630,14 @@ int launch_cfg(klnmf_ctx *ctx, const GemmDesc &d, TcParams p) {
     else KL_TRY(make_map(&tmAlo, d.A_lo, d.M, d.K, d.a_sk, 32, true));
     if (!B_MN) KL_TRY(make_map(&tmBlo, d.B_lo, d.K, d.N, d.b_sn, BN, false));
     else KL_TRY(make_map(&tmBlo, d.B_lo, d.N, d.K, d.b_sk, 32, true));
+  }
+  tmX = tmA;
+  tmQ = tmA;
+  if (XT) {
+    // X (aux) and Q (out): row-major M x N, 32-column x 128-row boxes, 128B swizzle; columns >= N and
+    // rows >= M are zero-filled on load and clipped on store
+    KL_TRY(make_map(&tmX, d.aux, d.N, d.M, d.ldaux, BM, false));
+    if (!p.only_kl) KL_TRY(make_map(&tmQ, d.out, d.N, d.M, d.ldo, BM, false));
   }
   p.m_tiles = (int)ceil_div(d.M, BM);
   p.n_tiles = (int)ceil_div(d.N, BN);
@@ -526,13 +661,13 @@ int launch_cfg(klnmf_ctx *ctx, const GemmDesc &d, TcParams p) {
   const int64_t units = (int64_t)p.m_tiles * p.n_tiles * p.splits;
   if (units == 0 || p.kb_total == 0) return KLNMF_OK;
   const int grid = (int)(units < ctx->sm_count ? units : ctx->sm_count);
-  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, SPLIT>;
+  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, SPLIT, XT>;
   static bool attr_done = false;
   if (!attr_done) {
     KL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_done = true;
   }
-  kern<<<grid, NUM_THREADS, C::SMEM_BYTES, ctx->stream>>>(tmA, tmAlo, tmB, tmBlo, p);
+  kern<<<grid, XT ? NUM_THREADS_XT : NUM_THREADS, C::SMEM_BYTES, ctx->stream>>>(tmA, tmAlo, tmB, tmBlo, tmX, tmQ, p);
   ctx->n_launch++;
   KL_CUDA(cudaGetLastError());
   return KLNMF_OK;
@@ -587,6 +722,9 @@ int tc_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d) {
   bool narrow = d.N <= 128;
   if (force) narrow = atoi(force) == 128;
   if (!a_mn && !b_mn) return launch_major<false, false>(ctx, d, p, split, narrow);
+  // the ratio contraction of the loop: X and Q go through shared memory by TMA
+  if (!a_mn && b_mn && epi == EPI_RATIO && !split && !narrow && !getenv("KLNMF_TC_NO_XT"))
+    return launch_cfg<256, false, true, false, true>(ctx, d, p);
   if (!a_mn && b_mn) return launch_major<false, true>(ctx, d, p, split, narrow);
   if (a_mn && b_mn) return launch_major<true, true>(ctx, d, p, split, narrow);
   return launch_major<true, false>(ctx, d, p, split, narrow);
