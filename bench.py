@@ -333,6 +333,7 @@ def run_ours(args):
                 avail = min(avail, int(lim))
         except Exception:
             pass
+        avail = avail / max(1, world)       # every rank of the box pins its own shard
         rows = n_local
         if kind != "sparse_fit" and x_bytes * 2.5 > avail:
             rows = max(1024, int(avail / 2.5 / (f * 4)) // 1024 * 1024)
