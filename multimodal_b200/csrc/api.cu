@@ -985,12 +985,25 @@ int klnmf_contract_bench(int device, int mode, int64_t M, int64_t N, int64_t K, 
   d.A = dA; d.A_lo = dAlo; d.a_sm = a_trans ? 1 : lda; d.a_sk = a_trans ? lda : 1;
   d.B = dB; d.B_lo = dBlo; d.b_sk = b_trans ? 1 : ldb; d.b_sn = b_trans ? ldb : 1;
   d.out = dO; d.ldo = ldo;
+  // KLNMF_BENCH_EPI=ratio|ratio_kl: time the ratio epilogue (with / without the Q store) instead of a plain store
+  int epi = EPI_STORE;
+  void *dX = nullptr;
+  double *dkl = nullptr;
+  const char *be = getenv("KLNMF_BENCH_EPI");
+  if (rc == KLNMF_OK && be && strncmp(be, "ratio", 5) == 0) {
+    epi = EPI_RATIO;
+    rc = dmalloc(&dX, M * ldo * es);
+    if (rc == KLNMF_OK) rc = dmalloc((void **)&dkl, 8);
+    if (rc == KLNMF_OK) rc = launch_fill_uniform(ctx, dX, (int)es, M, N, ldo, 3);
+    if (rc == KLNMF_OK) cudaMemsetAsync(dkl, 0, 8, ctx->stream);
+    d.aux = dX; d.ldaux = ldo; d.kl = dkl; d.only_kl = strcmp(be, "ratio_kl") == 0;
+  }
   cudaEvent_t e0 = nullptr, e1 = nullptr;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);
-  for (int i = 0; i < 2 && rc == KLNMF_OK; i++) rc = dense_gemm(ctx, EPI_STORE, d);
+  for (int i = 0; i < 2 && rc == KLNMF_OK; i++) rc = dense_gemm(ctx, epi, d);
   cudaEventRecord(e0, ctx->stream);
-  for (int i = 0; i < iters && rc == KLNMF_OK; i++) rc = dense_gemm(ctx, EPI_STORE, d);
+  for (int i = 0; i < iters && rc == KLNMF_OK; i++) rc = dense_gemm(ctx, epi, d);
   cudaEventRecord(e1, ctx->stream);
   cudaError_t se = cudaStreamSynchronize(ctx->stream);
   if (rc == KLNMF_OK && se != cudaSuccess) {
@@ -1002,7 +1015,7 @@ int klnmf_contract_bench(int device, int mode, int64_t M, int64_t N, int64_t K, 
   *ms_out = (double)ms / iters;
   cudaEventDestroy(e0);
   cudaEventDestroy(e1);
-  void *ptrs[] = {dA, dAlo, dB, dBlo, dO};
+  void *ptrs[] = {dA, dAlo, dB, dBlo, dO, dX, dkl};
   for (void *q : ptrs)
     if (q) cudaFree(q);
   klnmf_destroy(ctx);

@@ -30,7 +30,8 @@ constexpr int NUM_THREADS = 320; // producer warp + MMA warp + 8 epilogue warps
 constexpr int NUM_THREADS_XT = 352; // + one warp that streams X chunks by TMA (ratio epilogue)
 constexpr int EPI_WARPS = 8;
 constexpr int XCHUNK_BYTES = BM * 32 * 4;   // one 128-row x 32-column fp32 chunk of X or Q (128B-swizzled)
-constexpr int XBUFS = 3;                    // X chunks in flight per CTA
+constexpr int XBUFS = 4;                    // X chunks in flight per CTA (their HBM latency is hidden by L2 prefetch)
+constexpr int QWARP_BYTES = 2 * 32 * 32 * 4; // per epilogue warp: two 32-row x 32-column Q staging boxes
 
 struct TcParams {
   int64_t M, N, K;
@@ -107,6 +108,10 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap *map, uint32_t sr
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap *map, int32_t c0, int32_t c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -115,23 +120,75 @@ __device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap *map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
 }
 
+// CG = 1: one CTA per tile.  CG = 2: a CTA pair (cluster of 2 on one TPC) works on a 256-row tile with
+// tcgen05 cta_group::2 -- each CTA stages its own 128 rows of A and HALF of the B tile, the leader issues
+// the MMAs for both, accumulators land in each CTA's own TMEM.
+template <int CG>
 __device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  if (CG == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  } else {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
 }
+template <int CG>
 __device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+  if (CG == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+  else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
 }
+template <int CG>
 __device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
-      "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
-      : "memory");
+  if (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::tf32 [%0], %1, %2, %3, p;\n\t}" ::"r"(d_tmem),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(acc)
+        : "memory");
 }
+// completion of all MMAs issued so far by this thread -> mbarrier (CG = 2: the barrier at the same smem
+// offset in BOTH CTAs of the pair)
+template <int CG>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if (CG == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(bar),
+                 "h"((uint16_t)3)
+                 : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {   // shared::cta -> shared::cluster of CTA `rank`
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ void cluster_sync() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// TMA load issued by one CTA of a pair into its OWN smem, completing bytes on a barrier of either CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map, uint32_t bar_cluster, int32_t c0, int32_t c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar_cluster), "r"(c0), "r"(c1)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
   asm volatile(
@@ -193,14 +250,14 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
 
 // XT = the ratio epilogue with TMA-staged X and Q: three operand stages instead of four make
 // room for XBUFS X chunks plus one Q staging chunk per epilogue half.
-template <int BN, bool SPLIT, bool XT = false>
+template <int BN, bool SPLIT, bool XT = false, int CG = 1>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 4;
-  static constexpr int B_BYTES = BN * BK * 4;
+  static constexpr int B_BYTES = (BN / CG) * BK * 4;     // a CTA pair splits the B tile
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (SPLIT ? 2 : 1);
-  static constexpr int STAGES = ((XT ? 144 : 192) * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = ((XT ? 96 : 192) * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;   // power of two: 256 or 512
-  static constexpr int XQ_BYTES = XT ? (XBUFS + 2) * XCHUNK_BYTES : 0;
+  static constexpr int XQ_BYTES = XT ? XBUFS * XCHUNK_BYTES + EPI_WARPS * QWARP_BYTES : 0;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + XQ_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -229,6 +286,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams &p, int64_t row, i
   if (row >= p.M || col0 >= p.n_store) return;
   const int epi = p.epi;
   if (epi == EPI_STORE) {
+    if (p.only_kl) return;     // diagnostic (KLNMF_BENCH_NOSTORE): contraction without the output traffic
     if (SPLIT && p.out_lo) {
       float hi[32], lo[32];
 #pragma unroll
@@ -294,14 +352,15 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams &p, int64_t row, i
 // XT = true: the ratio contraction (EPI_RATIO, A K-major, B MN-major) with X streamed into a
 // 128B-swizzled smem ring by TMA (warp 10) and Q leaving through smem + TMA store, so that both
 // cross HBM as full 128-byte lines instead of one 16-byte piece per thread and row.
-template <int BN, bool A_MN, bool B_MN, bool SPLIT, bool XT>
+template <int BN, bool A_MN, bool B_MN, bool SPLIT, bool XT, int CG>
 __global__ void __launch_bounds__(XT ? NUM_THREADS_XT : NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQ, const TcParams p) {
-  using C = Cfg<BN, SPLIT, XT>;
+  using C = Cfg<BN, SPLIT, XT, CG>;
   constexpr int STAGES = C::STAGES;
   if (p.stop != nullptr && *p.stop != 0) return;
+  const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;   // position in the CTA pair; 0 issues the MMAs
 
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -327,18 +386,20 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (SPLIT) { tma_prefetch_desc(&tmAlo); tma_prefetch_desc(&tmBlo); }
     if (XT) { tma_prefetch_desc(&tmX); tma_prefetch_desc(&tmQ); }
     for (int s = 0; s < STAGES; s++) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS); }
+    for (int a = 0; a < 2; a++) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), EPI_WARPS * CG); }
     if (XT)
       for (int b = 0; b < XBUFS; b++) { mbar_init(xfull_bar(b), 1); mbar_init(xempty_bar(b), EPI_WARPS / 2); }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_ptr_addr, C::TMEM_COLS);
+  if (warp == 1) tmem_alloc<CG>(tmem_ptr_addr, C::TMEM_COLS);
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync(); else __syncthreads();     // barrier inits visible to the peer before any remote signal
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr_gen;
 
+  // work units are per CTA pair when CG == 2 (p.m_tiles counts 256-row tiles then)
   const int64_t total_units = (int64_t)p.m_tiles * p.n_tiles * p.splits;
+  const int64_t u_first = blockIdx.x / CG, u_step = gridDim.x / CG;
   auto decode = [&](int64_t u, int &mi, int &ni, int &si) {
     if (p.m_fastest) { mi = (int)(u % p.m_tiles); u /= p.m_tiles; ni = (int)(u % p.n_tiles); si = (int)(u / p.n_tiles); }
     else { ni = (int)(u % p.n_tiles); u /= p.n_tiles; mi = (int)(u % p.m_tiles); si = (int)(u / p.m_tiles); }
@@ -350,7 +411,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // that for split-TF32): every lane issues at most one box, so a stage costs one issue slot of the
     // warp instead of a dozen serial UTMALDGs on one thread.
     {
-      constexpr int NA = A_MN ? BM / 32 : 1, NB = B_MN ? BN / 32 : 1;
+      constexpr int NA = A_MN ? BM / 32 : 1, NB = B_MN ? BN / 32 / CG : 1;
       static_assert(NA + NB <= 16, "lo operands use lanes 16..31");
       const int l = lane & 15;
       const bool is_lo = lane >= 16;
@@ -362,21 +423,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                                (is_lo ? (uint32_t)(is_a ? C::A_BYTES : C::B_BYTES) : 0u) + (uint32_t)grp * 4096u;
       const bool mn = is_a ? A_MN : B_MN;
       int stage = 0; uint32_t phase = 0;
-      for (int64_t u = blockIdx.x; u < total_units; u += gridDim.x) {
+      for (int64_t u = u_first; u < total_units; u += u_step) {
         int mi, ni, si;
         decode(u, mi, ni, si);
         const int64_t kb0 = (int64_t)si * p.kb_per_split;
         const int64_t kb1 = kb0 + p.kb_per_split < p.kb_total ? kb0 + p.kb_per_split : p.kb_total;
-        const int32_t mn0 = (is_a ? mi * BM : ni * BN) + (mn ? 32 * grp : 0);
+        const int32_t mn0 = (is_a ? (mi * CG + (int)crank) * BM : ni * BN + (int)crank * (BN / CG)) + (mn ? 32 * grp : 0);
         for (int64_t kb = kb0; kb < kb1; kb++) {
           mbar_wait(empty_bar(stage), phase ^ 1, p.err, 1);
-          if (lane == 0) mbar_expect_tx(full_bar(stage), C::STAGE_BYTES);
+          // the leader's barrier collects the bytes of both CTAs of a pair
+          if (lane == 0 && crank == 0) mbar_expect_tx(full_bar(stage), C::STAGE_BYTES * CG);
           __syncwarp();
           if (active) {
             const int32_t k0 = (int32_t)(kb * BK);
             const uint32_t dst = smem_base + stage * C::STAGE_BYTES + dst_off;
-            if (mn) tma_load_2d(dst, map, full_bar(stage), mn0, k0);
-            else tma_load_2d(dst, map, full_bar(stage), k0, mn0);
+            if (CG == 1) {
+              if (mn) tma_load_2d(dst, map, full_bar(stage), mn0, k0);
+              else tma_load_2d(dst, map, full_bar(stage), k0, mn0);
+            } else {
+              const uint32_t bar = mapa(full_bar(stage), 0);
+              if (mn) tma_load_2d_pair(dst, map, bar, mn0, k0);
+              else tma_load_2d_pair(dst, map, bar, k0, mn0);
+            }
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -384,13 +452,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4
+    if (lane == 0 && crank == 0) {
+      // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4 (M = 256 across a CTA pair)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
-      for (int64_t u = blockIdx.x; u < total_units; u += gridDim.x) {
+      for (int64_t u = u_first; u < total_units; u += u_step) {
         int mi, ni, si;
         decode(u, mi, ni, si);
         const int64_t kb0 = (int64_t)si * p.kb_per_split;
@@ -419,15 +487,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             if (SPLIT) {
               const uint64_t dal = make_desc(sAlo + a_off, a_lbo, a_sbo, a_lt);
               const uint64_t dbl = make_desc(sBlo + b_off, b_lbo, b_sbo, b_lt);
-              umma_tf32(d_tmem, dal, db, idesc, first);   // lo*hi
-              umma_tf32(d_tmem, da, dbl, idesc, 1u);      // hi*lo
-              umma_tf32(d_tmem, da, db, idesc, 1u);       // hi*hi
+              umma_tf32<CG>(d_tmem, dal, db, idesc, first);   // lo*hi
+              umma_tf32<CG>(d_tmem, da, dbl, idesc, 1u);      // hi*lo
+              umma_tf32<CG>(d_tmem, da, db, idesc, 1u);       // hi*hi
             } else {
-              umma_tf32(d_tmem, da, db, idesc, first);
+              umma_tf32<CG>(d_tmem, da, db, idesc, first);
             }
           }
-          umma_commit(empty_bar(stage));            // smem slot free once these MMAs retire
-          if (kb + 1 == kb1) umma_commit(tfull_bar(acc));   // accumulator complete
+          umma_commit<CG>(empty_bar(stage));            // smem slot free once these MMAs retire
+          if (kb + 1 == kb1) umma_commit<CG>(tfull_bar(acc));   // accumulator complete
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -435,14 +503,29 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (XT && warp == 10) {
     // =============================== X loader (ratio epilogue) ===============================
+    // The smem ring only has to cover the L2 latency: the X tile of the NEXT unit is prefetched into L2
+    // while the current one is consumed, which takes the HBM latency off the ring.
     if (lane == 0) {
-      uint32_t g = 0;
-      for (int64_t u = blockIdx.x; u < total_units; u += gridDim.x) {
+      auto x_tile = [&](int64_t u, int32_t &m0, int32_t &n0, int &nch) {
         int mi, ni, si;
         decode(u, mi, ni, si);
-        const int32_t m0 = mi * BM, n0 = ni * BN;
+        m0 = (mi * CG + (int)crank) * BM; n0 = ni * BN;
         const int64_t left = (p.n_store - (int64_t)n0) / 32;
-        const int nch = (int)(left < BN / 32 ? left : BN / 32);
+        nch = (int)(left < BN / 32 ? left : BN / 32);
+      };
+      uint32_t g = 0;
+      if (u_first < total_units) {
+        int32_t m0, n0; int nch;
+        x_tile(u_first, m0, n0, nch);
+        for (int c = 0; c < nch; c++) tma_prefetch_l2_2d(&tmX, n0 + 32 * c, m0);
+      }
+      for (int64_t u = u_first; u < total_units; u += u_step) {
+        int32_t m0, n0; int nch;
+        if (u + u_step < total_units) {
+          x_tile(u + u_step, m0, n0, nch);
+          for (int c = 0; c < nch; c++) tma_prefetch_l2_2d(&tmX, n0 + 32 * c, m0);
+        }
+        x_tile(u, m0, n0, nch);
         for (int c = 0; c < nch; c++, g++) {
           const uint32_t b = g % XBUFS, ph = (g / XBUFS) & 1u;
           mbar_wait(xempty_bar(b), ph ^ 1u, p.err, 5);
@@ -456,19 +539,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int e = warp - 2;                 // 0..7
     const int quarter = warp & 3;           // TMEM lanes this warp may touch: [32*quarter, +32)
     const int half = e >> 2;                // chunks c with (c & 1) == half belong to this half
-    const bool elected = (e & 3) == 0 && lane == 0;
     const int r = quarter * 32 + lane;      // row inside the tile = TMEM lane
-    const uint32_t sw = (uint32_t)(r & 7);
+    const uint32_t sw = (uint32_t)(lane & 7);
     uint8_t *xq_gen = smem_gen + STAGES * C::STAGE_BYTES;
-    uint8_t *qst_gen = xq_gen + (XBUFS + half) * XCHUNK_BYTES + r * 128;
-    const uint32_t qst = xq_base + (XBUFS + half) * XCHUNK_BYTES;
+    // Q leaves through two private 32 x 32 staging boxes per warp (128B-swizzled) and one TMA store per chunk:
+    // no barrier between warps, and the store of chunk i overlaps the arithmetic of chunk i+1
+    uint8_t *qst_gen = xq_gen + XBUFS * XCHUNK_BYTES + e * QWARP_BYTES + lane * 128;
+    const uint32_t qst = xq_base + XBUFS * XCHUNK_BYTES + e * QWARP_BYTES;
+    uint32_t qb = 0;
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t gbase = 0;
     double kl = 0.0;
-    for (int64_t u = blockIdx.x; u < total_units; u += gridDim.x) {
+    for (int64_t u = u_first; u < total_units; u += u_step) {
       int mi, ni, si;
       decode(u, mi, ni, si);
-      const int32_t m0 = mi * BM, n0 = ni * BN;
+      const int32_t m0 = (mi * CG + (int)crank) * BM, n0 = ni * BN;
       const int64_t left = (p.n_store - (int64_t)n0) / 32;
       const int nch = (int)(left < BN / 32 ? left : BN / 32);
       mbar_wait(tfull_bar(acc), acc_phase, p.err, 4);
@@ -501,23 +586,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const float part = part0 + part1;
         kl += (double)part;
         if (!p.only_kl) {
-          if (elected) bulk_wait_read0();           // the previous store has finished reading the staging chunk
-          named_bar(1 + half, 128);
+          if (lane == 0) bulk_wait_read1();         // the store issued two chunks ago has finished reading this box
+          __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; j++)
-            *reinterpret_cast<float4 *>(qst_gen + ((j ^ sw) << 4)) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            *reinterpret_cast<float4 *>(qst_gen + qb * (QWARP_BYTES / 2) + ((j ^ sw) << 4)) =
+                make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
           fence_proxy_async();
-          named_bar(1 + half, 128);
-          if (elected) tma_store_2d(&tmQ, qst, n0 + 32 * c, m0);
+          __syncwarp();
+          if (lane == 0) tma_store_2d(&tmQ, qst + qb * (QWARP_BYTES / 2), n0 + 32 * c, m0 + quarter * 32);
+          qb ^= 1u;
         }
       }
       gbase += (uint32_t)nch;
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {   // the accumulator of BOTH CTAs is free once all their epilogue warps are done
+        if (CG == 1 || crank == 0) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_cluster(mapa(tempty_bar(acc), 0));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
-    if (elected) bulk_wait_all();
+    if (lane == 0) bulk_wait_all();
     if (p.kl != nullptr) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) kl += __shfl_xor_sync(0xffffffffu, kl, o);
@@ -530,12 +620,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int half = e >> 2;                // column half of the tile
     int acc = 0; uint32_t acc_phase = 0;
     double kl = 0.0;
-    for (int64_t u = blockIdx.x; u < total_units; u += gridDim.x) {
+    for (int64_t u = u_first; u < total_units; u += u_step) {
       int mi, ni, si;
       decode(u, mi, ni, si);
       mbar_wait(tfull_bar(acc), acc_phase, p.err, 4);
       tc_fence_after();
-      const int64_t row = (int64_t)mi * BM + quarter * 32 + lane;
+      const int64_t row = ((int64_t)mi * CG + crank) * BM + quarter * 32 + lane;
 #pragma unroll 1
       for (int c = 0; c < BN / 64; c++) {
         const int col_in_tile = half * (BN / 2) + c * 32;
@@ -546,7 +636,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       }
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(tempty_bar(acc));
+      if (lane == 0) {   // the accumulator of BOTH CTAs is free once all their epilogue warps are done
+        if (CG == 1 || crank == 0) mbar_arrive(tempty_bar(acc));
+        else mbar_arrive_cluster(mapa(tempty_bar(acc), 0));
+      }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
     if (p.epi == EPI_RATIO && p.kl != nullptr) {
@@ -557,10 +650,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   }
 
   tc_fence_before();
-  __syncthreads();
+  if (CG == 2) cluster_sync(); else __syncthreads();     // nobody leaves while the peer may still signal or read its smem
   if (warp == 1) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, C::TMEM_COLS);
+    tmem_dealloc<CG>(tmem_base, C::TMEM_COLS);
   }
 }
 
@@ -612,23 +705,23 @@ struct TcState {
   int *err_dev = nullptr;
 };
 
-template <int BN, bool A_MN, bool B_MN, bool SPLIT, bool XT = false>
+template <int BN, bool A_MN, bool B_MN, bool SPLIT, bool XT = false, int CG = 1>
 int launch_cfg(klnmf_ctx *ctx, const GemmDesc &d, TcParams p) {
-  using C = Cfg<BN, SPLIT, XT>;
+  using C = Cfg<BN, SPLIT, XT, CG>;
   static_assert(C::STAGES >= 2, "pipeline too shallow");
   static_assert(C::SMEM_BYTES <= 232448, "shared memory budget exceeded");
   CUtensorMap tmA, tmAlo, tmB, tmBlo, tmX, tmQ;
   // A: K-major = memory M x K (inner K);  MN-major = memory K x M (inner M)
   if (!A_MN) KL_TRY(make_map(&tmA, d.A, d.K, d.M, d.a_sm, BM, false));
   else KL_TRY(make_map(&tmA, d.A, d.M, d.K, d.a_sk, 32, true));
-  if (!B_MN) KL_TRY(make_map(&tmB, d.B, d.K, d.N, d.b_sn, BN, false));
+  if (!B_MN) KL_TRY(make_map(&tmB, d.B, d.K, d.N, d.b_sn, BN / CG, false));
   else KL_TRY(make_map(&tmB, d.B, d.N, d.K, d.b_sk, 32, true));
   tmAlo = tmA;
   tmBlo = tmB;
   if (SPLIT) {
     if (!A_MN) KL_TRY(make_map(&tmAlo, d.A_lo, d.K, d.M, d.a_sm, BM, false));
     else KL_TRY(make_map(&tmAlo, d.A_lo, d.M, d.K, d.a_sk, 32, true));
-    if (!B_MN) KL_TRY(make_map(&tmBlo, d.B_lo, d.K, d.N, d.b_sn, BN, false));
+    if (!B_MN) KL_TRY(make_map(&tmBlo, d.B_lo, d.K, d.N, d.b_sn, BN / CG, false));
     else KL_TRY(make_map(&tmBlo, d.B_lo, d.N, d.K, d.b_sk, 32, true));
   }
   tmX = tmA;
@@ -637,10 +730,11 @@ int launch_cfg(klnmf_ctx *ctx, const GemmDesc &d, TcParams p) {
     // X (aux) and Q (out): row-major M x N, 32-column x 128-row boxes, 128B swizzle; columns >= N and
     // rows >= M are zero-filled on load and clipped on store
     KL_TRY(make_map(&tmX, d.aux, d.N, d.M, d.ldaux, BM, false));
-    if (!p.only_kl) KL_TRY(make_map(&tmQ, d.out, d.N, d.M, d.ldo, BM, false));
+    if (!p.only_kl) KL_TRY(make_map(&tmQ, d.out, d.N, d.M, d.ldo, 32, false));
   }
-  p.m_tiles = (int)ceil_div(d.M, BM);
+  p.m_tiles = (int)ceil_div(d.M, BM * CG);      // tiles of a CTA pair span 256 rows
   p.n_tiles = (int)ceil_div(d.N, BN);
+  const int64_t slots = ctx->sm_count / CG;     // CTAs or CTA pairs resident at once
   p.kb_total = ceil_div(d.K, BK);
   p.splits = 1;
   p.kb_per_split = p.kb_total;
@@ -651,7 +745,7 @@ int launch_cfg(klnmf_ctx *ctx, const GemmDesc &d, TcParams p) {
     int64_t best = 1; double best_eff = 0.0;
     for (int64_t s = 1; s <= max_s && s <= 64; s++) {
       const int64_t units = tiles * s;
-      const double eff = (double)units / (double)(ceil_div(units, ctx->sm_count) * ctx->sm_count);
+      const double eff = (double)units / (double)(ceil_div(units, slots) * slots);
       if (eff > best_eff + 1e-9) { best_eff = eff; best = s; }
       if (eff >= 0.95) { best = s; break; }
     }
@@ -660,23 +754,37 @@ int launch_cfg(klnmf_ctx *ctx, const GemmDesc &d, TcParams p) {
   }
   const int64_t units = (int64_t)p.m_tiles * p.n_tiles * p.splits;
   if (units == 0 || p.kb_total == 0) return KLNMF_OK;
-  const int grid = (int)(units < ctx->sm_count ? units : ctx->sm_count);
-  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, SPLIT, XT>;
+  const int grid = (int)(units < slots ? units : slots) * CG;
+  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, SPLIT, XT, CG>;
   static bool attr_done = false;
   if (!attr_done) {
     KL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
     attr_done = true;
   }
-  kern<<<grid, XT ? NUM_THREADS_XT : NUM_THREADS, C::SMEM_BYTES, ctx->stream>>>(tmA, tmAlo, tmB, tmBlo, tmX, tmQ, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid, 1, 1);
+  cfg.blockDim = dim3(XT ? NUM_THREADS_XT : NUM_THREADS, 1, 1);
+  cfg.dynamicSmemBytes = C::SMEM_BYTES;
+  cfg.stream = ctx->stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CG; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  KL_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmAlo, tmB, tmBlo, tmX, tmQ, p));
   ctx->n_launch++;
   KL_CUDA(cudaGetLastError());
   return KLNMF_OK;
 }
 
+// Wide tiles (N > 128) run on CTA pairs (cta_group::2); KLNMF_TC_CG=1 keeps single CTAs for comparison.
 template <bool A_MN, bool B_MN>
 int launch_major(klnmf_ctx *ctx, const GemmDesc &d, const TcParams &p, bool split, bool narrow) {
-  if (split) return narrow ? launch_cfg<128, A_MN, B_MN, true>(ctx, d, p) : launch_cfg<256, A_MN, B_MN, true>(ctx, d, p);
-  return narrow ? launch_cfg<128, A_MN, B_MN, false>(ctx, d, p) : launch_cfg<256, A_MN, B_MN, false>(ctx, d, p);
+  static const bool pair = !(getenv("KLNMF_TC_CG") && atoi(getenv("KLNMF_TC_CG")) == 1);
+  if (narrow) return split ? launch_cfg<128, A_MN, B_MN, true>(ctx, d, p) : launch_cfg<128, A_MN, B_MN, false>(ctx, d, p);
+  if (pair)
+    return split ? launch_cfg<256, A_MN, B_MN, true, false, 2>(ctx, d, p) : launch_cfg<256, A_MN, B_MN, false, false, 2>(ctx, d, p);
+  return split ? launch_cfg<256, A_MN, B_MN, true>(ctx, d, p) : launch_cfg<256, A_MN, B_MN, false>(ctx, d, p);
 }
 
 }  // namespace
@@ -703,6 +811,7 @@ int tc_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d) {
   TcParams p{};
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.epi = epi; p.only_kl = d.only_kl;
+  if (epi == EPI_STORE && getenv("KLNMF_BENCH_NOSTORE")) p.only_kl = 1;
   p.accurate = ctx->mode == KLNMF_MODE_TF32X3 ? 1 : 0;
   p.out = (float *)d.out; p.out_lo = (float *)d.out_lo; p.ldo = d.ldo;
   p.n_store = round_up(d.N, 32);
@@ -723,8 +832,10 @@ int tc_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d) {
   if (force) narrow = atoi(force) == 128;
   if (!a_mn && !b_mn) return launch_major<false, false>(ctx, d, p, split, narrow);
   // the ratio contraction of the loop: X and Q go through shared memory by TMA
-  if (!a_mn && b_mn && epi == EPI_RATIO && !split && !narrow && !getenv("KLNMF_TC_NO_XT"))
-    return launch_cfg<256, false, true, false, true>(ctx, d, p);
+  if (!a_mn && b_mn && epi == EPI_RATIO && !split && !narrow && !getenv("KLNMF_TC_NO_XT")) {
+    if (getenv("KLNMF_TC_CG") && atoi(getenv("KLNMF_TC_CG")) == 1) return launch_cfg<256, false, true, false, true, 1>(ctx, d, p);
+    return launch_cfg<256, false, true, false, true, 2>(ctx, d, p);
+  }
   if (!a_mn && b_mn) return launch_major<false, true>(ctx, d, p, split, narrow);
   if (a_mn && b_mn) return launch_major<true, true>(ctx, d, p, split, narrow);
   return launch_major<true, false>(ctx, d, p, split, narrow);

@@ -1,0 +1,8 @@
+#!/bin/bash
+mkdir -p gpurun_out
+{
+echo "=== speed2"; timeout 600 python tools/tc_speed2.py 2>&1 | tail -10
+echo "=== gpu tests"; timeout 1200 python -m pytest tests -m gpu -q -x 2>&1 | tail -8
+echo "=== cfg5 n=262144 tf32"; timeout 600 python bench.py --n 262144 --steps 5 --warmup 3 --mode tf32 --alt-mode tf32x3 --no-e2e --no-cpu 2>&1 | tail -1
+echo "=== cfg3 n=262144 tf32"; timeout 600 python bench.py --workload cfg3 --n 262144 --steps 5 --warmup 3 --mode tf32 --alt-mode tf32x3 --no-e2e --no-cpu 2>&1 | tail -1
+} > gpurun_out/run11.log 2>&1
