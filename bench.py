@@ -108,12 +108,12 @@ def cpu_sample(workload, n_total, f, k, kind, steps, warmup):
     import scipy.sparse as sp
     rs = np.random.RandomState(0)
     if kind == "sparse_fit":
-        n_cpu, m = 2048, int(round(f * 0.005))
+        n_cpu = 4096
         X = sp.random(n_cpu, f, density=0.005, random_state=rs, format="csr")
         X.data = 1.0 - X.data
         sample = "sparse n_cpu=%d of n=%d rows, f=%d, density 0.005, k=%d" % (n_cpu, n_total, f, k)
     else:
-        n_cpu = 2048 if k >= 512 else 4096
+        n_cpu = 16384 if k >= 512 else 32768      # about 3 s of float64 numpy work per iteration on 16 cores
         X = rs.random_sample((n_cpu, f))
         sample = "dense n_cpu=%d of n=%d rows, f=%d, k=%d" % (n_cpu, n_total, f, k)
     np.random.seed(0)
@@ -150,7 +150,7 @@ def run_reference(args):
     n_total, f, k, kind, desc = WORKLOADS[args.workload]
     if args.n:
         n_total = args.n
-    steps, warmup = max(1, min(args.steps, 3)), max(0, min(args.warmup, 1))
+    steps, warmup = max(1, min(args.steps, 8)), max(0, min(args.warmup, 2))
     base, t_step = cpu_sample(args.workload, n_total, f, k, kind, steps, warmup)
     line = {"impl": "reference", "metric": "KL-NMF iterations/sec", "value": base["value"], "unit": "iterations/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 / base["value"],
@@ -226,6 +226,21 @@ def make_engine(_native, n_local, f, k, kind, mode, local, rank, world, H0, scra
     return eng
 
 
+def ncu_traffic(kernel_key, rows_per_launch, f, k, mode):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the named kernel, from the committed
+    `ncu --set full` summary (profiles/ncu_traffic.json, written by tools/ncu_summarise.py). Only a capture of
+    the SAME launch shape counts; anything else is reported as null."""
+    p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    try:
+        for e in json.load(open(p)):
+            if (e["kernel"] == kernel_key and e["rows"] == rows_per_launch and e["f"] == f and e["k"] == k
+                    and e["mode"] == mode):
+                return e["dram_bytes"]
+    except Exception:
+        pass
+    return None
+
+
 def phase_roofline(ms, cnt, n_local, f, k, kind, steps, peaks, mode):
     if kind == "sparse_fit":
         # SURVEY 8d: compulsory bytes of one sparse iteration (CSR once, W r+w, H r + numerator w)
@@ -248,7 +263,9 @@ def phase_roofline(ms, cnt, n_local, f, k, kind, steps, peaks, mode):
     peak = peaks["bf16_sustained"] / 2.0                                 # TF32 dense = half the BF16 rate
     if mode == "fp64":
         peak = 40.0
-    r = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak, "traffic": None,
+    rows_per_launch = int(round(n_local * steps / float(launches)))
+    r = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
+         "traffic": ncu_traffic(dom, rows_per_launch, f, k, mode), "rows_per_launch": rows_per_launch,
          "kernel": names[dom], "avg_launch_ms": ms[dom] / launches, "launches": launches,
          "peak_source": ("TF32 = 1/2 x sustained cuBLAS bf16, " + peaks["source"]) if mode != "fp64" else "nominal B200 FP64",
          "phase_ms_per_step": {p: ms[p] / max(steps, 1) for p in ("ratio", "coefficient", "numerator", "dictionary", "allreduce")}}
@@ -377,7 +394,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu, _ = cpu_sample(args.workload, n_total, f, k, kind, 2, 1)
+        cpu, _ = cpu_sample(args.workload, n_total, f, k, kind, 4, 1)
 
     if rank == 0:
         line = {"metric": "KL-NMF iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": world,
