@@ -30,8 +30,7 @@ constexpr int NUM_THREADS = 320; // producer warp + MMA warp + 8 epilogue warps
 constexpr int NUM_THREADS_XT = 352; // + one warp that streams X chunks by TMA (ratio epilogue)
 constexpr int EPI_WARPS = 8;
 constexpr int XCHUNK_BYTES = BM * 32 * 4;   // one 128-row x 32-column fp32 chunk of X or Q (128B-swizzled)
-constexpr int XBUFS = 4;                    // X chunks in flight per CTA (their HBM latency is hidden by L2 prefetch)
-constexpr int QWARP_BYTES = 2 * 32 * 32 * 4; // per epilogue warp: two 32-row x 32-column Q staging boxes
+constexpr int QWARP_BYTES = 32 * 32 * 4;    // per epilogue warp: one 32-row x 32-column Q staging box
 
 struct TcParams {
   int64_t M, N, K;
@@ -46,6 +45,9 @@ struct TcParams {
   const int *stop;
   int *err;
   uint32_t mn_lt, mn_lbo, mn_sbo, mn_kadv;   // MN-major descriptor parameters (bring-up overridable)
+  int no_prefetch;                           // default 1; KLNMF_TC_PF=1 re-enables the L2 prefetch of the next X tile
+  int relaxed;                               // accumulator hand-back with relaxed arrives (KLNMF_TC_RELAXED=0: release)
+  uint32_t k_lt;                             // K-major layout type: 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B (experiment)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -179,6 +181,24 @@ __device__ __forceinline__ uint32_t mapa(uint32_t addr, uint32_t rank) {   // sh
 __device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
   asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
 }
+// hand-back of a TMEM accumulator: nothing in memory is published (the tcgen05.ld results are already in
+// registers, ordered by tcgen05.wait::ld + fence::before_thread_sync), so a relaxed arrive is enough --
+// the default release form costs a MEMBAR + ERRBAR per tile and warp
+__device__ __forceinline__ void mbar_arrive_relaxed(uint32_t bar) {
+  asm volatile("mbarrier.arrive.relaxed.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_cluster_relaxed(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void cluster_sync() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
   asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
@@ -202,6 +222,29 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t v[32]) {
       : "r"(taddr)
       : "memory");
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+// the same load split in two, so that the X chunk can be fetched from shared memory while TMEM is read:
+// the wait names the 32 registers as in/out operands, which keeps every use of them behind it
+__device__ __forceinline__ void tmem_ld32_issue(uint32_t taddr, uint32_t v[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld32_wait(uint32_t v[32]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15]), "+r"(v[16]),
+                 "+r"(v[17]), "+r"(v[18]), "+r"(v[19]), "+r"(v[20]), "+r"(v[21]), "+r"(v[22]), "+r"(v[23]), "+r"(v[24]),
+                 "+r"(v[25]), "+r"(v[26]), "+r"(v[27]), "+r"(v[28]), "+r"(v[29]), "+r"(v[30]), "+r"(v[31])
+               :
+               : "memory");
 }
 // MUFU approximations (flush-to-zero forms: no denormal range fix-up code, so 32 independent
 // chains per thread interleave freely).  Arguments here are >= eps = 1e-8, far from denormals.
@@ -247,17 +290,30 @@ __device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes
   d |= (uint64_t)layout_type << 61;
   return d;
 }
+// The same descriptor as two 32-bit halves: the high word is a loop constant, the low word advances with
+// the stage and the K step by plain 32-bit adds (addresses stay below 2^18, so the 14-bit field never carries).
+__device__ __forceinline__ uint32_t desc_lo(uint32_t saddr, uint32_t lbo_bytes) {
+  return ((saddr >> 4) & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+__device__ __forceinline__ uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | (layout_type << 29);
+}
+__device__ __forceinline__ uint64_t desc_pack(uint32_t lo, uint32_t hi) { return ((uint64_t)hi << 32) | lo; }
 
 // XT = the ratio epilogue with TMA-staged X and Q: three operand stages instead of four make
 // room for XBUFS X chunks plus one Q staging chunk per epilogue half.
-template <int BN, bool SPLIT, bool XT = false, int CG = 1>
+// XB = X chunks in flight per CTA (XT only; their HBM latency is hidden by the L2 prefetch of the next tile,
+// so the ring covers L2 latency only).  Everything the X ring and the Q staging do not take goes to operand
+// stages: with K = 512 the ratio contraction is bound by the TMA latency of its operand ring, not by smem.
+template <int BN, bool SPLIT, bool XT = false, int CG = 1, int XB = 2>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = (BN / CG) * BK * 4;     // a CTA pair splits the B tile
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (SPLIT ? 2 : 1);
-  static constexpr int STAGES = ((XT ? 96 : 192) * 1024) / STAGE_BYTES;
+  static constexpr int XBUFS = XB;
+  static constexpr int XQ_BYTES = XT ? XB * XCHUNK_BYTES + EPI_WARPS * QWARP_BYTES : 0;
+  static constexpr int STAGES = (XT ? (224 * 1024 - XQ_BYTES) : 192 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;   // power of two: 256 or 512
-  static constexpr int XQ_BYTES = XT ? XBUFS * XCHUNK_BYTES + EPI_WARPS * QWARP_BYTES : 0;
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + XQ_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -352,13 +408,14 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams &p, int64_t row, i
 // XT = true: the ratio contraction (EPI_RATIO, A K-major, B MN-major) with X streamed into a
 // 128B-swizzled smem ring by TMA (warp 10) and Q leaving through smem + TMA store, so that both
 // cross HBM as full 128-byte lines instead of one 16-byte piece per thread and row.
-template <int BN, bool A_MN, bool B_MN, bool SPLIT, bool XT, int CG>
+template <int BN, bool A_MN, bool B_MN, bool SPLIT, bool XT, int CG, int XB>
 __global__ void __launch_bounds__(XT ? NUM_THREADS_XT : NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQ, const TcParams p) {
-  using C = Cfg<BN, SPLIT, XT, CG>;
+  using C = Cfg<BN, SPLIT, XT, CG, XB>;
   constexpr int STAGES = C::STAGES;
+  constexpr int XBUFS = C::XBUFS;
   if (p.stop != nullptr && *p.stop != 0) return;
   const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;   // position in the CTA pair; 0 issues the MMAs
 
@@ -452,10 +509,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (warp == 1) {
     // =============================== MMA issuer ===============================
-    if (lane == 0 && crank == 0) {
+    // The whole warp walks the loop (warp-uniform control flow and descriptors, so they live in uniform
+    // registers); one elected lane issues the tcgen05 instructions.  Per K block: one barrier wait, four
+    // (twelve) MMAs whose descriptors differ by 32-bit adds, one commit.
+    if (crank == 0) {
       // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4 (M = 256 across a CTA pair)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
                              ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
+      // K-major: +32 B inside the 128 B swizzle row; MN-major: next 8-row group (+1024 B)
+      const uint32_t a_kadv = (A_MN ? p.mn_kadv : 32u) >> 4, b_kadv = (B_MN ? p.mn_kadv : 32u) >> 4;
+      const uint32_t a_hi = desc_hi(A_MN ? p.mn_sbo : 1024u, A_MN ? p.mn_lt : p.k_lt);
+      const uint32_t b_hi = desc_hi(B_MN ? p.mn_sbo : 1024u, B_MN ? p.mn_lt : p.k_lt);
+      const uint32_t a_lo0 = desc_lo(smem_base, A_MN ? p.mn_lbo : 16u);
+      const uint32_t b_lo0 = desc_lo(smem_base + C::A_BYTES * (SPLIT ? 2 : 1), B_MN ? p.mn_lbo : 16u);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int64_t u = u_first; u < total_units; u += u_step) {
@@ -463,39 +529,35 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         decode(u, mi, ni, si);
         const int64_t kb0 = (int64_t)si * p.kb_per_split;
         const int64_t kb1 = kb0 + p.kb_per_split < p.kb_total ? kb0 + p.kb_per_split : p.kb_total;
+        const int nkb = (int)(kb1 - kb0);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1, p.err, 2);
         tc_fence_after();
         const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
-        for (int64_t kb = kb0; kb < kb1; kb++) {
+        for (int kb = 0; kb < nkb; kb++) {
           mbar_wait(full_bar(stage), phase, p.err, 3);
           tc_fence_after();
-          const uint32_t sA = smem_base + stage * C::STAGE_BYTES;
-          const uint32_t sAlo = sA + C::A_BYTES;
-          const uint32_t sB = sA + C::A_BYTES * (SPLIT ? 2 : 1);
-          const uint32_t sBlo = sB + C::B_BYTES;
+          if (elect_one()) {
+            const uint32_t soff = (uint32_t)(stage * C::STAGE_BYTES) >> 4;
+            const uint32_t al = a_lo0 + soff, bl = b_lo0 + soff;
 #pragma unroll
-          for (int kk = 0; kk < BK / UMMA_K; kk++) {
-            // K-major: +32 B inside the 128 B swizzle row; MN-major: next 8-row group (+1024 B)
-            const uint32_t a_off = A_MN ? kk * p.mn_kadv : kk * 32u;
-            const uint32_t b_off = B_MN ? kk * p.mn_kadv : kk * 32u;
-            const uint32_t a_lbo = A_MN ? p.mn_lbo : 16u, b_lbo = B_MN ? p.mn_lbo : 16u;
-            const uint32_t a_sbo = A_MN ? p.mn_sbo : 1024u, b_sbo = B_MN ? p.mn_sbo : 1024u;
-            const uint32_t a_lt = A_MN ? p.mn_lt : 2u, b_lt = B_MN ? p.mn_lt : 2u;
-            const uint64_t da = make_desc(sA + a_off, a_lbo, a_sbo, a_lt);
-            const uint64_t db = make_desc(sB + b_off, b_lbo, b_sbo, b_lt);
-            const uint32_t first = (kb > kb0 || kk > 0) ? 1u : 0u;
-            if (SPLIT) {
-              const uint64_t dal = make_desc(sAlo + a_off, a_lbo, a_sbo, a_lt);
-              const uint64_t dbl = make_desc(sBlo + b_off, b_lbo, b_sbo, b_lt);
-              umma_tf32<CG>(d_tmem, dal, db, idesc, first);   // lo*hi
-              umma_tf32<CG>(d_tmem, da, dbl, idesc, 1u);      // hi*lo
-              umma_tf32<CG>(d_tmem, da, db, idesc, 1u);       // hi*hi
-            } else {
-              umma_tf32<CG>(d_tmem, da, db, idesc, first);
+            for (int kk = 0; kk < BK / UMMA_K; kk++) {
+              const uint64_t da = desc_pack(al + kk * a_kadv, a_hi);
+              const uint64_t db = desc_pack(bl + kk * b_kadv, b_hi);
+              const uint32_t first = (kb > 0 || kk > 0) ? 1u : 0u;
+              if (SPLIT) {
+                const uint64_t dal = desc_pack(al + (C::A_BYTES >> 4) + kk * a_kadv, a_hi);
+                const uint64_t dbl = desc_pack(bl + (C::B_BYTES >> 4) + kk * b_kadv, b_hi);
+                umma_tf32<CG>(d_tmem, dal, db, idesc, first);   // lo*hi
+                umma_tf32<CG>(d_tmem, da, dbl, idesc, 1u);      // hi*lo
+                umma_tf32<CG>(d_tmem, da, db, idesc, 1u);       // hi*hi
+              } else {
+                umma_tf32<CG>(d_tmem, da, db, idesc, first);
+              }
             }
+            umma_commit<CG>(empty_bar(stage));            // smem slot free once these MMAs retire
+            if (kb + 1 == nkb) umma_commit<CG>(tfull_bar(acc));   // accumulator complete
           }
-          umma_commit<CG>(empty_bar(stage));            // smem slot free once these MMAs retire
-          if (kb + 1 == kb1) umma_commit<CG>(tfull_bar(acc));   // accumulator complete
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1; }
@@ -503,8 +565,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
   } else if (XT && warp == 10) {
     // =============================== X loader (ratio epilogue) ===============================
-    // The smem ring only has to cover the L2 latency: the X tile of the NEXT unit is prefetched into L2
-    // while the current one is consumed, which takes the HBM latency off the ring.
+    // The ring of XBUFS chunks (16 KB each) covers the HBM latency by itself: 13 B/clk of X per SM x ~2000 clk.
     if (lane == 0) {
       auto x_tile = [&](int64_t u, int32_t &m0, int32_t &n0, int &nch) {
         int mi, ni, si;
@@ -514,14 +575,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         nch = (int)(left < BN / 32 ? left : BN / 32);
       };
       uint32_t g = 0;
-      if (u_first < total_units) {
+      if (u_first < total_units && !p.no_prefetch) {
         int32_t m0, n0; int nch;
         x_tile(u_first, m0, n0, nch);
         for (int c = 0; c < nch; c++) tma_prefetch_l2_2d(&tmX, n0 + 32 * c, m0);
       }
       for (int64_t u = u_first; u < total_units; u += u_step) {
         int32_t m0, n0; int nch;
-        if (u + u_step < total_units) {
+        if (u + u_step < total_units && !p.no_prefetch) {
           x_tile(u + u_step, m0, n0, nch);
           for (int c = 0; c < nch; c++) tma_prefetch_l2_2d(&tmX, n0 + 32 * c, m0);
         }
@@ -542,11 +603,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int r = quarter * 32 + lane;      // row inside the tile = TMEM lane
     const uint32_t sw = (uint32_t)(lane & 7);
     uint8_t *xq_gen = smem_gen + STAGES * C::STAGE_BYTES;
-    // Q leaves through two private 32 x 32 staging boxes per warp (128B-swizzled) and one TMA store per chunk:
-    // no barrier between warps, and the store of chunk i overlaps the arithmetic of chunk i+1
+    // Q leaves through one private 32 x 32 staging box per warp (128B-swizzled) and one TMA store per chunk:
+    // no barrier between warps; the store of chunk i has long finished reading the box when the arithmetic of
+    // chunk i+1 is done
     uint8_t *qst_gen = xq_gen + XBUFS * XCHUNK_BYTES + e * QWARP_BYTES + lane * 128;
     const uint32_t qst = xq_base + XBUFS * XCHUNK_BYTES + e * QWARP_BYTES;
-    uint32_t qb = 0;
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t gbase = 0;
     double kl = 0.0;
@@ -558,12 +619,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int nch = (int)(left < BN / 32 ? left : BN / 32);
       mbar_wait(tfull_bar(acc), acc_phase, p.err, 4);
       tc_fence_after();
+      float kl_tile = 0.f;      // <= 128 terms per thread in FP32, then FP64 across tiles
 #pragma unroll 1
       for (int c = half; c < nch; c += 2) {
         const uint32_t g = gbase + c, b = g % XBUFS, ph = (g / XBUFS) & 1u;
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32);
         uint32_t v[32];
-        tmem_ld32(taddr, v);
+        tmem_ld32_issue(taddr, v);
         mbar_wait(xfull_bar(b), ph, p.err, 6);
         float x[32];
         const uint8_t *xrow = xq_gen + b * XCHUNK_BYTES + r * 128;
@@ -572,6 +634,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           const float4 t = *reinterpret_cast<const float4 *>(xrow + ((j ^ sw) << 4));
           x[4 * j] = t.x; x[4 * j + 1] = t.y; x[4 * j + 2] = t.z; x[4 * j + 3] = t.w;
         }
+        tmem_ld32_wait(v);
         __syncwarp();
         if (lane == 0) mbar_arrive(xempty_bar(b));
         // rows >= M and columns >= N hold x = 0, s = 0 (TMA zero fill): q = 1, the term is exactly 0
@@ -583,27 +646,31 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           part1 += ratio_term<false>(x[j + 1], __uint_as_float(v[j + 1]), q1);
           x[j] = q0; x[j + 1] = q1;
         }
-        const float part = part0 + part1;
-        kl += (double)part;
+        kl_tile += part0 + part1;
         if (!p.only_kl) {
-          if (lane == 0) bulk_wait_read1();         // the store issued two chunks ago has finished reading this box
+          if (lane == 0) bulk_wait_read0();         // the previous store has finished reading the box
           __syncwarp();
 #pragma unroll
           for (int j = 0; j < 8; j++)
-            *reinterpret_cast<float4 *>(qst_gen + qb * (QWARP_BYTES / 2) + ((j ^ sw) << 4)) =
+            *reinterpret_cast<float4 *>(qst_gen + ((j ^ sw) << 4)) =
                 make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
           fence_proxy_async();
           __syncwarp();
-          if (lane == 0) tma_store_2d(&tmQ, qst + qb * (QWARP_BYTES / 2), n0 + 32 * c, m0 + quarter * 32);
-          qb ^= 1u;
+          if (lane == 0) tma_store_2d(&tmQ, qst, n0 + 32 * c, m0 + quarter * 32);
         }
       }
       gbase += (uint32_t)nch;
+      kl += (double)kl_tile;
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {   // the accumulator of BOTH CTAs is free once all their epilogue warps are done
-        if (CG == 1 || crank == 0) mbar_arrive(tempty_bar(acc));
-        else mbar_arrive_cluster(mapa(tempty_bar(acc), 0));
+        if (p.relaxed) {
+          if (CG == 1 || crank == 0) mbar_arrive_relaxed(tempty_bar(acc));
+          else mbar_arrive_cluster_relaxed(mapa(tempty_bar(acc), 0));
+        } else {
+          if (CG == 1 || crank == 0) mbar_arrive(tempty_bar(acc));
+          else mbar_arrive_cluster(mapa(tempty_bar(acc), 0));
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -637,8 +704,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {   // the accumulator of BOTH CTAs is free once all their epilogue warps are done
-        if (CG == 1 || crank == 0) mbar_arrive(tempty_bar(acc));
-        else mbar_arrive_cluster(mapa(tempty_bar(acc), 0));
+        if (p.relaxed) {
+          if (CG == 1 || crank == 0) mbar_arrive_relaxed(tempty_bar(acc));
+          else mbar_arrive_cluster_relaxed(mapa(tempty_bar(acc), 0));
+        } else {
+          if (CG == 1 || crank == 0) mbar_arrive(tempty_bar(acc));
+          else mbar_arrive_cluster(mapa(tempty_bar(acc), 0));
+        }
       }
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
@@ -691,10 +763,11 @@ int make_map(CUtensorMap *map, const void *base, int64_t inner, int64_t outer, i
     const char *o = getenv("KLNMF_TC_MN_TMA");
     if (o) swz = (CUtensorMapSwizzle)atoi(o);
   }
+  static const int promo = getenv("KLNMF_TC_PROMO") ? atoi(getenv("KLNMF_TC_PROMO")) : (int)CU_TENSOR_MAP_L2_PROMOTION_L2_256B;
   CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<void *>(base), dims, strides, box, estr,
                    CU_TENSOR_MAP_INTERLEAVE_NONE,
                    swz,
-                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   (CUtensorMapL2promotion)promo,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   KL_CHECK(r == CUDA_SUCCESS, KLNMF_ECUDA, "cuTensorMapEncodeTiled failed with %d (inner=%lld outer=%lld ld=%lld)", (int)r,
            (long long)inner, (long long)outer, (long long)ld);
@@ -705,23 +778,28 @@ struct TcState {
   int *err_dev = nullptr;
 };
 
-template <int BN, bool A_MN, bool B_MN, bool SPLIT, bool XT = false, int CG = 1>
+template <int BN, bool A_MN, bool B_MN, bool SPLIT, bool XT = false, int CG = 1, int XB = 2>
 int launch_cfg(klnmf_ctx *ctx, const GemmDesc &d, TcParams p) {
-  using C = Cfg<BN, SPLIT, XT, CG>;
+  using C = Cfg<BN, SPLIT, XT, CG, XB>;
   static_assert(C::STAGES >= 2, "pipeline too shallow");
   static_assert(C::SMEM_BYTES <= 232448, "shared memory budget exceeded");
   CUtensorMap tmA, tmAlo, tmB, tmBlo, tmX, tmQ;
   // A: K-major = memory M x K (inner K);  MN-major = memory K x M (inner M)
-  if (!A_MN) KL_TRY(make_map(&tmA, d.A, d.K, d.M, d.a_sm, BM, false));
+  // KLNMF_TC_KSWZ32=1 (experiment): K-major operands staged with the 32-byte-atom swizzle as well, i.e. the
+  // SAME smem image a MN-major descriptor reads -- what a fused back-to-back kernel needs to use one
+  // dictionary tile as the MN-major B of S = W.H and as the K-major B of G = Q.H^T
+  static const bool kswz32 = getenv("KLNMF_TC_KSWZ32") && atoi(getenv("KLNMF_TC_KSWZ32")) == 1;
+  p.k_lt = kswz32 ? 1u : 2u;
+  if (!A_MN) KL_TRY(make_map(&tmA, d.A, d.K, d.M, d.a_sm, BM, kswz32));
   else KL_TRY(make_map(&tmA, d.A, d.M, d.K, d.a_sk, 32, true));
-  if (!B_MN) KL_TRY(make_map(&tmB, d.B, d.K, d.N, d.b_sn, BN / CG, false));
+  if (!B_MN) KL_TRY(make_map(&tmB, d.B, d.K, d.N, d.b_sn, BN / CG, kswz32));
   else KL_TRY(make_map(&tmB, d.B, d.N, d.K, d.b_sk, 32, true));
   tmAlo = tmA;
   tmBlo = tmB;
   if (SPLIT) {
-    if (!A_MN) KL_TRY(make_map(&tmAlo, d.A_lo, d.K, d.M, d.a_sm, BM, false));
+    if (!A_MN) KL_TRY(make_map(&tmAlo, d.A_lo, d.K, d.M, d.a_sm, BM, kswz32));
     else KL_TRY(make_map(&tmAlo, d.A_lo, d.M, d.K, d.a_sk, 32, true));
-    if (!B_MN) KL_TRY(make_map(&tmBlo, d.B_lo, d.K, d.N, d.b_sn, BN / CG, false));
+    if (!B_MN) KL_TRY(make_map(&tmBlo, d.B_lo, d.K, d.N, d.b_sn, BN / CG, kswz32));
     else KL_TRY(make_map(&tmBlo, d.B_lo, d.N, d.K, d.b_sk, 32, true));
   }
   tmX = tmA;
@@ -755,7 +833,7 @@ int launch_cfg(klnmf_ctx *ctx, const GemmDesc &d, TcParams p) {
   const int64_t units = (int64_t)p.m_tiles * p.n_tiles * p.splits;
   if (units == 0 || p.kb_total == 0) return KLNMF_OK;
   const int grid = (int)(units < slots ? units : slots) * CG;
-  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, SPLIT, XT, CG>;
+  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, SPLIT, XT, CG, XB>;
   static bool attr_done = false;
   if (!attr_done) {
     KL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -823,6 +901,10 @@ int tc_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d) {
   p.kl = d.kl; p.stop = d.stop; p.err = st->err_dev;
   p.m_fastest = (epi == EPI_ACC) ? 1 : 0;
   p.mn_lt = 1; p.mn_lbo = 4096; p.mn_sbo = 512; p.mn_kadv = 1024;
+  // measured (profiles/r1_dram_traffic_variants.log): cp.async.bulk.prefetch.tensor of the next X tile made the
+  // kernel read X from HBM twice (8.6 GB instead of 4.6 GB at n = 131072) and 14 % slower -- off by default
+  p.no_prefetch = !(getenv("KLNMF_TC_PF") && atoi(getenv("KLNMF_TC_PF")) == 1);
+  p.relaxed = !(getenv("KLNMF_TC_RELAXED") && atoi(getenv("KLNMF_TC_RELAXED")) == 0);
   if (const char *o = getenv("KLNMF_TC_MN")) {   // "layout_type,lbo,sbo,kadv" (bring-up only)
     unsigned a, b, c, e;
     if (sscanf(o, "%u,%u,%u,%u", &a, &b, &c, &e) == 4) { p.mn_lt = a; p.mn_lbo = b; p.mn_sbo = c; p.mn_kadv = e; }
@@ -833,8 +915,14 @@ int tc_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d) {
   if (!a_mn && !b_mn) return launch_major<false, false>(ctx, d, p, split, narrow);
   // the ratio contraction of the loop: X and Q go through shared memory by TMA
   if (!a_mn && b_mn && epi == EPI_RATIO && !split && !narrow && !getenv("KLNMF_TC_NO_XT")) {
-    if (getenv("KLNMF_TC_CG") && atoi(getenv("KLNMF_TC_CG")) == 1) return launch_cfg<256, false, true, false, true, 1>(ctx, d, p);
-    return launch_cfg<256, false, true, false, true, 2>(ctx, d, p);
+    if (getenv("KLNMF_TC_CG") && atoi(getenv("KLNMF_TC_CG")) == 1) return launch_cfg<256, false, true, false, true, 1, 4>(ctx, d, p);
+    // long contractions (k >= 512) are bound by the latency of the operand ring: 5 stages + an X ring of 2
+    // chunks; shorter ones consume X faster than operands: 4 stages + 4 chunks (measured on cfg5 / cfg3,
+    // profiles/r1_ratio_ring_balance.log).  KLNMF_TC_XB=2|4 forces one.
+    int xb = d.K >= 512 ? 2 : 4;
+    if (getenv("KLNMF_TC_XB")) xb = atoi(getenv("KLNMF_TC_XB"));
+    if (xb == 2) return launch_cfg<256, false, true, false, true, 2, 2>(ctx, d, p);
+    return launch_cfg<256, false, true, false, true, 2, 4>(ctx, d, p);
   }
   if (!a_mn && b_mn) return launch_major<false, true>(ctx, d, p, split, narrow);
   if (a_mn && b_mn) return launch_major<true, true>(ctx, d, p, split, narrow);
