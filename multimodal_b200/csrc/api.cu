@@ -216,6 +216,30 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
   const int64_t es = ctx->es;
   const int cur = ctx->cur, hc = ctx->hcur;
   const int *stop = only_error ? nullptr : ctx->flags + FL_STOP;
+  if (!fit && !only_error && !dict_only && !ratio_host && fused_supported(ctx) && ctx->n > 0) {
+    // transform with k <= 128: one fused kernel per iteration, the ratio never leaves the SM (dense_fused.cu)
+    if (!ctx->Ht) {
+      ctx->ldht = ctx->ldw;
+      KL_TRY(dmalloc(&ctx->Ht, ctx->f * ctx->ldht * es));
+      KL_CUDA(cudaMemsetAsync(ctx->Ht, 0, ctx->f * ctx->ldht * es, ctx->stream));
+      ctx->ht_of = -1;
+    }
+    if (ctx->ht_of != hc || ctx->ht_stale) {
+      KL_TRY(launch_convert(ctx, ctx->H[hc], nullptr, KLNMF_F32, ctx->ldh, ctx->Ht, 4, ctx->ldht, ctx->k, ctx->f, true));
+      ctx->ht_of = hc;
+      ctx->ht_stale = false;
+    }
+    PhaseTimer t(ctx, prof, PH_RATIO);
+    FusedDesc d{};
+    d.M = ctx->n; d.F = ctx->f; d.K = ctx->k;
+    d.W = ctx->W[cur]; d.ldw = ctx->ldw;
+    d.H = ctx->H[hc]; d.ldh = ctx->ldh;
+    d.Ht = ctx->Ht; d.ldht = ctx->ldht;
+    d.X = ctx->X; d.ldx = ctx->ldx;
+    d.Wout = ctx->W[cur ^ 1]; d.ldwo = ctx->ldw;
+    d.kl = ctx->dred; d.stop = stop;
+    return fused_coef_step(ctx, d);
+  }
   for (int64_t r0 = 0; r0 < ctx->n; r0 += ctx->panel_rows) {
     const int64_t rows = ctx->n - r0 < ctx->panel_rows ? ctx->n - r0 : ctx->panel_rows;
     const char *Wc = (const char *)ctx->W[cur] + r0 * ctx->ldw * es;
@@ -341,6 +365,8 @@ int klnmf_destroy(klnmf_ctx *ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   nccl_comm_destroy(ctx);
   tc_release(ctx);
+  fused_release(ctx);
+  if (ctx->Ht) cudaFree(ctx->Ht);
   release_data(ctx);
   for (int i = 0; i < 2; i++) {
     if (ctx->W[i]) cudaFree(ctx->W[i]);
@@ -520,6 +546,7 @@ int klnmf_set_dictionary_host(klnmf_ctx *ctx, const double *H, int64_t ld) {
                         ctx->ldh));
   KL_TRY(launch_rowsum_h(ctx));
   ctx->have_h = true;
+  ctx->ht_stale = true;
   return KLNMF_OK;
 }
 
@@ -663,6 +690,8 @@ int klnmf_run(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, double *err
       rc = ctx->sparse ? launch_dict_update_t(ctx, ctx->H[hc], ctx->H[hc ^ 1])
                        : launch_dict_update(ctx, ctx->H[hc], ctx->H[hc ^ 1], ctx->split ? ctx->Hlo[hc ^ 1] : nullptr);
       ctx->hcur ^= 1;
+  ctx->ht_stale = true;
+      ctx->ht_stale = true;
     }
     ctx->cur ^= 1;
     enq++;
@@ -759,6 +788,7 @@ int klnmf_dictionary_step(klnmf_ctx *ctx) {
   KL_TRY(ctx->sparse ? launch_dict_update_t(ctx, ctx->H[hc], ctx->H[hc ^ 1])
                      : launch_dict_update(ctx, ctx->H[hc], ctx->H[hc ^ 1], ctx->split ? ctx->Hlo[hc ^ 1] : nullptr));
   ctx->hcur ^= 1;
+  ctx->ht_stale = true;
   KL_TRY(reset_reduction(ctx));
   KL_CUDA(cudaStreamSynchronize(ctx->stream));
   return KLNMF_OK;

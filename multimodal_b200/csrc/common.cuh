@@ -113,6 +113,11 @@ struct klnmf_ctx {
   int64_t prof_cnt[5] = {0, 0, 0, 0, 0};
   bool profile = false;        // per-phase events (adds syncs at the end only)
   void *tc = nullptr;          // tcgen05 engine private state (tensor maps, ...)
+  void *fused = nullptr;       // fused half-step kernel private state
+  void *Ht = nullptr;          // dense TF32 mode, k <= 128: transposed dictionary f x ldht for the fused kernel
+  int64_t ldht = 0;
+  int ht_of = -1;              // which H buffer Ht mirrors (-1: none)
+  bool ht_stale = true;        // the dictionary changed since Ht was written
 };
 
 namespace klnmf {
@@ -144,6 +149,22 @@ int generic_gemm(klnmf_ctx *ctx, int es, int epi, const GemmDesc &d);
 int tc_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d);
 int tc_selftest(int *n_fail, char *report, int report_len);
 void tc_release(klnmf_ctx *ctx);
+
+// ---- fused coefficient half-step (k <= 128, TF32): dense_fused.cu --------------------------------
+struct FusedDesc {
+  int64_t M, F, K;
+  const void *W; int64_t ldw;        // current coefficients M x K (zero padded to ldw)
+  const void *H; int64_t ldh;        // dictionary K x F
+  const void *Ht; int64_t ldht;      // its transpose F x K (zero padded to ldht)
+  const void *X; int64_t ldx;        // data M x F
+  void *Wout; int64_t ldwo;          // updated coefficients
+  double *kl;                        // objective accumulator or nullptr
+  const int *stop;
+  int only_kl;
+};
+bool fused_supported(const klnmf_ctx *ctx);
+int fused_coef_step(klnmf_ctx *ctx, const FusedDesc &d);
+void fused_release(klnmf_ctx *ctx);
 
 // ---- elementwise / reductions: elementwise.cu ----------------------------------------------------
 int launch_dict_update(klnmf_ctx *ctx, const void *H_old, void *H_new, void *Hlo_new);

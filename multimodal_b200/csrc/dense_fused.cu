@@ -1,0 +1,391 @@
+// Fused coefficient half-step of KL-NMF for k <= 128 (tcgen05 / TMEM / TMA, sm_100a):
+//
+//     S = W.H            (nmf.py:336)      first contraction, accumulator in TMEM
+//     Q = (X+eps)/(S+eps), KL += X*log Q - X + S   (nmf.py:325-336, metrics.py:18-20) in the TMEM epilogue
+//     G += Q.H^T         (nmf.py:342)      second contraction, fed from shared memory -- Q never reaches HBM
+//     W' = W (.) G       (nmf.py:343)      final epilogue of the row block
+//
+// One persistent CTA per SM owns row blocks of 128 samples.  The 128 x KP block of W stays in shared memory as
+// the A operand of the first contraction for the whole sweep over the features; the dictionary streams past
+// in steps of 32 features, once as H^T rows (B of S = W.H, K-major over k) and once as H rows (B of
+// G = Q.H^T, K-major over f).  TMEM holds G (KP columns, lives for the whole row block) and two 32-column
+// S buffers, so the ratio epilogue of step j overlaps the first contraction of step j+1 and the second
+// contraction of step j-1.  HBM traffic per iteration: X once + W read + W' written -- the compulsory bytes of
+// SURVEY 8d -- instead of X + 3 x Q of the unfused form.  WRITE_Q (fit): the ratio tile additionally leaves
+// through a TMA store for the dictionary numerator N += W'^T.Q (nmf.py:349), which needs the finished W'.
+//
+//   warp 0      TMA producer : W block per row block; per step the two dictionary tiles
+//   warp 1      MMA issuer   : whole warp walks the loop, one elected lane issues tcgen05.mma / commit
+//   warps 2..9  epilogue     : tcgen05.ld 32x32b.x16 -> ratio / objective -> Q tile (128B-swizzled A operand)
+//   warp 10     X loader     : 128 x 32 chunks of X by TMA into a swizzled ring
+#include <cuda.h>
+
+#include "common.cuh"
+#include "tc_ptx.cuh"
+
+namespace klnmf {
+
+namespace {
+
+constexpr int FBM = 128;                 // samples per row block (UMMA M)
+constexpr int FBN = 32;                  // features per step = one 128-byte swizzle span
+constexpr int F_THREADS = 352;
+constexpr int F_EPI_WARPS = 8;
+constexpr int CHUNK_BYTES = FBM * FBN * 4;   // a 128 x 32 fp32 tile: X chunk, Q tile, one K block of W
+
+template <int KP>
+struct FCfg {
+  static constexpr int KB = KP / 32;                       // K blocks of the first contraction
+  static constexpr int W_BYTES = KB * CHUNK_BYTES;         // resident A operand
+  static constexpr int H1_BYTES = KB * FBN * 32 * 4;       // H^T tile: KB blocks of 32 feature rows x 32 k
+  static constexpr int H2_BYTES = KP * FBN * 4;            // H tile: KP rows x 32 features
+  static constexpr int HSTAGE_BYTES = H1_BYTES + H2_BYTES;
+  static constexpr int XB = KP >= 128 ? 2 : 4;
+  static constexpr int HS = KP >= 128 ? 3 : 4;
+  static constexpr int SMEM_BYTES = W_BYTES + HS * HSTAGE_BYTES + 2 * CHUNK_BYTES + XB * CHUNK_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = KP + 64 <= 128 ? 128 : 256;
+  static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
+};
+
+struct FusedParams {
+  int64_t M, F;
+  int n_blocks, n_steps;
+  const float *W;          // current coefficients (multiplied into G in the final epilogue)
+  int64_t ldw;
+  float *Wout;
+  int64_t ldwo, w_cols;    // columns < w_cols are written (multiple of 16)
+  double *kl;
+  const int *stop;
+  int *err;
+  int only_kl;
+};
+
+__device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld16_wait(uint32_t v[16]) {
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(v[0]), "+r"(v[1]), "+r"(v[2]), "+r"(v[3]), "+r"(v[4]), "+r"(v[5]), "+r"(v[6]), "+r"(v[7]), "+r"(v[8]),
+                 "+r"(v[9]), "+r"(v[10]), "+r"(v[11]), "+r"(v[12]), "+r"(v[13]), "+r"(v[14]), "+r"(v[15])
+               :
+               : "memory");
+}
+
+template <int KP, bool WRITE_Q>
+__global__ void __launch_bounds__(F_THREADS, 1)
+fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmHt,
+                  const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmX,
+                  const __grid_constant__ CUtensorMap tmQ, const FusedParams p) {
+  using C = FCfg<KP>;
+  constexpr int KB = C::KB, HS = C::HS, XB = C::XB;
+  if (p.stop != nullptr && *p.stop != 0) return;
+
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t *smem_gen = smem_raw + (smem_base - smem_u32(smem_raw));
+  const uint32_t w_s = smem_base;
+  const uint32_t h_s = w_s + C::W_BYTES;
+  const uint32_t q_s = h_s + HS * C::HSTAGE_BYTES;
+  const uint32_t x_s = q_s + 2 * CHUNK_BYTES;
+  const uint32_t bar_base = x_s + XB * CHUNK_BYTES;
+  uint8_t *q_gen = smem_gen + (q_s - smem_base);
+  uint8_t *x_gen = smem_gen + (x_s - smem_base);
+  // barriers: w_full | w_empty | g_full | g_empty | h_full[HS] | h_empty[HS] | s_full[2] | s_empty[2] |
+  //           q_full[2] | q_empty[2] | x_full[XB] | x_empty[XB] | tmem_ptr
+  const uint32_t w_full = bar_base, w_empty = bar_base + 8, g_full = bar_base + 16, g_empty = bar_base + 24;
+  auto h_full = [&](int s) { return bar_base + 32u + 8u * s; };
+  auto h_empty = [&](int s) { return bar_base + 32u + 8u * (HS + s); };
+  const uint32_t b2 = bar_base + 32u + 16u * HS;
+  auto s_full = [&](int a) { return b2 + 8u * a; };
+  auto s_empty = [&](int a) { return b2 + 16u + 8u * a; };
+  auto q_full = [&](int a) { return b2 + 32u + 8u * a; };
+  auto q_empty = [&](int a) { return b2 + 48u + 8u * a; };
+  auto x_full = [&](int b) { return b2 + 64u + 8u * b; };
+  auto x_empty = [&](int b) { return b2 + 64u + 8u * (XB + b); };
+  const uint32_t tmem_ptr_addr = b2 + 64u + 16u * XB;
+  volatile uint32_t *tmem_ptr_gen = reinterpret_cast<volatile uint32_t *>(smem_gen + (tmem_ptr_addr - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmHt); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmX);
+    if (WRITE_Q) tma_prefetch_desc(&tmQ);
+    mbar_init(w_full, 1); mbar_init(w_empty, 1); mbar_init(g_full, 1); mbar_init(g_empty, F_EPI_WARPS);
+    for (int s = 0; s < HS; s++) { mbar_init(h_full(s), 1); mbar_init(h_empty(s), 1); }
+    for (int a = 0; a < 2; a++) {
+      mbar_init(s_full(a), 1); mbar_init(s_empty(a), F_EPI_WARPS);
+      mbar_init(q_full(a), F_EPI_WARPS); mbar_init(q_empty(a), 1);
+    }
+    for (int b = 0; b < XB; b++) { mbar_init(x_full(b), 1); mbar_init(x_empty(b), F_EPI_WARPS); }
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<1>(tmem_ptr_addr, C::TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_gen;
+  const uint32_t g_tmem = tmem_base;                 // columns [0, KP)
+  const uint32_t s_tmem = tmem_base + KP;            // two 32-column S buffers
+
+  const int nsteps = p.n_steps;
+
+  if (warp == 0) {
+    // =============================== TMA producer: W block, dictionary tiles ===============================
+    if (lane == 0) {
+      uint32_t hc = 0, rbc = 0;
+      for (int rb = blockIdx.x; rb < p.n_blocks; rb += gridDim.x, rbc++) {
+        mbar_wait(w_empty, (rbc & 1u) ^ 1u, p.err, 1);
+        mbar_expect_tx(w_full, C::W_BYTES);
+        for (int kb = 0; kb < KB; kb++) tma_load_2d(w_s + kb * CHUNK_BYTES, &tmW, w_full, kb * 32, rb * FBM);
+        for (int j = 0; j < nsteps; j++, hc++) {
+          const uint32_t s = hc % HS, ph = (hc / HS) & 1u;
+          mbar_wait(h_empty(s), ph ^ 1u, p.err, 2);
+          mbar_expect_tx(h_full(s), C::HSTAGE_BYTES);
+          const uint32_t dst = h_s + s * C::HSTAGE_BYTES;
+          for (int kb = 0; kb < KB; kb++) tma_load_2d(dst + kb * 4096, &tmHt, h_full(s), kb * 32, j * FBN);
+          tma_load_2d(dst + C::H1_BYTES, &tmH, h_full(s), j * FBN, 0);
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    // instruction descriptors: D=f32, A=B=tf32, both K-major, N>>3, M>>4
+    const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(FBN >> 3) << 17) | ((uint32_t)(FBM >> 4) << 24);
+    const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(KP >> 3) << 17) | ((uint32_t)(FBM >> 4) << 24);
+    const uint32_t hi = desc_hi(1024u, 2u);          // K-major SWIZZLE_128B, 8-row groups 1024 B apart
+    const uint32_t w_lo = desc_lo(w_s, 16u), h_lo = desc_lo(h_s, 16u), q_lo = desc_lo(q_s, 16u);
+    uint32_t c1 = 0, c2 = 0, rbc = 0;                // first / second contractions issued, row blocks done
+    for (int rb = blockIdx.x; rb < p.n_blocks; rb += gridDim.x, rbc++) {
+      mbar_wait(w_full, rbc & 1u, p.err, 3);
+      for (int j = 0; j <= nsteps; j++) {
+        if (j < nsteps) {
+          // ---- S[a] = W . H^T-tile(j) ----
+          const uint32_t s = c1 % HS, a = c1 & 1u;
+          mbar_wait(h_full(s), (c1 / HS) & 1u, p.err, 4);
+          mbar_wait(s_empty(a), ((c1 >> 1) & 1u) ^ 1u, p.err, 5);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t bl = h_lo + ((s * C::HSTAGE_BYTES) >> 4);
+#pragma unroll
+            for (int kb = 0; kb < KB; kb++)
+#pragma unroll
+              for (int kk = 0; kk < 4; kk++)
+                umma_tf32<1>(s_tmem + a * FBN, desc_pack(w_lo + ((kb * CHUNK_BYTES + kk * 32) >> 4), hi),
+                             desc_pack(bl + ((kb * 4096 + kk * 32) >> 4), hi), idesc1, (kb | kk) ? 1u : 0u);
+            umma_commit<1>(s_full(a));
+          }
+          __syncwarp();
+          c1++;
+        }
+        if (j >= 1) {
+          // ---- G += Q(j-1) . H-tile(j-1)^T ----
+          const uint32_t s = c2 % HS, b = c2 & 1u;
+          mbar_wait(q_full(b), (c2 >> 1) & 1u, p.err, 6);
+          if (j == 1) mbar_wait(g_empty, (rbc & 1u) ^ 1u, p.err, 7);
+          tc_fence_after();
+          if (elect_one()) {
+            const uint32_t al = q_lo + ((b * CHUNK_BYTES) >> 4);
+            const uint32_t bl = h_lo + ((s * C::HSTAGE_BYTES + C::H1_BYTES) >> 4);
+#pragma unroll
+            for (int kk = 0; kk < 4; kk++)
+              umma_tf32<1>(g_tmem, desc_pack(al + ((kk * 32) >> 4), hi), desc_pack(bl + ((kk * 32) >> 4), hi), idesc2,
+                           (j > 1 || kk > 0) ? 1u : 0u);
+            umma_commit<1>(h_empty(s));        // dictionary stage free once both of its contractions retired
+            umma_commit<1>(q_empty(b));
+            if (j == nsteps) { umma_commit<1>(g_full); umma_commit<1>(w_empty); }
+          }
+          __syncwarp();
+          c2++;
+        }
+      }
+    }
+  } else if (warp == 10) {
+    // =============================== X loader ===============================
+    if (lane == 0) {
+      uint32_t g = 0;
+      for (int rb = blockIdx.x; rb < p.n_blocks; rb += gridDim.x)
+        for (int j = 0; j < nsteps; j++, g++) {
+          const uint32_t b = g % XB, ph = (g / XB) & 1u;
+          mbar_wait(x_empty(b), ph ^ 1u, p.err, 8);
+          mbar_expect_tx(x_full(b), CHUNK_BYTES);
+          tma_load_2d(x_s + b * CHUNK_BYTES, &tmX, x_full(b), j * FBN, rb * FBM);
+        }
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int e = warp - 2;                 // 0..7
+    const int quarter = warp & 3;           // TMEM lanes this warp may touch: [32*quarter, +32)
+    const int ch = e >> 2;                  // column half: 16 of the 32 columns of a step
+    const int r = quarter * 32 + lane;      // row inside the block = TMEM lane
+    const uint32_t sw = (uint32_t)(r & 7);
+    const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
+    uint32_t c = 0, rbc = 0;
+    double kl = 0.0;
+    for (int rb = blockIdx.x; rb < p.n_blocks; rb += gridDim.x, rbc++) {
+      float kl_blk = 0.f;
+#pragma unroll 1
+      for (int j = 0; j < nsteps; j++, c++) {
+        const uint32_t a = c & 1u, ph2 = (c >> 1) & 1u, xb = c % XB, phx = (c / XB) & 1u;
+        mbar_wait(s_full(a), ph2, p.err, 9);
+        tc_fence_after();
+        uint32_t v[16];
+        tmem_ld16_issue(s_tmem + lane_addr + a * FBN + ch * 16, v);
+        mbar_wait(x_full(xb), phx, p.err, 10);
+        float x[16];
+        const uint8_t *xrow = x_gen + xb * CHUNK_BYTES + r * 128;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+          const float4 t = *reinterpret_cast<const float4 *>(xrow + (((uint32_t)(4 * ch + i) ^ sw) << 4));
+          x[4 * i] = t.x; x[4 * i + 1] = t.y; x[4 * i + 2] = t.z; x[4 * i + 3] = t.w;
+        }
+        tmem_ld16_wait(v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive_relaxed(s_empty(a)); mbar_arrive(x_empty(xb)); }
+        // rows >= M and columns >= F hold x = 0, s = 0 (TMA zero fill): q = 1, the term is exactly 0 and the
+        // zero-filled dictionary columns keep it out of G
+        float part0 = 0.f, part1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < 16; i += 2) {
+          float q0, q1;
+          part0 += ratio_term<false>(x[i], __uint_as_float(v[i]), q0);
+          part1 += ratio_term<false>(x[i + 1], __uint_as_float(v[i + 1]), q1);
+          x[i] = q0; x[i + 1] = q1;
+        }
+        kl_blk += part0 + part1;
+        if (!p.only_kl) {
+          mbar_wait(q_empty(a), ph2 ^ 1u, p.err, 11);
+          uint8_t *qrow = q_gen + a * CHUNK_BYTES + r * 128;
+#pragma unroll
+          for (int i = 0; i < 4; i++)
+            *reinterpret_cast<float4 *>(qrow + (((uint32_t)(4 * ch + i) ^ sw) << 4)) =
+                make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+          fence_proxy_async();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(q_full(a));
+        } else {
+          // objective only: keep the issuer's protocol alive without producing Q
+          __syncwarp();
+          if (lane == 0) mbar_arrive(q_full(a));
+        }
+      }
+      kl += (double)kl_blk;
+      // ---- final epilogue of the row block: W' = W (.) G ----
+      mbar_wait(g_full, rbc & 1u, p.err, 12);
+      tc_fence_after();
+      const int64_t row = (int64_t)rb * FBM + r;
+#pragma unroll 1
+      for (int cc = 0; cc < KP / 32; cc++) {
+        const int col0 = ch * (KP / 2) + cc * 16;
+        uint32_t v[16];
+        tmem_ld16_issue(g_tmem + lane_addr + col0, v);
+        tmem_ld16_wait(v);
+        if (!p.only_kl && row < p.M && col0 < p.w_cols) {
+          const float *wi = p.W + row * p.ldw + col0;
+          float *wo = p.Wout + row * p.ldwo + col0;
+#pragma unroll
+          for (int i = 0; i < 4; i++) {
+            const float4 w = __ldg(reinterpret_cast<const float4 *>(wi + 4 * i));
+            *reinterpret_cast<float4 *>(wo + 4 * i) =
+                make_float4(w.x * __uint_as_float(v[4 * i]), w.y * __uint_as_float(v[4 * i + 1]),
+                            w.z * __uint_as_float(v[4 * i + 2]), w.w * __uint_as_float(v[4 * i + 3]));
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_relaxed(g_empty);
+    }
+    if (p.kl != nullptr) {
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) kl += __shfl_xor_sync(0xffffffffu, kl, o);
+      if (lane == 0) atomicAdd(p.kl, kl);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc<1>(tmem_base, C::TMEM_COLS);
+  }
+}
+
+struct FusedState {
+  int *err_dev = nullptr;
+};
+
+template <int KP>
+int launch_fused(klnmf_ctx *ctx, const FusedDesc &d, FusedParams p) {
+  using C = FCfg<KP>;
+  CUtensorMap tmW, tmHt, tmH, tmX, tmQ;
+  // every operand is K-major with 128B swizzle; extents are the stored (zero padded) ones, everything beyond
+  // them is zero-filled by TMA
+  KL_TRY(make_map(&tmW, d.W, d.ldw, d.M, d.ldw, FBM, false));        // box 32 k x 128 rows
+  KL_TRY(make_map(&tmHt, d.Ht, d.ldht, d.F, d.ldht, 32, false));     // box 32 k x 32 feature rows
+  KL_TRY(make_map(&tmH, d.H, d.F, d.K, d.ldh, KP, false));           // box 32 features x KP rows
+  KL_TRY(make_map(&tmX, d.X, d.F, d.M, d.ldx, FBM, false));          // box 32 features x 128 rows
+  tmQ = tmX;
+  p.n_blocks = (int)ceil_div(d.M, FBM);
+  p.n_steps = (int)ceil_div(d.F, FBN);
+  if (p.n_blocks == 0 || p.n_steps == 0) return KLNMF_OK;
+  const int grid = p.n_blocks < ctx->sm_count ? p.n_blocks : ctx->sm_count;
+  auto kern = fused_coef_kernel<KP, false>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    KL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
+    attr_done = true;
+  }
+  kern<<<grid, F_THREADS, C::SMEM_BYTES, ctx->stream>>>(tmW, tmHt, tmH, tmX, tmQ, p);
+  ctx->n_launch++;
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
+}  // namespace
+
+bool fused_supported(const klnmf_ctx *ctx) {
+  const bool off = getenv("KLNMF_FUSED") && atoi(getenv("KLNMF_FUSED")) == 0;   // read per call: tests toggle it
+  return !off && ctx->mode == KLNMF_MODE_TF32 && !ctx->sparse && !ctx->debug_simt && ctx->k <= 128;
+}
+
+int fused_coef_step(klnmf_ctx *ctx, const FusedDesc &d) {
+  if (d.M <= 0) return KLNMF_OK;
+  FusedState *st = (FusedState *)ctx->fused;
+  if (!st) {
+    st = new FusedState();
+    if (cudaMalloc((void **)&st->err_dev, 4) != cudaSuccess) {
+      delete st;
+      set_error("fused_coef_step: cudaMalloc failed");
+      return KLNMF_ENOMEM;
+    }
+    cudaMemsetAsync(st->err_dev, 0, 4, ctx->stream);
+    ctx->fused = st;
+  }
+  KL_CHECK(d.K <= 128 && d.ldw % 32 == 0 && d.ldht % 32 == 0, KLNMF_EINVAL, "fused_coef_step: k=%lld not supported",
+           (long long)d.K);
+  FusedParams p{};
+  p.M = d.M; p.F = d.F;
+  p.W = (const float *)d.W; p.ldw = d.ldw;
+  p.Wout = (float *)d.Wout; p.ldwo = d.ldwo;
+  p.w_cols = d.ldw < d.ldwo ? d.ldw : d.ldwo;
+  p.kl = d.kl; p.stop = d.stop; p.err = st->err_dev; p.only_kl = d.only_kl;
+  if (d.K <= 64) return launch_fused<64>(ctx, d, p);
+  return launch_fused<128>(ctx, d, p);
+}
+
+void fused_release(klnmf_ctx *ctx) {
+  FusedState *st = (FusedState *)ctx->fused;
+  if (!st) return;
+  if (st->err_dev) cudaFree(st->err_dev);
+  delete st;
+  ctx->fused = nullptr;
+}
+
+}  // namespace klnmf

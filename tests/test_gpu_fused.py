@@ -1,0 +1,77 @@
+"""-m gpu: the fused coefficient half-step (dense_fused.cu: S = W.H -> Q in the TMEM epilogue -> G += Q.H^T
+without writing Q to HBM) against the float64 oracle's transform (nmf.py:275-291, 325-343) and against the
+unfused three-kernel form of the same mode, on ragged shapes and both k paddings (64, 128)."""
+import os
+
+import numpy as np
+import pytest
+
+from multimodal_b200 import _native
+from oracle import cases, klnmf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+SHAPES = [
+    (128, 32, 8),        # one row block, one step
+    (700, 1000, 50),     # ragged rows / features, k padded to 64
+    (513, 333, 100),     # k padded to 128, features not a multiple of 32
+    (4096, 2048, 128),   # many row blocks per CTA: barrier phases wrap, TMEM accumulator is reused
+    (300, 4100, 33),     # long feature sweep
+]
+
+
+def run_transform(X, H, iters, fused):
+    os.environ["KLNMF_FUSED"] = "1" if fused else "0"
+    try:
+        n, f = X.shape
+        with _native.Engine(n, f, H.shape[0], mode="tf32") as e:
+            e.set_dense(X)
+            e.set_dictionary(H)
+            e.init_coefficients()
+            c0 = e.counters()["launches"]
+            errs, _ = e.run(iters, 0.0, False)
+            launches = e.counters()["launches"] - c0
+            return e.get_coefficients(), np.asarray(errs), launches
+    finally:
+        os.environ.pop("KLNMF_FUSED", None)
+
+
+@pytest.mark.parametrize("n,f,k", SHAPES)
+def test_fused_transform_matches_oracle_and_unfused(n, f, k):
+    rs = np.random.RandomState(n + f + k)
+    X = rs.random_sample((n, f))
+    X[rs.random_sample((n, f)) < 0.2] = 0.0          # exact zeros: q = eps/(s+eps) there (nmf.py:336)
+    np.random.seed(5)
+    H = O.init_dictionary(k, f)
+    iters = 6
+    W_ref = np.asarray(X.dot(H.T))
+    errs_ref = []
+    for _ in range(iters):
+        errs_ref.append(O.error(X, W_ref, H))
+        W_ref, _ = O.update(X, W_ref, H, fit=False)
+    Wf, ef, lf = run_transform(X, H, iters, True)
+    Wu, eu, lu = run_transform(X, H, iters, False)
+    assert lf < lu, "the fused path must be the one that ran (one kernel per iteration)"
+    assert np.isfinite(Wf).all()
+    # stated tolerance of the single-pass TF32 mode (tests/test_gpu_parity.py): 3e-3 on W, 1e-2 on the objective
+    assert cases.rel_fro(Wf, W_ref) < 3e-3, cases.rel_fro(Wf, W_ref)
+    np.testing.assert_allclose(ef, errs_ref, rtol=1e-2)
+    # fused and unfused run the same arithmetic up to the order of the FP32 accumulation
+    assert cases.rel_fro(Wf, Wu) < 1e-3, cases.rel_fro(Wf, Wu)
+    np.testing.assert_allclose(ef, eu, rtol=1e-4)
+
+
+def test_fused_transform_through_the_estimator():
+    # the public API takes the fused path for transform in tf32 mode (k <= 128)
+    from multimodal_b200.lib.nmf import KLdivNMF
+    rs = np.random.RandomState(0)
+    X = rs.random_sample((257, 190))
+    np.random.seed(1)
+    H = O.init_dictionary(20, 190)
+    est = KLdivNMF(n_components=20, max_iter=25, tol=0, mode="tf32")
+    est.components_ = H
+    W = est.transform(X)
+    W_ref = np.asarray(X.dot(H.T))
+    for _ in range(25):
+        W_ref, _ = O.update(X, W_ref, H, fit=False)
+    assert cases.rel_fro(W, W_ref) < 3e-3
