@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--mode", default=os.environ.get("KLNMF_BENCH_MODE", "tf32"))
     ap.add_argument("--workload", default=os.environ.get("KLNMF_BENCH_WORKLOAD", "cfg5"), choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="override the total sample count (development only)")
+    ap.add_argument("--k", type=int, default=0, help="override the number of components (development only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--alt-mode", default=os.environ.get("KLNMF_BENCH_ALT", "tf32x3"),
@@ -232,10 +233,15 @@ def ncu_traffic(kernel_key, rows_per_launch, f, k, mode):
     the SAME launch shape counts; anything else is reported as null."""
     p = os.path.join(ROOT, "profiles", "ncu_traffic.json")
     try:
+        best = None
         for e in json.load(open(p)):
-            if (e["kernel"] == kernel_key and e["rows"] == rows_per_launch and e["f"] == f and e["k"] == k
-                    and e["mode"] == mode):
-                return e["dram_bytes"]
+            if e["kernel"] == kernel_key and e["f"] == f and e["k"] == k and e["mode"] == mode:
+                if best is None or abs(e["rows"] - rows_per_launch) < abs(best["rows"] - rows_per_launch):
+                    best = e
+        if best is not None:
+            # every byte of these kernels scales with the rows of the launch (X, Q, W panels; the dictionary is
+            # 16.8 MB): a capture at the panel size is scaled to the average launch of this run
+            return best["dram_bytes"] * rows_per_launch / float(best["rows"])
     except Exception:
         pass
     return None
@@ -258,6 +264,13 @@ def phase_roofline(ms, cnt, n_local, f, k, kind, steps, peaks, mode):
     dom = max(names, key=lambda p: ms[p])
     launches = max(cnt[dom], 1)
     flops_per_launch = 2.0 * n_local * k * f * steps / launches        # each contraction is 2 n k f per iteration
+    fused = kind == "dense_transform" and mode == "tf32" and k <= 128 and os.environ.get("KLNMF_FUSED", "1") != "0"
+    if fused:
+        # one kernel per iteration does both contractions of the transform (dense_fused.cu): 4 n k f
+        names["ratio"] = "fused_coef_kernel<S=W.H -> Q=(X+eps)/(S+eps), KL -> G+=Q.H^T -> W'=W(.)G>"
+        dom = "ratio"
+        launches = max(cnt[dom], 1)
+        flops_per_launch = 4.0 * n_local * k * f * steps / launches
     avg_s = ms[dom] / launches * 1e-3
     ach = flops_per_launch / avg_s / 1e12
     peak = peaks["bf16_sustained"] / 2.0                                 # TF32 dense = half the BF16 rate
@@ -265,7 +278,7 @@ def phase_roofline(ms, cnt, n_local, f, k, kind, steps, peaks, mode):
         peak = 40.0
     rows_per_launch = int(round(n_local * steps / float(launches)))
     r = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-         "traffic": ncu_traffic(dom, rows_per_launch, f, k, mode), "rows_per_launch": rows_per_launch,
+         "traffic": ncu_traffic("fused" if fused else dom, rows_per_launch, f, k, mode), "rows_per_launch": rows_per_launch,
          "kernel": names[dom], "avg_launch_ms": ms[dom] / launches, "launches": launches,
          "peak_source": ("TF32 = 1/2 x sustained cuBLAS bf16, " + peaks["source"]) if mode != "fp64" else "nominal B200 FP64",
          "phase_ms_per_step": {p: ms[p] / max(steps, 1) for p in ("ratio", "coefficient", "numerator", "dictionary", "allreduce")}}
@@ -311,6 +324,9 @@ def run_ours(args):
     if args.n:
         n_total = args.n
         desc += " [n overridden to %d]" % n_total
+    if args.k:
+        k = args.k
+        desc += " [k overridden to %d]" % k
     bounds = D.shard_bounds(n_total, world)
     n_local = bounds[rank + 1] - bounds[rank]
     fit = kind != "dense_transform"
