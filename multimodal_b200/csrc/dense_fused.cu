@@ -16,7 +16,8 @@
 //
 //   warp 0      TMA producer : W block per row block; per step the two dictionary tiles
 //   warp 1      MMA issuer   : whole warp walks the loop, one elected lane issues tcgen05.mma / commit
-//   warps 2..9  epilogue     : tcgen05.ld 32x32b.x16 -> ratio / objective -> Q tile (128B-swizzled A operand)
+//   warps 2..9  epilogue     : two groups on alternate steps: tcgen05.ld 32x32b.x32 -> ratio / objective -> Q tile
+//                              (128B-swizzled A operand of the second contraction)
 //   warp 10     X loader     : 128 x 32 chunks of X by TMA into a swizzled ring
 #include <cuda.h>
 
@@ -33,17 +34,24 @@ constexpr int F_THREADS = 352;
 constexpr int F_EPI_WARPS = 8;
 constexpr int CHUNK_BYTES = FBM * FBN * 4;   // a 128 x 32 fp32 tile: X chunk, Q tile, one K block of W
 
-template <int KP>
+// TSW: the W block lives in TMEM (A operand of the first contraction read from tensor memory, "TS" form of
+// tcgen05.mma) instead of shared memory: no 4 KB shared-memory read of A per N = 32 instruction, and its
+// 64 KB go to dictionary stages.
+template <int KP, bool TSW, int V = 0>
 struct FCfg {
   static constexpr int KB = KP / 32;                       // K blocks of the first contraction
-  static constexpr int W_BYTES = KB * CHUNK_BYTES;         // resident A operand
+  static constexpr int W_BYTES = TSW ? 0 : KB * CHUNK_BYTES;   // resident A operand
   static constexpr int H1_BYTES = KB * FBN * 32 * 4;       // H^T tile: KB blocks of 32 feature rows x 32 k
   static constexpr int H2_BYTES = KP * FBN * 4;            // H tile: KP rows x 32 features
   static constexpr int HSTAGE_BYTES = H1_BYTES + H2_BYTES;
-  static constexpr int XB = KP >= 128 ? 2 : 4;
-  static constexpr int HS = KP >= 128 ? 3 : 4;
+  // the X ring has to cover the HBM latency by itself: 44 GB/s per SM x ~2 us = 88 KB in flight at the HBM
+  // roofline, so every byte the operands do not need goes to X chunks (16 KB each)
+  // V = 1 (k > 64, W in TMEM): five dictionary stages and a two-chunk X ring instead of four and four
+  static constexpr int HS = KP >= 128 ? (TSW ? (V ? 5 : 4) : 3) : (TSW ? 6 : 4);
+  static constexpr int XB = KP >= 128 ? (TSW ? (V ? 2 : 4) : 2) : (TSW ? 6 : 6);
   static constexpr int SMEM_BYTES = W_BYTES + HS * HSTAGE_BYTES + 2 * CHUNK_BYTES + XB * CHUNK_BYTES + 1024 + 256;
-  static constexpr int TMEM_COLS = KP + 64 <= 128 ? 128 : 256;
+  static constexpr int TMEM_USED = KP + 64 + (TSW ? KP : 0);
+  static constexpr int TMEM_COLS = TMEM_USED <= 128 ? 128 : (TMEM_USED <= 256 ? 256 : 512);
   static_assert(SMEM_BYTES <= 232448, "shared memory budget exceeded");
 };
 
@@ -58,6 +66,7 @@ struct FusedParams {
   const int *stop;
   int *err;
   int only_kl;
+  int lookahead;           // steps the first contraction runs ahead of the second one (1 or 2)
 };
 
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t v[16]) {
@@ -77,12 +86,31 @@ __device__ __forceinline__ void tmem_ld16_wait(uint32_t v[16]) {
                : "memory");
 }
 
-template <int KP, bool WRITE_Q>
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t v[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]), "r"(v[9]),
+      "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// D[tmem] (+)= A[tmem] . B[smem]: the A operand (M lanes x 8 columns of 32-bit K elements) comes from TMEM
+__device__ __forceinline__ void umma_tf32_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t acc) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(acc)
+      : "memory");
+}
+
+template <int KP, bool WRITE_Q, bool TSW, int V>
 __global__ void __launch_bounds__(F_THREADS, 1)
 fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant__ CUtensorMap tmHt,
                   const __grid_constant__ CUtensorMap tmH, const __grid_constant__ CUtensorMap tmX,
                   const __grid_constant__ CUtensorMap tmQ, const FusedParams p) {
-  using C = FCfg<KP>;
+  using C = FCfg<KP, TSW, V>;
   constexpr int KB = C::KB, HS = C::HS, XB = C::XB;
   if (p.stop != nullptr && *p.stop != 0) return;
 
@@ -116,13 +144,13 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmW); tma_prefetch_desc(&tmHt); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmX);
     if (WRITE_Q) tma_prefetch_desc(&tmQ);
-    mbar_init(w_full, 1); mbar_init(w_empty, 1); mbar_init(g_full, 1); mbar_init(g_empty, F_EPI_WARPS);
+    mbar_init(w_full, TSW ? F_EPI_WARPS : 1); mbar_init(w_empty, 1); mbar_init(g_full, 1); mbar_init(g_empty, F_EPI_WARPS);
     for (int s = 0; s < HS; s++) { mbar_init(h_full(s), 1); mbar_init(h_empty(s), 1); }
     for (int a = 0; a < 2; a++) {
-      mbar_init(s_full(a), 1); mbar_init(s_empty(a), F_EPI_WARPS);
-      mbar_init(q_full(a), F_EPI_WARPS); mbar_init(q_empty(a), 1);
+      mbar_init(s_full(a), 1); mbar_init(s_empty(a), F_EPI_WARPS / 2);
+      mbar_init(q_full(a), F_EPI_WARPS / 2); mbar_init(q_empty(a), 1);
     }
-    for (int b = 0; b < XB; b++) { mbar_init(x_full(b), 1); mbar_init(x_empty(b), F_EPI_WARPS); }
+    for (int b = 0; b < XB; b++) { mbar_init(x_full(b), 1); mbar_init(x_empty(b), F_EPI_WARPS / 2); }
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<1>(tmem_ptr_addr, C::TMEM_COLS);
@@ -132,6 +160,7 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
   const uint32_t tmem_base = *tmem_ptr_gen;
   const uint32_t g_tmem = tmem_base;                 // columns [0, KP)
   const uint32_t s_tmem = tmem_base + KP;            // two 32-column S buffers
+  const uint32_t w_tmem = tmem_base + KP + 64;       // TSW: the W block, KP columns
 
   const int nsteps = p.n_steps;
 
@@ -140,9 +169,11 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     if (lane == 0) {
       uint32_t hc = 0, rbc = 0;
       for (int rb = blockIdx.x; rb < p.n_blocks; rb += gridDim.x, rbc++) {
-        mbar_wait(w_empty, (rbc & 1u) ^ 1u, p.err, 1);
-        mbar_expect_tx(w_full, C::W_BYTES);
-        for (int kb = 0; kb < KB; kb++) tma_load_2d(w_s + kb * CHUNK_BYTES, &tmW, w_full, kb * 32, rb * FBM);
+        if (!TSW) {
+          mbar_wait(w_empty, (rbc & 1u) ^ 1u, p.err, 1);
+          mbar_expect_tx(w_full, C::W_BYTES);
+          for (int kb = 0; kb < KB; kb++) tma_load_2d(w_s + kb * CHUNK_BYTES, &tmW, w_full, kb * 32, rb * FBM);
+        }
         for (int j = 0; j < nsteps; j++, hc++) {
           const uint32_t s = hc % HS, ph = (hc / HS) & 1u;
           mbar_wait(h_empty(s), ph ^ 1u, p.err, 2);
@@ -163,7 +194,12 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     uint32_t c1 = 0, c2 = 0, rbc = 0;                // first / second contractions issued, row blocks done
     for (int rb = blockIdx.x; rb < p.n_blocks; rb += gridDim.x, rbc++) {
       mbar_wait(w_full, rbc & 1u, p.err, 3);
-      for (int j = 0; j <= nsteps; j++) {
+      if (TSW) tc_fence_after();
+      // the first contraction runs LA steps ahead of the second one: with LA = 2, S(j+2) only needs the S buffer
+      // back (released as soon as epilogue j has read it), not the end of epilogue j -- at the price of one more
+      // dictionary stage in flight
+      const int LA = p.lookahead;
+      for (int j = 0; j < nsteps + LA; j++) {
         if (j < nsteps) {
           // ---- S[a] = W . H^T-tile(j) ----
           const uint32_t s = c1 % HS, a = c1 & 1u;
@@ -175,19 +211,22 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 #pragma unroll
             for (int kb = 0; kb < KB; kb++)
 #pragma unroll
-              for (int kk = 0; kk < 4; kk++)
-                umma_tf32<1>(s_tmem + a * FBN, desc_pack(w_lo + ((kb * CHUNK_BYTES + kk * 32) >> 4), hi),
-                             desc_pack(bl + ((kb * 4096 + kk * 32) >> 4), hi), idesc1, (kb | kk) ? 1u : 0u);
+              for (int kk = 0; kk < 4; kk++) {
+                const uint64_t db = desc_pack(bl + ((kb * 4096 + kk * 32) >> 4), hi);
+                if (TSW) umma_tf32_ts(s_tmem + a * FBN, w_tmem + kb * 32 + kk * 8, db, idesc1, (kb | kk) ? 1u : 0u);
+                else umma_tf32<1>(s_tmem + a * FBN, desc_pack(w_lo + ((kb * CHUNK_BYTES + kk * 32) >> 4), hi), db, idesc1,
+                                  (kb | kk) ? 1u : 0u);
+              }
             umma_commit<1>(s_full(a));
           }
           __syncwarp();
           c1++;
         }
-        if (j >= 1) {
-          // ---- G += Q(j-1) . H-tile(j-1)^T ----
+        if (j >= LA) {
+          // ---- G += Q(j-LA) . H-tile(j-LA)^T ----
           const uint32_t s = c2 % HS, b = c2 & 1u;
           mbar_wait(q_full(b), (c2 >> 1) & 1u, p.err, 6);
-          if (j == 1) mbar_wait(g_empty, (rbc & 1u) ^ 1u, p.err, 7);
+          if (j == LA) mbar_wait(g_empty, (rbc & 1u) ^ 1u, p.err, 7);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t al = q_lo + ((b * CHUNK_BYTES) >> 4);
@@ -195,10 +234,10 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 #pragma unroll
             for (int kk = 0; kk < 4; kk++)
               umma_tf32<1>(g_tmem, desc_pack(al + ((kk * 32) >> 4), hi), desc_pack(bl + ((kk * 32) >> 4), hi), idesc2,
-                           (j > 1 || kk > 0) ? 1u : 0u);
+                           (j > LA || kk > 0) ? 1u : 0u);
             umma_commit<1>(h_empty(s));        // dictionary stage free once both of its contractions retired
             umma_commit<1>(q_empty(b));
-            if (j == nsteps) { umma_commit<1>(g_full); umma_commit<1>(w_empty); }
+            if (j == nsteps + LA - 1) { umma_commit<1>(g_full); umma_commit<1>(w_empty); }
           }
           __syncwarp();
           c2++;
@@ -219,9 +258,12 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     }
   } else {
     // =============================== epilogue ===============================
+    // Two groups of four warps (one warp per TMEM lane quarter) take alternate steps, so that the MUFU-bound
+    // arithmetic of one group overlaps the TMEM / barrier latencies of the other.  Group g owns S buffer g and
+    // Q buffer g.
     const int e = warp - 2;                 // 0..7
     const int quarter = warp & 3;           // TMEM lanes this warp may touch: [32*quarter, +32)
-    const int ch = e >> 2;                  // column half: 16 of the 32 columns of a step
+    const int grp = e >> 2;
     const int r = quarter * 32 + lane;      // row inside the block = TMEM lane
     const uint32_t sw = (uint32_t)(r & 7);
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
@@ -229,30 +271,59 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     double kl = 0.0;
     for (int rb = blockIdx.x; rb < p.n_blocks; rb += gridDim.x, rbc++) {
       float kl_blk = 0.f;
-#pragma unroll 1
-      for (int j = 0; j < nsteps; j++, c++) {
-        const uint32_t a = c & 1u, ph2 = (c >> 1) & 1u, xb = c % XB, phx = (c / XB) & 1u;
-        mbar_wait(s_full(a), ph2, p.err, 9);
+      if (TSW) {
+        // ---- the W block of this row block goes to TMEM: lane = row, column = component ----
+        mbar_wait(w_empty, (rbc & 1u) ^ 1u, p.err, 13);     // first contractions of the previous block retired
         tc_fence_after();
-        uint32_t v[16];
-        tmem_ld16_issue(s_tmem + lane_addr + a * FBN + ch * 16, v);
-        mbar_wait(x_full(xb), phx, p.err, 10);
-        float x[16];
-        const uint8_t *xrow = x_gen + xb * CHUNK_BYTES + r * 128;
+        const int64_t row = (int64_t)rb * FBM + r;
+#pragma unroll 1
+        for (int cc = 0; cc < KP / 32; cc++) {
+          const int col0 = grp * (KP / 2) + cc * 16;
+          uint32_t wv[16];
+          if (row < p.M && col0 < p.ldw) {
+            const float *wi = p.W + row * p.ldw + col0;
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const float4 t = *reinterpret_cast<const float4 *>(xrow + (((uint32_t)(4 * ch + i) ^ sw) << 4));
-          x[4 * i] = t.x; x[4 * i + 1] = t.y; x[4 * i + 2] = t.z; x[4 * i + 3] = t.w;
+            for (int i = 0; i < 4; i++) {
+              const float4 w = __ldg(reinterpret_cast<const float4 *>(wi + 4 * i));
+              wv[4 * i] = __float_as_uint(w.x); wv[4 * i + 1] = __float_as_uint(w.y);
+              wv[4 * i + 2] = __float_as_uint(w.z); wv[4 * i + 3] = __float_as_uint(w.w);
+            }
+          } else {
+#pragma unroll
+            for (int i = 0; i < 16; i++) wv[i] = 0u;
+          }
+          tmem_st16(w_tmem + lane_addr + col0, wv);
         }
-        tmem_ld16_wait(v);
+        tmem_st_wait();
         tc_fence_before();
         __syncwarp();
-        if (lane == 0) { mbar_arrive_relaxed(s_empty(a)); mbar_arrive(x_empty(xb)); }
+        if (lane == 0) mbar_arrive(w_full);
+      }
+#pragma unroll 1
+      for (int j = 0; j < nsteps; j++, c++) {
+        if ((int)(c & 1u) != grp) continue;
+        const uint32_t ph2 = (c >> 1) & 1u, xb = c % XB, phx = (c / XB) & 1u;
+        mbar_wait(s_full(grp), ph2, p.err, 9);
+        tc_fence_after();
+        uint32_t v[32];
+        tmem_ld32_issue(s_tmem + lane_addr + grp * FBN, v);
+        mbar_wait(x_full(xb), phx, p.err, 10);
+        float x[32];
+        const uint8_t *xrow = x_gen + xb * CHUNK_BYTES + r * 128;
+#pragma unroll
+        for (int i = 0; i < 8; i++) {
+          const float4 t = *reinterpret_cast<const float4 *>(xrow + (((uint32_t)i ^ sw) << 4));
+          x[4 * i] = t.x; x[4 * i + 1] = t.y; x[4 * i + 2] = t.z; x[4 * i + 3] = t.w;
+        }
+        tmem_ld32_wait(v);
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) { mbar_arrive_relaxed(s_empty(grp)); mbar_arrive(x_empty(xb)); }
         // rows >= M and columns >= F hold x = 0, s = 0 (TMA zero fill): q = 1, the term is exactly 0 and the
         // zero-filled dictionary columns keep it out of G
         float part0 = 0.f, part1 = 0.f;
 #pragma unroll
-        for (int i = 0; i < 16; i += 2) {
+        for (int i = 0; i < 32; i += 2) {
           float q0, q1;
           part0 += ratio_term<false>(x[i], __uint_as_float(v[i]), q0);
           part1 += ratio_term<false>(x[i + 1], __uint_as_float(v[i + 1]), q1);
@@ -260,29 +331,25 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         }
         kl_blk += part0 + part1;
         if (!p.only_kl) {
-          mbar_wait(q_empty(a), ph2 ^ 1u, p.err, 11);
-          uint8_t *qrow = q_gen + a * CHUNK_BYTES + r * 128;
+          mbar_wait(q_empty(grp), ph2 ^ 1u, p.err, 11);
+          uint8_t *qrow = q_gen + grp * CHUNK_BYTES + r * 128;
 #pragma unroll
-          for (int i = 0; i < 4; i++)
-            *reinterpret_cast<float4 *>(qrow + (((uint32_t)(4 * ch + i) ^ sw) << 4)) =
+          for (int i = 0; i < 8; i++)
+            *reinterpret_cast<float4 *>(qrow + (((uint32_t)i ^ sw) << 4)) =
                 make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
           fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(q_full(a));
-        } else {
-          // objective only: keep the issuer's protocol alive without producing Q
-          __syncwarp();
-          if (lane == 0) mbar_arrive(q_full(a));
         }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(q_full(grp));
       }
       kl += (double)kl_blk;
-      // ---- final epilogue of the row block: W' = W (.) G ----
+      // ---- final epilogue of the row block: W' = W (.) G, each group one half of the columns ----
       mbar_wait(g_full, rbc & 1u, p.err, 12);
       tc_fence_after();
       const int64_t row = (int64_t)rb * FBM + r;
 #pragma unroll 1
       for (int cc = 0; cc < KP / 32; cc++) {
-        const int col0 = ch * (KP / 2) + cc * 16;
+        const int col0 = grp * (KP / 2) + cc * 16;
         uint32_t v[16];
         tmem_ld16_issue(g_tmem + lane_addr + col0, v);
         tmem_ld16_wait(v);
@@ -321,9 +388,9 @@ struct FusedState {
   int *err_dev = nullptr;
 };
 
-template <int KP>
+template <int KP, bool TSW, int V = 0>
 int launch_fused(klnmf_ctx *ctx, const FusedDesc &d, FusedParams p) {
-  using C = FCfg<KP>;
+  using C = FCfg<KP, TSW, V>;
   CUtensorMap tmW, tmHt, tmH, tmX, tmQ;
   // every operand is K-major with 128B swizzle; extents are the stored (zero padded) ones, everything beyond
   // them is zero-filled by TMA
@@ -336,7 +403,7 @@ int launch_fused(klnmf_ctx *ctx, const FusedDesc &d, FusedParams p) {
   p.n_steps = (int)ceil_div(d.F, FBN);
   if (p.n_blocks == 0 || p.n_steps == 0) return KLNMF_OK;
   const int grid = p.n_blocks < ctx->sm_count ? p.n_blocks : ctx->sm_count;
-  auto kern = fused_coef_kernel<KP, false>;
+  auto kern = fused_coef_kernel<KP, false, TSW, V>;
   static bool attr_done = false;
   if (!attr_done) {
     KL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -376,8 +443,14 @@ int fused_coef_step(klnmf_ctx *ctx, const FusedDesc &d) {
   p.Wout = (float *)d.Wout; p.ldwo = d.ldwo;
   p.w_cols = d.ldw < d.ldwo ? d.ldw : d.ldwo;
   p.kl = d.kl; p.stop = d.stop; p.err = st->err_dev; p.only_kl = d.only_kl;
-  if (d.K <= 64) return launch_fused<64>(ctx, d, p);
-  return launch_fused<128>(ctx, d, p);
+  // default: W block in TMEM ("TS" form of tcgen05.mma); KLNMF_FUSED_TS=0 keeps it in shared memory
+  const bool ts = !(getenv("KLNMF_FUSED_TS") && atoi(getenv("KLNMF_FUSED_TS")) == 0);
+  const int v = getenv("KLNMF_FUSED_V") ? atoi(getenv("KLNMF_FUSED_V")) : 0;
+  p.lookahead = d.K <= 64 && ts ? 2 : 1;
+  if (getenv("KLNMF_FUSED_LA")) p.lookahead = atoi(getenv("KLNMF_FUSED_LA")) == 2 ? 2 : 1;
+  if (d.K <= 64) return ts ? launch_fused<64, true>(ctx, d, p) : launch_fused<64, false>(ctx, d, p);
+  if (ts && v == 1) return launch_fused<128, true, 1>(ctx, d, p);
+  return ts ? launch_fused<128, true>(ctx, d, p) : launch_fused<128, false>(ctx, d, p);
 }
 
 void fused_release(klnmf_ctx *ctx) {

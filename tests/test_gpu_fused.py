@@ -20,8 +20,9 @@ SHAPES = [
 ]
 
 
-def run_transform(X, H, iters, fused):
+def run_transform(X, H, iters, fused, ts=False):
     os.environ["KLNMF_FUSED"] = "1" if fused else "0"
+    os.environ["KLNMF_FUSED_TS"] = "1" if ts else "0"
     try:
         n, f = X.shape
         with _native.Engine(n, f, H.shape[0], mode="tf32") as e:
@@ -34,10 +35,12 @@ def run_transform(X, H, iters, fused):
             return e.get_coefficients(), np.asarray(errs), launches
     finally:
         os.environ.pop("KLNMF_FUSED", None)
+        os.environ.pop("KLNMF_FUSED_TS", None)
 
 
+@pytest.mark.parametrize("ts", [False, True], ids=["w_in_smem", "w_in_tmem"])
 @pytest.mark.parametrize("n,f,k", SHAPES)
-def test_fused_transform_matches_oracle_and_unfused(n, f, k):
+def test_fused_transform_matches_oracle_and_unfused(n, f, k, ts):
     rs = np.random.RandomState(n + f + k)
     X = rs.random_sample((n, f))
     X[rs.random_sample((n, f)) < 0.2] = 0.0          # exact zeros: q = eps/(s+eps) there (nmf.py:336)
@@ -49,7 +52,7 @@ def test_fused_transform_matches_oracle_and_unfused(n, f, k):
     for _ in range(iters):
         errs_ref.append(O.error(X, W_ref, H))
         W_ref, _ = O.update(X, W_ref, H, fit=False)
-    Wf, ef, lf = run_transform(X, H, iters, True)
+    Wf, ef, lf = run_transform(X, H, iters, True, ts)
     Wu, eu, lu = run_transform(X, H, iters, False)
     assert lf < lu, "the fused path must be the one that ran (one kernel per iteration)"
     assert np.isfinite(Wf).all()
