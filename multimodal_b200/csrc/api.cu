@@ -216,8 +216,9 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
   const int64_t es = ctx->es;
   const int cur = ctx->cur, hc = ctx->hcur;
   const int *stop = only_error ? nullptr : ctx->flags + FL_STOP;
-  if (!fit && !only_error && !dict_only && !ratio_host && fused_supported(ctx) && ctx->n > 0) {
-    // transform with k <= 128: one fused kernel per iteration, the ratio never leaves the SM (dense_fused.cu)
+  const bool fused = !only_error && !dict_only && !ratio_host && fused_supported(ctx) && ctx->n > 0;
+  if (fused) {
+    // k <= 128: the coefficient half-step is one fused kernel, the ratio never leaves the SM (dense_fused.cu)
     if (!ctx->Ht) {
       ctx->ldht = ctx->ldw;
       KL_TRY(dmalloc(&ctx->Ht, ctx->f * ctx->ldht * es));
@@ -229,6 +230,8 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
       ctx->ht_of = hc;
       ctx->ht_stale = false;
     }
+  }
+  if (fused && !fit) {
     PhaseTimer t(ctx, prof, PH_RATIO);
     FusedDesc d{};
     d.M = ctx->n; d.F = ctx->f; d.K = ctx->k;
@@ -246,7 +249,19 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
     const char *Wclo = ctx->split ? (const char *)ctx->Wlo[cur] + r0 * ctx->ldw * es : nullptr;
     char *Wn = (char *)ctx->W[cur ^ 1] + r0 * ctx->ldw * es;
     char *Wnlo = ctx->split ? (char *)ctx->Wlo[cur ^ 1] + r0 * ctx->ldw * es : nullptr;
-    {  // ratio + objective: Q = (X+eps)/(W.H+eps)   (nmf.py:325-336, metrics.py:18-20)
+    if (fused) {   // fit, k <= 128: ratio + objective + coefficient update in one kernel, Q written once for the numerator
+      PhaseTimer t(ctx, prof, PH_RATIO);
+      FusedDesc d{};
+      d.M = rows; d.F = ctx->f; d.K = ctx->k;
+      d.W = Wc; d.ldw = ctx->ldw;
+      d.H = ctx->H[hc]; d.ldh = ctx->ldh;
+      d.Ht = ctx->Ht; d.ldht = ctx->ldht;
+      d.X = (const char *)ctx->X + r0 * ctx->ldx * es; d.ldx = ctx->ldx;
+      d.Wout = Wn; d.ldwo = ctx->ldw;
+      d.Q = ctx->Q; d.ldq = ctx->ldq;
+      d.kl = ctx->dred; d.stop = stop;
+      KL_TRY(fused_coef_step(ctx, d));
+    } else {  // ratio + objective: Q = (X+eps)/(W.H+eps)   (nmf.py:325-336, metrics.py:18-20)
       PhaseTimer t(ctx, prof, PH_RATIO);
       GemmDesc d{};
       d.M = rows; d.N = ctx->f; d.K = ctx->k;
@@ -264,7 +279,7 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
       continue;
     }
     if (only_error) continue;
-    if (!dict_only) {  // coefficients: W' = W (.) (Q.H^T)           (nmf.py:338-343)
+    if (!dict_only && !fused) {  // coefficients: W' = W (.) (Q.H^T)           (nmf.py:338-343)
       PhaseTimer t(ctx, prof, PH_COEF);
       GemmDesc d{};
       d.M = rows; d.N = ctx->k; d.K = ctx->f;

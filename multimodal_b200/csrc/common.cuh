@@ -158,6 +158,7 @@ struct FusedDesc {
   const void *Ht; int64_t ldht;      // its transpose F x K (zero padded to ldht)
   const void *X; int64_t ldx;        // data M x F
   void *Wout; int64_t ldwo;          // updated coefficients
+  void *Q; int64_t ldq;              // fit only: the ratio panel M x F is also written (nullptr: transform)
   double *kl;                        // objective accumulator or nullptr
   const int *stop;
   int only_kl;

@@ -148,7 +148,7 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
     for (int s = 0; s < HS; s++) { mbar_init(h_full(s), 1); mbar_init(h_empty(s), 1); }
     for (int a = 0; a < 2; a++) {
       mbar_init(s_full(a), 1); mbar_init(s_empty(a), F_EPI_WARPS / 2);
-      mbar_init(q_full(a), F_EPI_WARPS / 2); mbar_init(q_empty(a), 1);
+      mbar_init(q_full(a), WRITE_Q ? 1 : F_EPI_WARPS / 2); mbar_init(q_empty(a), 1);
     }
     for (int b = 0; b < XB; b++) { mbar_init(x_full(b), 1); mbar_init(x_empty(b), F_EPI_WARPS / 2); }
     fence_barrier_init();
@@ -332,6 +332,11 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         kl_blk += part0 + part1;
         if (!p.only_kl) {
           mbar_wait(q_empty(grp), ph2 ^ 1u, p.err, 11);
+          if (WRITE_Q) {
+            // the TMA store of this group's previous tile must have finished reading the buffer as well
+            if (quarter == 0 && lane == 0) bulk_wait_read0();
+            named_bar(1 + grp, 128);
+          }
           uint8_t *qrow = q_gen + grp * CHUNK_BYTES + r * 128;
 #pragma unroll
           for (int i = 0; i < 8; i++)
@@ -339,8 +344,18 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
                 make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
           fence_proxy_async();
         }
-        __syncwarp();
-        if (lane == 0) mbar_arrive(q_full(grp));
+        if (WRITE_Q) {
+          // fit: the finished 128 x 32 ratio tile also leaves for HBM (one TMA store per step), the dictionary
+          // numerator N += W'^T.Q (nmf.py:349) reads it once W' of the whole panel exists
+          named_bar(1 + grp, 128);
+          if (quarter == 0 && lane == 0) {
+            if (!p.only_kl) tma_store_2d(&tmQ, q_s + grp * CHUNK_BYTES, j * FBN, rb * FBM);
+            mbar_arrive(q_full(grp));
+          }
+        } else {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(q_full(grp));
+        }
       }
       kl += (double)kl_blk;
       // ---- final epilogue of the row block: W' = W (.) G, each group one half of the columns ----
@@ -369,6 +384,7 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
       __syncwarp();
       if (lane == 0) mbar_arrive_relaxed(g_empty);
     }
+    if (WRITE_Q && quarter == 0 && lane == 0) bulk_wait_all();
     if (p.kl != nullptr) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) kl += __shfl_xor_sync(0xffffffffu, kl, o);
@@ -388,7 +404,7 @@ struct FusedState {
   int *err_dev = nullptr;
 };
 
-template <int KP, bool TSW, int V = 0>
+template <int KP, bool TSW, int V = 0, bool WRITE_Q = false>
 int launch_fused(klnmf_ctx *ctx, const FusedDesc &d, FusedParams p) {
   using C = FCfg<KP, TSW, V>;
   CUtensorMap tmW, tmHt, tmH, tmX, tmQ;
@@ -399,11 +415,12 @@ int launch_fused(klnmf_ctx *ctx, const FusedDesc &d, FusedParams p) {
   KL_TRY(make_map(&tmH, d.H, d.F, d.K, d.ldh, KP, false));           // box 32 features x KP rows
   KL_TRY(make_map(&tmX, d.X, d.F, d.M, d.ldx, FBM, false));          // box 32 features x 128 rows
   tmQ = tmX;
+  if (WRITE_Q) KL_TRY(make_map(&tmQ, d.Q, d.F, d.M, d.ldq, FBM, false));   // box 32 features x 128 rows, clipped at the edges
   p.n_blocks = (int)ceil_div(d.M, FBM);
   p.n_steps = (int)ceil_div(d.F, FBN);
   if (p.n_blocks == 0 || p.n_steps == 0) return KLNMF_OK;
   const int grid = p.n_blocks < ctx->sm_count ? p.n_blocks : ctx->sm_count;
-  auto kern = fused_coef_kernel<KP, false, TSW, V>;
+  auto kern = fused_coef_kernel<KP, WRITE_Q, TSW, V>;
   static bool attr_done = false;
   if (!attr_done) {
     KL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -448,6 +465,11 @@ int fused_coef_step(klnmf_ctx *ctx, const FusedDesc &d) {
   const int v = getenv("KLNMF_FUSED_V") ? atoi(getenv("KLNMF_FUSED_V")) : 0;
   p.lookahead = d.K <= 64 && ts ? 2 : 1;
   if (getenv("KLNMF_FUSED_LA")) p.lookahead = atoi(getenv("KLNMF_FUSED_LA")) == 2 ? 2 : 1;
+  if (d.Q != nullptr) {   // fit: the ratio panel is written for the numerator contraction
+    KL_CHECK(d.ldq >= round_up(d.F, 4), KLNMF_EINVAL, "fused_coef_step: ratio panel leading dimension too small");
+    if (d.K <= 64) return launch_fused<64, true, 0, true>(ctx, d, p);
+    return launch_fused<128, true, 0, true>(ctx, d, p);
+  }
   if (d.K <= 64) return ts ? launch_fused<64, true>(ctx, d, p) : launch_fused<64, false>(ctx, d, p);
   if (ts && v == 1) return launch_fused<128, true, 1>(ctx, d, p);
   return ts ? launch_fused<128, true>(ctx, d, p) : launch_fused<128, false>(ctx, d, p);

@@ -78,3 +78,40 @@ def test_fused_transform_through_the_estimator():
     for _ in range(25):
         W_ref, _ = O.update(X, W_ref, H, fit=False)
     assert cases.rel_fro(W, W_ref) < 3e-3
+
+
+def run_fit(X, H, iters, fused):
+    os.environ["KLNMF_FUSED"] = "1" if fused else "0"
+    try:
+        n, f = X.shape
+        with _native.Engine(n, f, H.shape[0], mode="tf32") as e:
+            e.set_dense(X)
+            e.set_dictionary(H)
+            e.init_coefficients()
+            c0 = e.counters()["launches"]
+            errs, _ = e.run(iters, 0.0, True)
+            launches = e.counters()["launches"] - c0
+            return e.get_coefficients(), e.get_dictionary(), np.asarray(errs), launches
+    finally:
+        os.environ.pop("KLNMF_FUSED", None)
+
+
+@pytest.mark.parametrize("n,f,k", [(700, 1000, 50), (513, 333, 100), (2000, 96, 8)])
+def test_fused_fit_matches_oracle_and_unfused(n, f, k):
+    # fit: the fused kernel also writes the ratio panel (TMA store) for the numerator N += W'^T.Q (nmf.py:349)
+    rs = np.random.RandomState(n * 3 + f + k)
+    X = rs.random_sample((n, f))
+    X[rs.random_sample((n, f)) < 0.3] = 0.0
+    np.random.seed(9)
+    H0 = O.init_dictionary(k, f)
+    W_ref, H_ref = np.asarray(X.dot(H0.T)), H0
+    errs_ref = []
+    for _ in range(10):
+        errs_ref.append(O.error(X, W_ref, H_ref))
+        W_ref, H_ref = O.update(X, W_ref, H_ref, fit=True)
+    Wf, Hf, ef, lf = run_fit(X, H0, 10, True)
+    Wu, Hu, eu, lu = run_fit(X, H0, 10, False)
+    assert lf <= lu       # one fused kernel (+ the H^T refresh) replaces the ratio and coefficient contractions
+    assert cases.rel_fro(Wf, W_ref) < 3e-3 and cases.rel_fro(Hf, H_ref) < 3e-3
+    np.testing.assert_allclose(ef, errs_ref, rtol=1e-2)
+    assert cases.rel_fro(Wf, Wu) < 1e-3 and cases.rel_fro(Hf, Hu) < 1e-3
