@@ -55,20 +55,76 @@ __device__ __forceinline__ T warp_sum(T v) {
   return v;
 }
 
+template <typename T>
+__device__ __forceinline__ void ldg4(const T *p, T v[4]) {   // read-only path (the dictionary never changes inside a pass)
+  if (sizeof(T) == 4) {
+    float4 t = __ldg(reinterpret_cast<const float4 *>(p));
+    v[0] = (T)t.x; v[1] = (T)t.y; v[2] = (T)t.z; v[3] = (T)t.w;
+  } else {
+    double2 t0 = __ldg(reinterpret_cast<const double2 *>(p));
+    double2 t1 = __ldg(reinterpret_cast<const double2 *>(p + 2));
+    v[0] = (T)t0.x; v[1] = (T)t0.y; v[2] = (T)t1.x; v[3] = (T)t1.y;
+  }
+}
+
+// One halving step of the batched warp reduction: every lane holds CNT partial sums (one per non-zero of the
+// batch); lanes whose OFF bit is set keep the upper half, the others the lower half, and each adds what its
+// partner held of the half it keeps.  log2(B) such steps followed by plain butterflies leave the complete
+// sum of non-zero b on the lanes with lane >> (5 - log2 B) == b: B - 1 + (5 - log2 B) shuffles per batch
+// instead of 5 per non-zero.
+template <typename T, int CNT, int OFF>
+__device__ __forceinline__ void halve(T v[], int lane) {
+  const bool up = (lane & OFF) != 0;
+#pragma unroll
+  for (int i = 0; i < CNT / 2; i++) {
+    const T send = up ? v[i] : v[i + CNT / 2];
+    const T keep = up ? v[i + CNT / 2] : v[i];
+    v[i] = keep + __shfl_xor_sync(0xffffffffu, send, OFF);
+  }
+  (void)lane;
+}
+template <typename T, int B>
+__device__ __forceinline__ T batch_reduce(T v[], int lane) {
+  static_assert(B == 8 || B == 4 || B == 2 || B == 1, "batch of 1, 2, 4 or 8 non-zeros");
+  if (B >= 2) halve<T, B, 16>(v, lane);
+  if (B >= 4) halve<T, B / 2, 8>(v, lane);
+  if (B >= 8) halve<T, B / 4, 4>(v, lane);
+  T r = v[0];
+  if (B < 2) r += __shfl_xor_sync(0xffffffffu, r, 16);
+  if (B < 4) r += __shfl_xor_sync(0xffffffffu, r, 8);
+  if (B < 8) r += __shfl_xor_sync(0xffffffffu, r, 4);
+  r += __shfl_xor_sync(0xffffffffu, r, 2);
+  r += __shfl_xor_sync(0xffffffffu, r, 1);
+  return r;
+}
+// batch size: the gathered columns of a batch stay in registers (<= 64 32-bit words per lane)
+template <typename T, int VPL>
+struct Batch {
+  static constexpr int WORDS = VPL * 4 * (int)(sizeof(T) / 4);
+  static constexpr int B = WORDS <= 8 ? 8 : (WORDS <= 16 ? 4 : (WORDS <= 32 ? 2 : 1));
+  static constexpr int SH = B == 8 ? 2 : (B == 4 ? 3 : (B == 2 ? 4 : 5));   // lanes per entry after the reduction = 1 << SH
+};
+
 // lane owns the k-elements { 128*c + 4*lane + e : c < VPL, e < 4 } (zero padded up to ld)
 // MODE 0: full pass 1;  MODE 1: objective only;  MODE 2: W0 = X . H0^T (nmf.py:156);
 // MODE 3: SDDMM only, qnz <- (W.H) at the non-zeros (nmf.py:52-70)
+// A row is walked in batches of B stored entries: B dictionary columns are gathered (one coalesced k-vector
+// each), their dot products with the row of W are reduced together, and the lanes {b << SH} finish entry b
+// (ratio, objective term) in parallel before the SAME gathered columns are reused for G += q_b H[:,j_b].
 template <typename T, int VPL, int MODE>
 __global__ void __launch_bounds__(WARPS * 32)
 sparse_rows_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                    const T *__restrict__ vals, const T *__restrict__ W, int64_t ldw, const T *__restrict__ Ht,
                    int64_t ldh, T *__restrict__ Wn, T *__restrict__ qnz, int64_t n, double *__restrict__ dred,
                    const int *stop) {
+  constexpr int B = Batch<T, VPL>::B, SH = Batch<T, VPL>::SH;
   if (stop != nullptr && *stop != 0) return;
   __shared__ double red[WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t warp_global = (int64_t)blockIdx.x * WARPS + warp;
   const int64_t n_warps = (int64_t)gridDim.x * WARPS;
+  const int mine = lane >> SH;                      // the entry of a batch this lane finishes
+  const bool leader = (lane & ((1 << SH) - 1)) == 0;
   bool act[VPL];
 #pragma unroll
   for (int c = 0; c < VPL; c++) act[c] = (128 * c + 4 * lane) < ldh && (128 * c + 4 * lane) < ldw;
@@ -93,55 +149,57 @@ sparse_rows_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict
       }
     }
     const int64_t p0 = indptr[i], p1 = indptr[i + 1];
-    for (int64_t p = p0; p < p1; p += 2) {
-      const bool two = (p + 1 < p1);
-      const int32_t ja = indices[p], jb = two ? indices[p + 1] : ja;
-      const T xa = vals[p], xb = two ? vals[p + 1] : (T)0;
-      T ha[VPL][4], hb[VPL][4];
-      T sa = (T)0, sb = (T)0;
+    float klf = 0.f;
+    for (int64_t p = p0; p < p1; p += B) {
+      const int nb = (int)(p1 - p < B ? p1 - p : B);        // entries of this batch
+      const bool have = mine < nb;
+      const T xm = have ? __ldg(vals + p + mine) : (T)0;    // the value of "my" entry
+      T h[B][VPL][4];
+      T s[B];
 #pragma unroll
-      for (int c = 0; c < VPL; c++) {
+      for (int b = 0; b < B; b++) {
+        // entries past the end of the row re-read the first column of the batch; their coefficient is forced to 0
+        const int32_t j = __ldg(indices + (b < nb ? p + b : p));
+        s[b] = (T)0;
 #pragma unroll
-        for (int e = 0; e < 4; e++) { ha[c][e] = (T)0; hb[c][e] = (T)0; }
-        if (act[c]) {
-          ld4(Ht + (int64_t)ja * ldh + 128 * c + 4 * lane, ha[c]);
-          ld4(Ht + (int64_t)jb * ldh + 128 * c + 4 * lane, hb[c]);
+        for (int c = 0; c < VPL; c++) {
+#pragma unroll
+          for (int e = 0; e < 4; e++) h[b][c][e] = (T)0;
+          if (act[c]) ldg4(Ht + (int64_t)j * ldh + 128 * c + 4 * lane, h[b][c]);
         }
       }
+      T coef;                                               // what multiplies column b in the SpMM, on lanes of entry b
       if (MODE == 2) {
+        coef = xm;
+      } else {
 #pragma unroll
-        for (int c = 0; c < VPL; c++)
+        for (int b = 0; b < B; b++)
 #pragma unroll
-          for (int e = 0; e < 4; e++) g[c][e] += xa * ha[c][e] + xb * hb[c][e];
-        continue;
-      }
+          for (int c = 0; c < VPL; c++)
 #pragma unroll
-      for (int c = 0; c < VPL; c++)
-#pragma unroll
-        for (int e = 0; e < 4; e++) { sa += w[c][e] * ha[c][e]; sb += w[c][e] * hb[c][e]; }
-      sa = warp_sum(sa);
-      sb = warp_sum(sb);
-      const T qa = (xa + (T)KL_EPS) / (sa + (T)KL_EPS);
-      const T qb = two ? (xb + (T)KL_EPS) / (sb + (T)KL_EPS) : (T)0;
-      if (lane == 0) {
-        kl += (double)xa * log((double)qa);
-        if (two) kl += (double)xb * log((double)qb);
-        if (MODE == 0) {
-          qnz[p] = qa;
-          if (two) qnz[p + 1] = qb;
-        }
-        if (MODE == 3) {
-          qnz[p] = sa;
-          if (two) qnz[p + 1] = sb;
+            for (int e = 0; e < 4; e++) s[b] += w[c][e] * h[b][c][e];
+        const T sm = batch_reduce<T, B>(s, lane);          // complete dot product of entry `mine`
+        const T q = have ? (xm + (T)KL_EPS) / (sm + (T)KL_EPS) : (T)0;
+        coef = q;
+        if (have && leader) {
+          if (sizeof(T) == 4) klf += (float)xm * logf((float)q);
+          else kl += (double)xm * log((double)q);
+          if (MODE == 0) qnz[p + mine] = q;
+          if (MODE == 3) qnz[p + mine] = sm;
         }
       }
-      if (MODE == 0) {
+      if (MODE == 0 || MODE == 2) {
 #pragma unroll
-        for (int c = 0; c < VPL; c++)
+        for (int b = 0; b < B; b++) {
+          const T cb = __shfl_sync(0xffffffffu, coef, b << SH);
 #pragma unroll
-          for (int e = 0; e < 4; e++) g[c][e] += qa * ha[c][e] + qb * hb[c][e];
+          for (int c = 0; c < VPL; c++)
+#pragma unroll
+            for (int e = 0; e < 4; e++) g[c][e] += cb * h[b][c][e];
+        }
       }
     }
+    kl += (double)klf;                                       // <= a row of terms in FP32, FP64 across rows
     if (MODE == 0 || MODE == 2) {
 #pragma unroll
       for (int c = 0; c < VPL; c++) {
@@ -161,12 +219,13 @@ sparse_rows_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict
 #pragma unroll
       for (int e = 0; e < 4; e++) atomicAdd(&dred[2 + 128 * c + 4 * lane + e], cs[c][e]);
     }
+  kl = warp_sum(kl);
   if (lane == 0) red[warp] = kl;
   __syncthreads();
   if (threadIdx.x == 0) {
-    double s = 0.0;
-    for (int w = 0; w < WARPS; w++) s += red[w];
-    atomicAdd(&dred[0], s);
+    double t = 0.0;
+    for (int w = 0; w < WARPS; w++) t += red[w];
+    atomicAdd(&dred[0], t);
   }
 }
 
