@@ -255,7 +255,12 @@ def phase_roofline(ms, cnt, n_local, f, k, kind, steps, peaks, mode):
         t = (ms["ratio"] + ms["numerator"]) / max(steps, 1) * 1e-3
         ach = alg / t / 1e9
         return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
-                "traffic": None, "kernel": "sparse_rows_kernel + sparse_scatter_kernel", "peak_source": peaks["source"]}
+                "traffic": ncu_traffic("sparse", n_local, f, k, "tf32" if mode != "fp64" else "fp64"),
+                "algorithmic_bytes": alg, "kernel": "sparse_rows_kernel + sparse_scatter_kernel",
+                "peak_source": peaks["source"],
+                "phase_ms_per_step": {p: ms[p] / max(steps, 1) for p in ("ratio", "numerator", "dictionary", "allreduce")},
+                "note": "one launch = one iteration's rows pass + scatter pass; bound in practice by the L2 gather / "
+                        "atomic traffic of 2 x nnz x 4k bytes (DESIGN.md 4.4), not by HBM"}
     names = {"ratio": "tc_gemm_kernel<ratio: S=W.H, Q=(X+eps)/(S+eps), KL>",
              "coefficient": "tc_gemm_kernel<coefficient: W'=W(.)(Q.H^T)>",
              "numerator": "tc_gemm_kernel<numerator: N+=W'^T.Q>"}
@@ -372,7 +377,36 @@ def run_ours(args):
             rows = max(1024, int(avail / 2.5 / (f * 4)) // 1024 * 1024)
         rows = min(rows, n_local)
         if kind == "sparse_fit":
-            e2e = {"value": None, "unit": "iterations/s", "note": "e2e leg not implemented for the synthetic CSR workload"}
+            # host scipy CSR (same stratified pattern as the device generator), pinned arrays; bounded row count,
+            # scaled linearly in n (cost is exactly linear in the rows of a shard)
+            import torch
+            import scipy.sparse as sp
+            eng.close()
+            m = int(round(f * 0.005))
+            rows = min(n_local, 262144)
+            rs = np.random.RandomState(77 + rank)
+            ind = torch.empty((rows * m,), dtype=torch.int32, pin_memory=True).numpy()
+            val = torch.empty((rows * m,), dtype=torch.float32, pin_memory=True).numpy()
+            ptr = torch.empty((rows + 1,), dtype=torch.int64, pin_memory=True).numpy()
+            lo = (np.arange(m, dtype=np.int64) * f) // m
+            width = ((np.arange(m, dtype=np.int64) + 1) * f) // m - lo
+            blk = 16384
+            for r0 in range(0, rows, blk):
+                r1 = min(rows, r0 + blk)
+                u = rs.random_sample((r1 - r0, m))
+                ind[r0 * m:r1 * m] = (lo[None, :] + (u * width[None, :]).astype(np.int64)).astype(np.int32).ravel()
+                val[r0 * m:r1 * m] = (1.0 - rs.random_sample((r1 - r0) * m)).astype(np.float32)
+            ptr[:] = np.arange(rows + 1, dtype=np.int64) * m
+            Xs = sp.csr_matrix((val, ind, ptr), shape=(rows, f), copy=False)
+            dt, h2d, d2h = run_e2e(args, rows, f, k, kind, args.mode, local, rank, world, dist, Xs, H0, args.steps)
+            scale = rows / float(n_local)
+            e2e = {"value": args.steps / dt * scale, "unit": "iterations/s",
+                   "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
+                   "seconds": dt, "rows_per_rank": rows,
+                   "note": "one KLdivNMF.fit_transform call of %d iterations on a host scipy CSR matrix (pinned arrays); "
+                           "the CSR crosses PCIe once per call, so per-step bytes are the call's bytes / steps" % args.steps +
+                           ("" if rows == n_local else "; measured on %d rows and scaled linearly in n" % rows)}
+            del Xs, ind, val, ptr
         else:
             import torch
             Xh = torch.empty((rows, f), dtype=torch.float32, pin_memory=True).numpy()

@@ -59,6 +59,22 @@ def main():
         tj = os.path.join(ROOT, "profiles", "ncu_traffic.json")
         entries = json.load(open(tj)) if os.path.exists(tj) else []
         for key, rows_, f, k, mode in traffic:
+            if key == "sparse":      # one sparse iteration = rows pass + scatter pass: sum the first launch of each
+                rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
+                tr = tw = 0.0
+                for sub in ("sparse_rows_kernel", "sparse_scatter_kernel"):
+                    for r in body:
+                        if sub in r[hdr.index("Kernel Name")]:
+                            tr += float(r[rd]) * UNIT[units[rd]]
+                            tw += float(r[wr]) * UNIT[units[wr]]
+                            break
+                e = {"kernel": key, "rows": int(rows_), "f": int(f), "k": int(k), "mode": mode, "dram_bytes": tr + tw,
+                     "dram_bytes_read": tr, "dram_bytes_write": tw, "report": os.path.basename(rep),
+                     "kernel_name": "sparse_rows_kernel + sparse_scatter_kernel"}
+                entries = [x for x in entries if not (x["kernel"] == key and x["rows"] == e["rows"] and x["f"] == e["f"]
+                                                      and x["k"] == e["k"] and x["mode"] == mode)]
+                entries.append(e)
+                continue
             for r in body:
                 if MATCH[key] in r[hdr.index("Kernel Name")]:
                     rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
