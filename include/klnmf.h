@@ -142,6 +142,20 @@ int klnmf_counters(klnmf_ctx *ctx, int64_t out[4]);
  * [3] dictionary update + normalise, [4] all-reduce, [5] whole run; launches per phase in
  * counts[0..4]. */
 int klnmf_last_run_profile(klnmf_ctx *ctx, double ms[6], int64_t counts[5]);
+/* ---- evaluation: nearest-example classification on the coefficients ------------------------
+ * Replaces evaluation.all_distances / classify_NN / dists_to_found_labels (evaluation.py:68-116) with the
+ * measures of metrics.py:58-86.  A is n_test x d, B is n_ex x d (host, row-major float64).  Any of `dists`
+ * (n_test x n_ex, ld ldd), `argmin` (n_test; np.argmin semantics: first minimum) and `minval` may be NULL;
+ * with dists == NULL the distance matrix is never materialised. */
+#define KLNMF_MEASURE_KL           0   /* metrics.kl_div(a, b)       */
+#define KLNMF_MEASURE_REV_KL       1   /* metrics.rev_kl_div(a, b)   */
+#define KLNMF_MEASURE_SYM_KL       2   /* metrics.sym_kl_div(a, b)   */
+#define KLNMF_MEASURE_FROBENIUS    3   /* metrics.frobenius(a, b)    */
+#define KLNMF_MEASURE_COSINE_DIFF  4   /* metrics.cosine_diff(a, b)  */
+int klnmf_pairwise_host(int device, int measure, int64_t n_test, int64_t n_ex, int64_t d, const double *A,
+                        int64_t lda, const double *B, int64_t ldb, double *dists, int64_t ldd, int32_t *argmin,
+                        double *minval);
+
 /* diagnostic: one contraction out(M x N) = op(A).op(B) on host float64 buffers through the
  * dense engine of `mode` (the kernels klnmf_run uses).  a_trans=0: A is M x K row-major,
  * a_trans=1: A is stored K x M; b_trans=0: B is K x N row-major, b_trans=1: B is stored N x K. */

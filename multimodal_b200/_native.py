@@ -64,6 +64,8 @@ PROTOTYPES = {
     "klnmf_contract_bench": (_c_int, [_c_int, _c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_int,
                                       ctypes.POINTER(_c_dbl)]),
     "klnmf_engine_name": (ctypes.c_char_p, [_c_vp]),
+    "klnmf_pairwise_host": (_c_int, [_c_int, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64,
+                                     _c_vp, _c_vp]),
 }
 
 _lib = None
@@ -339,3 +341,24 @@ def contract_bench(M, N, K, mode, a_trans=False, b_trans=False, iters=10, device
     _check(lib.klnmf_contract_bench(int(device), resolve_mode(mode), int(M), int(N), int(K), 1 if a_trans else 0,
                                     1 if b_trans else 0, int(iters), ctypes.byref(ms)))
     return ms.value
+
+
+MEASURES = {"kl_div": 0, "rev_kl_div": 1, "sym_kl_div": 2, "frobenius": 3, "cosine_diff": 4}
+
+
+def pairwise(A, B, measure, want_dists=True, want_argmin=False, device=0):
+    """Distances of every row of A (n_test, d) to every row of B (n_ex, d) under `measure` (a key of MEASURES)
+    on the device (csrc/evaluation.cu); returns (dists or None, argmin or None)."""
+    lib = load()
+    A, B = _as_f64(np.atleast_2d(A)), _as_f64(np.atleast_2d(B))
+    if A.shape[1] != B.shape[1]:
+        raise ValueError("operands could not be broadcast together with shapes %s %s" % (A.shape, B.shape))
+    nt, ne, d = A.shape[0], B.shape[0], A.shape[1]
+    D = np.empty((nt, ne), dtype=np.float64) if want_dists else None
+    idx = np.empty((nt,), dtype=np.int32) if want_argmin else None
+    if want_argmin and ne == 0:
+        raise ValueError("attempt to get argmin of an empty sequence")
+    _check(lib.klnmf_pairwise_host(int(device), MEASURES[measure], nt, ne, d, _ptr(A), max(d, 1), _ptr(B), max(d, 1),
+                                   _ptr(D) if D is not None else None, max(ne, 1),
+                                   _ptr(idx) if idx is not None else None, None))
+    return D, idx

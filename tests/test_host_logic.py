@@ -106,3 +106,18 @@ def test_two_rank_sharding_over_gloo(tmp_path):
     Wref, Href = O.update(X, X.dot(r0["H0"].T), r0["H0"])
     assert cases.rel_fro(np.vstack([r0["W"], r1["W"]]), Wref) < 1e-14
     assert cases.rel_fro(r0["H"], Href) < 1e-13 and np.array_equal(r0["H"], r1["H"])
+
+
+def test_measures_known_answers():
+    # reference tests/test_metrics.py:48-54 (KL known answer) and the zero guard of cosine_similarity (metrics.py:73-78)
+    from multimodal_b200.lib import metrics as M
+    x, y = np.array([1., 2., 0.]), np.array([2., 2., 3.])
+    assert abs(M.generalized_KL(x, y) - (np.log(.5) + 1. + 3.)) < 1e-7
+    assert abs(M.kl_div(x, y) - M.generalized_KL(x, y)) == 0
+    assert M.rev_kl_div(x, y) == M.kl_div(y, x)
+    assert M.sym_kl_div(x, y) == .5 * (M.kl_div(x, y) + M.kl_div(y, x))
+    assert M.frobenius(np.array([3., 0.]), np.array([0., 4.])) == 5.0
+    assert M.cosine_similarity(np.zeros(3), y) == 0.0 and M.cosine_diff(y, y) == pytest.approx(-1.0)
+    a = np.array([[1., 3.]])
+    M.kl_div(a, a.copy(), normalize=True)
+    assert np.allclose(a, [[.25, .75]])          # normalisation happens in place, as in the reference
