@@ -81,3 +81,43 @@ def evaluate_label_reco(reco_acti, true_labels):
     best = reco_acti.argmax(axis=1)
     assert best.shape == labels.shape
     return np.average(best == labels)
+
+
+# ---- host-side label bookkeeping of the reference (evaluation.py:8-44): list / small-array logic, no arithmetic
+def chose_examples(labels, label_set=None, number=1):
+    """Indices of the first `number` occurrences of every label (evaluation.py:33-44); ValueError when a label has
+    fewer occurrences, like list.index."""
+    wanted = set(labels) if label_set is None else label_set
+    picked = []
+    for lab in wanted:
+        pos = -1
+        for _ in range(number):
+            pos = labels.index(lab, pos + 1)
+            picked.append(pos)
+    return picked
+
+
+def compare_labels_given_nb(reco_label_vect, true_label_vect):
+    """Per example: are the nb_true highest activations exactly the true labels (evaluation.py:8-19)."""
+    reco = np.atleast_2d(reco_label_vect)
+    true = np.atleast_2d(true_label_vect)
+    n_true = true.sum(axis=-1)
+    order = np.argsort(-reco, axis=-1)            # decreasing activation
+    out = np.empty(true.shape[0], dtype=bool)
+    for i in range(true.shape[0]):
+        top = np.zeros(true.shape[-1])
+        np.add.at(top, order[i, :int(n_true[i])], 1.)
+        out[i] = (top == true[i]).all()
+    return out
+
+
+def score_labels_given_nb(reco_label_vect, true_label_vect):
+    return np.average(compare_labels_given_nb(reco_label_vect, true_label_vect))
+
+
+def compare_labels_threshold(reco_label_vect, true_label_vect, threshold):
+    return ((reco_label_vect >= threshold) == true_label_vect).all(axis=-1)
+
+
+def score_labels_threshold(reco_label_vect, true_label_vect, threshold):
+    return np.average(compare_labels_threshold(reco_label_vect, true_label_vect, threshold))
