@@ -107,6 +107,12 @@ def measured_peaks():
 def cpu_sample(workload, n_total, f, k, kind, steps, warmup):
     from oracle import klnmf_oracle as O
     import scipy.sparse as sp
+    # torchrun exports OMP_NUM_THREADS=1 to its ranks; the CPU arm is meant to use every host core it can
+    try:
+        from threadpoolctl import threadpool_limits
+        threadpool_limits(limits=os.cpu_count(), user_api="blas")
+    except Exception:
+        pass
     rs = np.random.RandomState(0)
     if kind == "sparse_fit":
         n_cpu = 4096

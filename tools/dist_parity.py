@@ -26,5 +26,20 @@ for mode, tol in (("fp64", 1e-9), ("tf32x3", 2e-5), ("tf32", 3e-3)):
     eK = abs(errs[-1] - er[-1]) / abs(er[-1])
     print("rank %d mode %-6s relerr W %.2e H %.2e KL %.2e %s" % (rank, mode, eW, eH, eK, "ok" if max(eW, eH) < tol else "FAIL"), flush=True)
     assert max(eW, eH) < tol and len(errs) == 10
+# sparse shard (CSR rows) through the same all-reduce
+import scipy.sparse as sp
+Xs = sp.random(1200, 900, density=0.05, random_state=np.random.RandomState(8), format="csr")
+Xs.data = np.ceil(5 * Xs.data)
+np.random.seed(6)
+H0s = O.init_dictionary(24, Xs.shape[1])
+bs = D.shard_bounds(Xs.shape[0], world)
+for mode, tol in (("fp64", 1e-9), ("tf32", 2e-5)):
+    sh = D.ShardedNMF(24, max_iter=10, tol=0, mode=mode, device=local)
+    W, errs = sh.fit_transform(Xs[bs[rank]:bs[rank + 1]], Xs.shape[0], H0=H0s, fit=True, return_errors=True)
+    np.random.seed(6)
+    Wr, Hr, er, _ = O.fit_transform(Xs.copy(), k=24, max_iter=10, tol=0)
+    eW = cases.rel_fro(W, Wr[bs[rank]:bs[rank + 1]]); eH = cases.rel_fro(sh.components_, Hr)
+    print("rank %d sparse mode %-6s relerr W %.2e H %.2e %s" % (rank, mode, eW, eH, "ok" if max(eW, eH) < tol else "FAIL"), flush=True)
+    assert max(eW, eH) < tol and len(errs) == 10
 dist.barrier()
 dist.destroy_process_group()
