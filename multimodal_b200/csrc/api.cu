@@ -115,6 +115,7 @@ void release_data(klnmf_ctx *ctx) {
     if (ctx->vals) cudaFree(ctx->vals);
   }
   if (ctx->qnz) cudaFree(ctx->qnz);
+  sparse_release_pattern(ctx);
   ctx->X = nullptr; ctx->indptr = nullptr; ctx->indices = nullptr; ctx->vals = nullptr; ctx->qnz = nullptr;
   ctx->x_owned = ctx->csr_owned = false;
   ctx->have_x = false;

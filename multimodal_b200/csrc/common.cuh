@@ -70,6 +70,7 @@ struct klnmf_ctx {
   void *vals = nullptr;        // nnz
   bool csr_owned = false;
   void *qnz = nullptr;         // nnz ratio values (sparse path)
+  void *bcsc = nullptr;        // blocked-CSC copy of the pattern for the numerator pass (sparse.cu), built lazily
 
   // ---- state -------------------------------------------------------------------------
   bool have_h = false, have_w = false;
@@ -186,6 +187,7 @@ int sparse_rows(klnmf_ctx *ctx, int mode);    // 0 full pass, 1 objective only, 
 int sparse_scatter(klnmf_ctx *ctx, bool use_current_w);
 int sparse_init_w(klnmf_ctx *ctx);
 int sparse_fill_synthetic(klnmf_ctx *ctx, int64_t nnz_per_row, uint64_t seed);
+void sparse_release_pattern(klnmf_ctx *ctx);   // drop the blocked-CSC copy (the data changed)
 
 // ---- NCCL through dlopen: nccl_dyn.cu ----------------------------------------------------------------
 int nccl_load(const char *path);
