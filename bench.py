@@ -262,11 +262,11 @@ def phase_roofline(ms, cnt, n_local, f, k, kind, steps, peaks, mode):
         ach = alg / t / 1e9
         return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
                 "traffic": ncu_traffic("sparse", n_local, f, k, "tf32" if mode != "fp64" else "fp64"),
-                "algorithmic_bytes": alg, "kernel": "sparse_rows_kernel + sparse_scatter_kernel",
+                "algorithmic_bytes": alg, "kernel": "sparse_rows_kernel + sparse_numerator_bcsc_kernel",
                 "peak_source": peaks["source"],
                 "phase_ms_per_step": {p: ms[p] / max(steps, 1) for p in ("ratio", "numerator", "dictionary", "allreduce")},
-                "note": "one launch = one iteration's rows pass + scatter pass; bound in practice by the L2 gather / "
-                        "atomic traffic of 2 x nnz x 4k bytes (DESIGN.md 4.4), not by HBM"}
+                "note": "one launch = one iteration's rows pass + numerator pass; bound in practice by the L2 gather "
+                        "traffic of 2 x nnz x 4k bytes (DESIGN.md 4.4), not by HBM"}
     names = {"ratio": "tc_gemm_kernel<ratio: S=W.H, Q=(X+eps)/(S+eps), KL>",
              "coefficient": "tc_gemm_kernel<coefficient: W'=W(.)(Q.H^T)>",
              "numerator": "tc_gemm_kernel<numerator: N+=W'^T.Q>"}

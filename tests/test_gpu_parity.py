@@ -164,3 +164,26 @@ def test_multi_panel_equals_single_panel():
             outs.append((e.get_coefficients(), e.get_dictionary(), errs))
     assert cases.rel_fro(outs[1][0], outs[0][0]) < 1e-12 and cases.rel_fro(outs[1][1], outs[0][1]) < 1e-12
     np.testing.assert_allclose(outs[1][2], outs[0][2], rtol=1e-12)
+
+
+def test_cfg2_full_shapes_learner_vs_oracle():
+    """BASELINE.json configs[1] at its real shapes: 1000 samples, motion 450 dense + sound 110 000
+    CSR at 1 % -> a 1000 x 110 450 CSR stack (learner.py:53-56), k = 50; a few training iterations and a
+    reconstruction of the missing modality against the float64 oracle (3 iterations keep the oracle's
+    nnz x k temporaries, 3 x 0.6 GB, and its runtime in seconds)."""
+    motion, sound, coefs = cases.cfg2_inputs()
+    mods, dims = ['motion', 'sound'], [motion.shape[1], sound.shape[1]]
+    lr = MultimodalLearner(mods, dims, coefs, 50, mode="tf32x3")
+    np.random.seed(3)
+    lr.train([motion, sound.copy()], 3)
+    ref = O.Learner(mods, dims, coefs, 50)
+    np.random.seed(3)
+    ref.train([motion, sound.copy()], 3)
+    assert lr.dico.shape == (50, 110450)
+    assert cases.rel_fro(lr.dico, ref.dico) < 5e-5
+    internal = lr.reconstruct_internal('motion', motion[:40], 5)
+    internal_ref = ref.reconstruct_internal_multi(['motion'], [motion[:40]], 5)
+    assert cases.rel_fro(internal, internal_ref) < 5e-4
+    snd = lr.reconstruct_modality('sound', internal)
+    assert snd.shape == (40, 110000)
+    assert cases.rel_fro(snd, internal_ref.dot(ref.get_dico('sound'))) < 5e-4

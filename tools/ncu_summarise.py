@@ -26,7 +26,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed.sum"]
 MATCH = {"ratio": "tc_gemm_kernel<256, 0, 1, 0, 1", "coefficient": "tc_gemm_kernel<256, 0, 0, 0, 0",
          "numerator": "tc_gemm_kernel<256, 1, 1, 0, 0", "fused": "fused_coef_kernel",
-         "sparse_rows": "sparse_rows_kernel", "sparse_scatter": "sparse_scatter_kernel"}
+         "sparse_rows": "sparse_rows_kernel", "sparse_scatter": "sparse_numerator_bcsc_kernel"}
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 
 
@@ -62,7 +62,7 @@ def main():
             if key == "sparse":      # one sparse iteration = rows pass + scatter pass: sum the first launch of each
                 rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
                 tr = tw = 0.0
-                for sub in ("sparse_rows_kernel", "sparse_scatter_kernel"):
+                for sub in ("sparse_rows_kernel", "sparse_numerator_bcsc_kernel"):
                     for r in body:
                         if sub in r[hdr.index("Kernel Name")]:
                             tr += float(r[rd]) * UNIT[units[rd]]
@@ -70,7 +70,7 @@ def main():
                             break
                 e = {"kernel": key, "rows": int(rows_), "f": int(f), "k": int(k), "mode": mode, "dram_bytes": tr + tw,
                      "dram_bytes_read": tr, "dram_bytes_write": tw, "report": os.path.basename(rep),
-                     "kernel_name": "sparse_rows_kernel + sparse_scatter_kernel"}
+                     "kernel_name": "sparse_rows_kernel + sparse_numerator_bcsc_kernel"}
                 entries = [x for x in entries if not (x["kernel"] == key and x["rows"] == e["rows"] and x["f"] == e["f"]
                                                       and x["k"] == e["k"] and x["mode"] == mode)]
                 entries.append(e)
