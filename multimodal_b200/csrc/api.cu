@@ -7,6 +7,12 @@
 
 #include <vector>
 
+#include <string.h>
+
+#include <mutex>
+#include <thread>
+#include <vector>
+
 #include "common.cuh"
 
 namespace klnmf {
@@ -154,6 +160,81 @@ int upload_matrix(klnmf_ctx *ctx, const void *src, int dtype, int64_t ld, void *
   return KLNMF_OK;
 }
 
+// Large device -> pageable-host downloads (the coefficients of a big shard: GBs).  A plain cudaMemcpy into
+// pageable memory moved 4 GB/s (measured, tools/e2e_breakdown.py: 52 % of an end-to-end fit_transform call);
+// here the panel is converted on the device, lands in one of two pinned staging buffers at PCIe speed, and a
+// few host threads copy it into the caller's array (first-touch page faults included) while the next panel is
+// already on its way.
+int download_large(klnmf_ctx *ctx, const void *src, const void *src_lo, int64_t src_ld, void *dst, int dtype, int64_t ld,
+                   int64_t rows, int64_t cols) {
+  const int64_t des = dtype == KLNMF_F64 ? 8 : 4;
+  const int src_dtype = ctx->es == 8 ? KLNMF_F64 : KLNMF_F32;
+  constexpr int64_t kPin = (int64_t)64 << 20;
+  // the two pinned buffers are process-wide (pinning / unpinning 128 MB costs ~0.3 s per context otherwise) and
+  // held for the duration of one download
+  static std::mutex pin_mutex;
+  static void *g_pin[2] = {nullptr, nullptr};
+  std::lock_guard<std::mutex> pin_lock(pin_mutex);
+  for (int b = 0; b < 2; b++) {
+    if (!g_pin[b]) KL_CUDA(cudaHostAlloc(&g_pin[b], kPin, cudaHostAllocPortable));
+    ctx->pin_stage[b] = g_pin[b];
+  }
+  int64_t chunk = kPin / (cols * des);
+  if (chunk < 1) chunk = 1;
+  KL_CHECK(chunk * cols * des <= kPin, KLNMF_EINVAL, "download: one row exceeds the staging buffer");
+  KL_TRY(ensure_stage(ctx, 2 * chunk * cols * des));
+  cudaEvent_t ev[2];
+  KL_CUDA(cudaEventCreateWithFlags(&ev[0], cudaEventDisableTiming));
+  KL_CUDA(cudaEventCreateWithFlags(&ev[1], cudaEventDisableTiming));
+  unsigned nt = std::thread::hardware_concurrency();
+  nt = nt < 1 ? 1 : (nt > 8 ? 8 : nt);
+  auto host_copy = [&](int b, int64_t r0, int64_t r) {
+    const char *ps = (const char *)ctx->pin_stage[b];
+    std::vector<std::thread> th;
+    const int64_t per = (r + nt - 1) / nt;
+    for (unsigned t = 0; t < nt; t++) {
+      const int64_t a = t * per, e = a + per < r ? a + per : r;
+      if (a >= e) break;
+      th.emplace_back([=]() {
+        if (ld == cols) memcpy((char *)dst + (r0 + a) * ld * des, ps + a * cols * des, (size_t)((e - a) * cols * des));
+        else
+          for (int64_t i = a; i < e; i++) memcpy((char *)dst + (r0 + i) * ld * des, ps + i * cols * des, (size_t)(cols * des));
+      });
+    }
+    for (auto &x : th) x.join();
+  };
+  int rc = KLNMF_OK;
+  int64_t prev_r0 = -1, prev_r = 0;
+  int b = 0;
+  for (int64_t r0 = 0; r0 < rows && rc == KLNMF_OK; r0 += chunk, b ^= 1) {
+    const int64_t r = rows - r0 < chunk ? rows - r0 : chunk;
+    const void *s = (const char *)src + r0 * src_ld * ctx->es;
+    const void *sl = src_lo ? (const void *)((const char *)src_lo + r0 * src_ld * ctx->es) : nullptr;
+    void *dstage = (char *)ctx->stage + b * chunk * cols * des;
+    rc = launch_convert(ctx, s, sl, src_dtype, src_ld, dstage, (int)des, cols, r, cols, false);
+    if (rc == KLNMF_OK && cudaMemcpyAsync(ctx->pin_stage[b], dstage, (size_t)(r * cols * des), cudaMemcpyDeviceToHost,
+                                          ctx->stream) != cudaSuccess) {
+      set_error("download: cudaMemcpyAsync failed");
+      rc = KLNMF_ECUDA;
+    }
+    cudaEventRecord(ev[b], ctx->stream);
+    if (prev_r0 >= 0) {                         // the previous panel is (being) copied out while this one is in flight
+      cudaEventSynchronize(ev[b ^ 1]);
+      host_copy(b ^ 1, prev_r0, prev_r);
+    }
+    prev_r0 = r0; prev_r = r;
+    ctx->bytes_d2h += r * cols * des;
+  }
+  if (rc == KLNMF_OK && prev_r0 >= 0) {
+    if (cudaEventSynchronize(ev[b ^ 1]) != cudaSuccess) { set_error("download: device error"); rc = KLNMF_ECUDA; }
+    else host_copy(b ^ 1, prev_r0, prev_r);
+  }
+  cudaStreamSynchronize(ctx->stream);
+  cudaEventDestroy(ev[0]);
+  cudaEventDestroy(ev[1]);
+  return rc;
+}
+
 // device (es [+lo], src_ld) -> host double/float (ld), optional transpose (src is cols x rows then)
 int download_matrix(klnmf_ctx *ctx, const void *src, const void *src_lo, int64_t src_ld, void *dst, int dtype,
                     int64_t ld, int64_t rows, int64_t cols, bool transposed_src) {
@@ -175,6 +256,7 @@ int download_matrix(klnmf_ctx *ctx, const void *src, const void *src_lo, int64_t
     ctx->bytes_d2h += rows * cols * des;
     return KLNMF_OK;
   }
+  if (rows * cols * des >= ((int64_t)32 << 20)) return download_large(ctx, src, src_lo, src_ld, dst, dtype, ld, rows, cols);
   int64_t chunk = kStageBytes / (cols * des);
   if (chunk < 1) chunk = 1;
   KL_TRY(ensure_stage(ctx, (chunk < rows ? chunk : rows) * cols * des));

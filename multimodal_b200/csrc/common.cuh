@@ -91,6 +91,7 @@ struct klnmf_ctx {
   int64_t dred_len = 0;
   void *stage = nullptr;       // device staging for host<->device conversions
   int64_t stage_bytes = 0;
+  void *pin_stage[2] = {nullptr, nullptr};   // borrowed process-wide pinned staging of large downloads (api.cu: download_large)
 
   // ---- dense scratch -------------------------------------------------------------------
   void *Q = nullptr, *Qlo = nullptr;   // panel_rows x f ratio panel

@@ -115,3 +115,20 @@ def test_fused_fit_matches_oracle_and_unfused(n, f, k):
     assert cases.rel_fro(Wf, W_ref) < 3e-3 and cases.rel_fro(Hf, H_ref) < 3e-3
     np.testing.assert_allclose(ef, errs_ref, rtol=1e-2)
     assert cases.rel_fro(Wf, Wu) < 1e-3 and cases.rel_fro(Hf, Hu) < 1e-3
+
+
+def test_large_download_roundtrip():
+    # coefficient downloads >= 32 MB take the pipelined path (pinned staging + host copy threads, api.cu)
+    n, f, k = 70001, 40, 72
+    rs = np.random.RandomState(2)
+    W = rs.random_sample((n, k))
+    for mode in ("tf32", "tf32x3", "fp64"):
+        with _native.Engine(n, f, k, mode=mode) as e:
+            e.set_dense(np.ones((n, f), dtype=np.float32))
+            e.set_coefficients(W)
+            back = e.get_coefficients()
+        assert back.shape == W.shape
+        if mode == "fp64":
+            assert np.array_equal(back, W)
+        else:
+            np.testing.assert_allclose(back, W, rtol=1.2e-7)     # one float32 rounding (hi + lo keeps more in tf32x3)

@@ -121,3 +121,27 @@ def test_measures_known_answers():
     a = np.array([[1., 3.]])
     M.kl_div(a, a.copy(), normalize=True)
     assert np.allclose(a, [[.25, .75]])          # normalisation happens in place, as in the reference
+
+
+def test_evaluation_label_bookkeeping():
+    # host-side helpers of the evaluation mirror (reference evaluation.py:8-91): pure list / small-array logic
+    from multimodal_b200 import evaluation as E
+    labels = [0, 1, 2, 0, 1, 2, 2]
+    assert sorted(E.chose_examples(labels, number=2)) == [0, 1, 2, 3, 4, 5]
+    assert sorted(E.chose_examples(labels, label_set={2}, number=3)) == [2, 5, 6]
+    with pytest.raises(ValueError):
+        E.chose_examples(labels, label_set={0}, number=3)
+    reco = np.array([[.9, .1, .8], [.2, .7, .1]])
+    true = np.array([[1, 0, 1], [1, 0, 0]])
+    assert list(E.compare_labels_given_nb(reco, true)) == [True, False]
+    assert E.score_labels_given_nb(reco, true) == .5
+    assert list(E.compare_labels_given_nb(reco[0], true[0])) == [True]
+    assert E.score_labels_threshold(reco, true, .5) == .5
+    assert E.evaluate_label_reco(reco, [0, 1]) == 1.0
+    d = np.array([[3., 1., 1.], [0., 5., 5.]])
+    assert E.dists_to_found_labels(d, ['a', 'b', 'c']) == ['b', 'a']          # first minimum, like np.argmin
+    assert E.found_labels_to_score(['b', 'x'], ['b', 'a']) == .5
+    conf = E.found_labels_to_confusion([0, 0, 1], [0, 0, 1], 2)
+    assert conf[0, 0] == 1 and conf[1, 1] == 1                                 # repeated pairs count once (reference quirk)
+    with pytest.raises(TypeError):
+        E._measure_key(lambda a, b, axis=-1: 0)
