@@ -299,9 +299,10 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
   const int64_t es = ctx->es;
   const int cur = ctx->cur, hc = ctx->hcur;
   const int *stop = only_error ? nullptr : ctx->flags + FL_STOP;
-  const bool fused = !only_error && !dict_only && !ratio_host && fused_supported(ctx) && ctx->n > 0;
+  const bool fused = !only_error && !dict_only && !ratio_host && fused_supported(ctx, fit) && ctx->n > 0;
   if (fused) {
-    // k <= 128: the coefficient half-step is one fused kernel, the ratio never leaves the SM (dense_fused.cu)
+    // k <= 128 (fit, transform) / k <= 256 (transform): the coefficient half-step is one fused kernel, the ratio
+    // never leaves the SM (dense_fused.cu, dense_fused256.cu)
     if (!ctx->Ht) {
       ctx->ldht = ctx->ldw;
       KL_TRY(dmalloc(&ctx->Ht, ctx->f * ctx->ldht * es));

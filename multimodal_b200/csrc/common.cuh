@@ -165,7 +165,8 @@ struct FusedDesc {
   const int *stop;
   int only_kl;
 };
-bool fused_supported(const klnmf_ctx *ctx);
+bool fused_supported(const klnmf_ctx *ctx, int fit);
+int fused_coef_step256(klnmf_ctx *ctx, const FusedDesc &d, int *err_dev);   // 128 < k <= 256, transform, CTA pairs
 int fused_coef_step(klnmf_ctx *ctx, const FusedDesc &d);
 void fused_release(klnmf_ctx *ctx);
 

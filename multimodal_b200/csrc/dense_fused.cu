@@ -434,9 +434,12 @@ int launch_fused(klnmf_ctx *ctx, const FusedDesc &d, FusedParams p) {
 
 }  // namespace
 
-bool fused_supported(const klnmf_ctx *ctx) {
+bool fused_supported(const klnmf_ctx *ctx, int fit) {
   const bool off = getenv("KLNMF_FUSED") && atoi(getenv("KLNMF_FUSED")) == 0;   // read per call: tests toggle it
-  return !off && ctx->mode == KLNMF_MODE_TF32 && !ctx->sparse && !ctx->debug_simt && ctx->k <= 128;
+  // k <= 128: fit and transform (this file); 128 < k <= 256: transform on CTA pairs (dense_fused256.cu)
+  const bool off256 = getenv("KLNMF_FUSED256") && atoi(getenv("KLNMF_FUSED256")) == 0;
+  return !off && ctx->mode == KLNMF_MODE_TF32 && !ctx->sparse && !ctx->debug_simt &&
+         (ctx->k <= 128 || (!fit && !off256 && ctx->k <= 256));
 }
 
 int fused_coef_step(klnmf_ctx *ctx, const FusedDesc &d) {
@@ -452,6 +455,7 @@ int fused_coef_step(klnmf_ctx *ctx, const FusedDesc &d) {
     cudaMemsetAsync(st->err_dev, 0, 4, ctx->stream);
     ctx->fused = st;
   }
+  if (d.K > 128) return fused_coef_step256(ctx, d, st->err_dev);
   KL_CHECK(d.K <= 128 && d.ldw % 32 == 0 && d.ldht % 32 == 0, KLNMF_EINVAL, "fused_coef_step: k=%lld not supported",
            (long long)d.K);
   FusedParams p{};

@@ -11,6 +11,14 @@ from oracle import cases, klnmf_oracle as O
 
 pytestmark = pytest.mark.gpu
 
+SHAPES_256 = [
+    (128, 32, 130),      # one row block, one step, k just above the single-CTA limit
+    (700, 1000, 200),    # ragged rows / features
+    (513, 333, 256),     # full k, features not a multiple of 32 (nor of the 16 per CTA)
+    (4096, 2048, 256),   # many row blocks per cluster: barrier phases wrap
+    (300, 4100, 160),
+]
+
 SHAPES = [
     (128, 32, 8),        # one row block, one step
     (700, 1000, 50),     # ragged rows / features, k padded to 64
@@ -60,6 +68,30 @@ def test_fused_transform_matches_oracle_and_unfused(n, f, k, ts):
     assert cases.rel_fro(Wf, W_ref) < 3e-3, cases.rel_fro(Wf, W_ref)
     np.testing.assert_allclose(ef, errs_ref, rtol=1e-2)
     # fused and unfused run the same arithmetic up to the order of the FP32 accumulation
+    assert cases.rel_fro(Wf, Wu) < 1e-3, cases.rel_fro(Wf, Wu)
+    np.testing.assert_allclose(ef, eu, rtol=1e-4)
+
+
+@pytest.mark.parametrize("n,f,k", SHAPES_256)
+def test_fused_pair_transform_k256(n, f, k):
+    # 128 < k <= 256: the cluster-of-two kernel (dense_fused256.cu), Q exchanged through distributed shared memory
+    rs = np.random.RandomState(n + f + k)
+    X = rs.random_sample((n, f))
+    X[rs.random_sample((n, f)) < 0.2] = 0.0
+    np.random.seed(5)
+    H = O.init_dictionary(k, f)
+    iters = 5
+    W_ref = np.asarray(X.dot(H.T))
+    errs_ref = []
+    for _ in range(iters):
+        errs_ref.append(O.error(X, W_ref, H))
+        W_ref, _ = O.update(X, W_ref, H, fit=False)
+    Wf, ef, lf = run_transform(X, H, iters, True)
+    Wu, eu, lu = run_transform(X, H, iters, False)
+    assert lf < lu, "the fused path must be the one that ran"
+    assert np.isfinite(Wf).all()
+    assert cases.rel_fro(Wf, W_ref) < 3e-3, cases.rel_fro(Wf, W_ref)
+    np.testing.assert_allclose(ef, errs_ref, rtol=1e-2)
     assert cases.rel_fro(Wf, Wu) < 1e-3, cases.rel_fro(Wf, Wu)
     np.testing.assert_allclose(ef, eu, rtol=1e-4)
 
