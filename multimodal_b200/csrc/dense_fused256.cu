@@ -6,14 +6,21 @@
 //
 //   CTA r:  S_r = W . H[:, 16 features of the step]      (first contraction, N = 16: its half of the 32-feature step)
 //           Q_r = (X_r+eps)/(S_r+eps), objective          (TMEM epilogue; X_r = its 16 columns of X)
-//           Q_r is written into the Q tile of BOTH CTAs  (local st.shared + st.shared::cluster into the peer)
+//           Q_r is written into the Q tile of BOTH CTAs  (local st.shared, then one 2 KB cp.async.bulk per warp
+//                                                         from its own shared memory into the peer's)
 //           G_r += Q . H[128 r : 128 r + 128, step]^T     (second contraction, N = 128: its half of the components)
 //           W'[:, 128 r : 128 r + 128] = W (.) G_r        (final epilogue)
 //
 // No MMA work is duplicated, Q crosses the cluster's distributed shared memory (8 KB per step and direction) and
 // never HBM; each CTA holds the full W block in TMEM (A operand of the first contraction, TS form).  The protocol
-// is the one of dense_fused.cu with two changes: q_full collects the epilogue warps of both CTAs (8 arrivals, the
-// remote ones by mbarrier.arrive.release.cluster) and q_empty collects the tcgen05.commit of both issuers.
+// is the one of dense_fused.cu with two changes: q_full collects the four local epilogue warps plus the 8 KB the
+// peer's bulk copies complete on it (complete_tx, like a TMA load), and q_empty collects the tcgen05.commit of both
+// issuers.  The Q tile is two K-major half tiles of 128 rows x 16 features (64-byte rows, SWIZZLE_64B), one per
+// producing CTA, so that the 32 rows of a warp are one contiguous 2 KB range.  (The first version stored into the
+// peer with st.shared::cluster and signalled with mbarrier.arrive.release.cluster: the all-space fence.proxy.async
+// plus the cluster-scope release cost ~2300 clk per step and warp group -- MEMBAR.ALL.GPU, ERRBAR, FENCE.VIEW.ASYNC
+// were 31 % of all stall samples, profiles/r1_fused256_cfg3_n262144_summary.csv -- and the kernel ran at half the
+// speed of the unfused form.)
 // Reference lines as in dense_fused.cu (nmf.py:325-343, metrics.py:18-20).  Transform only (fit keeps the
 // three-contraction form at k > 128).
 #include <cuda.h>
@@ -32,13 +39,15 @@ constexpr int PKP = 256;                   // padded components
 constexpr int PKH = 128;                   // components per CTA (columns of G)
 constexpr int P_THREADS = 352;
 constexpr int P_EPI_WARPS = 8;
-constexpr int QTILE_BYTES = PBM * PBN * 4;             // 16 KB: the full 128 x 32 ratio tile (K-major, 128B swizzle)
-constexpr int XHALF_BYTES = PBM * PHN * 4;             // 8 KB: 128 rows x 16 features, unswizzled 64-byte rows
+constexpr int QTILE_BYTES = PBM * PBN * 4;             // 16 KB: the 128 x 32 ratio tile = two half tiles of 128 x 16 (K-major, 64B swizzle)
+constexpr int QHALF_BYTES = PBM * PHN * 4;             // 8 KB: the half one CTA produces
+constexpr int XHALF_BYTES = PBM * PHN * 4;             // 8 KB: 128 rows x 16 features, 64-byte rows (64B swizzle)
 constexpr int PH1_BYTES = (PKP / 32) * PHN * 32 * 4;   // 16 KB: H^T tile, 8 K blocks of 16 feature rows x 32 k
 constexpr int PH2_BYTES = PKH * PBN * 4;               // 16 KB: H tile, 128 component rows x 32 features
 constexpr int PSTAGE_BYTES = PH1_BYTES + PH2_BYTES;
-constexpr int PHS = 4;                                 // dictionary stages
-constexpr int PXB = 6;                                 // X half-chunks in flight
+constexpr int PHS = 5;                                 // dictionary stages
+constexpr int PXB = 4;                                 // X half-chunks in flight
+constexpr int PLA = 2;                                 // steps the first contraction runs ahead of the second
 constexpr int P_SMEM_BYTES = PHS * PSTAGE_BYTES + 2 * QTILE_BYTES + PXB * XHALF_BYTES + 1024 + 256;
 static_assert(P_SMEM_BYTES <= 232448, "shared memory budget exceeded");
 // TMEM columns: G_r [0,128) | S buffers [128,144) [160,176) | W [192,448)
@@ -56,39 +65,12 @@ struct Fused256Params {
   int *err;
 };
 
-__device__ __forceinline__ bool mbar_try_wait_cluster(uint32_t bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(bar), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-// bounded like mbar_wait; cluster-scope acquire: the peer's plain stores into our shared memory precede its arrive
-__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity, int *err, int code) {
-  if (mbar_try_wait_cluster(bar, parity)) return;
-  uint64_t t0;
-  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
-  for (;;) {
-    for (int i = 0; i < 2048; i++)
-      if (mbar_try_wait_cluster(bar, parity)) return;
-    uint64_t t1;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 4000000000ull) {
-      if (err) atomicExch(err, code);
-      __threadfence_system();
-      asm volatile("trap;");
-    }
-  }
-}
-__device__ __forceinline__ void st_cluster_v4(uint32_t cluster_addr, float a, float b, float c, float d) {
-  asm volatile("st.shared::cluster.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(cluster_addr), "f"(a), "f"(b), "f"(c), "f"(d)
+// bulk copy from our shared memory into the peer's; the bytes complete on a barrier of the PEER (both shared::cluster addresses)
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
+               "r"(src_cta), "r"(bytes), "r"(bar_cluster)
                : "memory");
 }
-__device__ __forceinline__ void fence_proxy_async_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld16i(uint32_t taddr, uint32_t v[16]) {
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
@@ -161,7 +143,7 @@ fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_cons
     for (int s = 0; s < PHS; s++) { mbar_init(h_full(s), 1); mbar_init(h_empty(s), 1); }
     for (int a = 0; a < 2; a++) {
       mbar_init(s_full(a), 1); mbar_init(s_empty(a), P_EPI_WARPS / 2);
-      mbar_init(q_full(a), P_EPI_WARPS);      // four warps of the step's group in EACH CTA of the cluster
+      mbar_init(q_full(a), P_EPI_WARPS / 2);  // the four local warps of the step's group (+ 8 KB of peer bulk copies)
       mbar_init(q_empty(a), 2);               // the tcgen05.commit of both issuers
     }
     for (int b = 0; b < PXB; b++) { mbar_init(x_full(b), 1); mbar_init(x_empty(b), P_EPI_WARPS / 2); }
@@ -197,12 +179,13 @@ fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_cons
     const uint32_t idesc1 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(PHN >> 3) << 17) | ((uint32_t)(PBM >> 4) << 24);
     const uint32_t idesc2 = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(PKH >> 3) << 17) | ((uint32_t)(PBM >> 4) << 24);
     const uint32_t hi = desc_hi(1024u, 2u);
+    const uint32_t hi64 = desc_hi(512u, 4u);             // Q half tiles: SWIZZLE_64B, 8-row groups 512 B apart
     const uint32_t h_lo = desc_lo(h_s, 16u), q_lo = desc_lo(q_s, 16u);
     uint32_t c1 = 0, c2 = 0, rbc = 0;
     for (int rb = cl_first; rb < p.n_blocks; rb += cl_step, rbc++) {
       mbar_wait(w_full, rbc & 1u, p.err, 3);
       tc_fence_after();
-      for (int j = 0; j <= nsteps; j++) {
+      for (int j = 0; j < nsteps + PLA; j++) {
         if (j < nsteps) {
           // ---- S_r[a] = W . H^T-tile(j)[its 16 features] ----
           const uint32_t s = c1 % PHS, a = c1 & 1u;
@@ -222,23 +205,23 @@ fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_cons
           __syncwarp();
           c1++;
         }
-        if (j >= 1) {
-          // ---- G_r += Q(j-1) . H-tile(j-1)[its 128 components]^T ----
+        if (j >= PLA) {
+          // ---- G_r += Q(j-PLA) . H-tile(j-PLA)[its 128 components]^T ----
           const uint32_t s = c2 % PHS, b = c2 & 1u;
-          mbar_wait_cluster(q_full(b), (c2 >> 1) & 1u, p.err, 6);
-          if (j == 1) mbar_wait(g_empty, (rbc & 1u) ^ 1u, p.err, 7);
+          mbar_wait(q_full(b), (c2 >> 1) & 1u, p.err, 6);
+          if (j == PLA) mbar_wait(g_empty, (rbc & 1u) ^ 1u, p.err, 7);
           tc_fence_after();
           if (elect_one()) {
             const uint32_t al = q_lo + ((b * QTILE_BYTES) >> 4);
             const uint32_t bl = h_lo + ((s * PSTAGE_BYTES + PH1_BYTES) >> 4);
 #pragma unroll
             for (int kk = 0; kk < 4; kk++)
-              umma_tf32<1>(g_tmem, desc_pack(al + ((kk * 32) >> 4), hi), desc_pack(bl + ((kk * 32) >> 4), hi), idesc2,
-                           (j > 1 || kk > 0) ? 1u : 0u);
+              umma_tf32<1>(g_tmem, desc_pack(al + (((kk >> 1) * QHALF_BYTES + (kk & 1) * 32) >> 4), hi64),
+                           desc_pack(bl + ((kk * 32) >> 4), hi), idesc2, (j > PLA || kk > 0) ? 1u : 0u);
             umma_commit<1>(h_empty(s));
             umma_commit<1>(q_empty(b));                    // our Q tile may be rewritten ...
             umma_commit<1>(mapa(q_empty(b), peer));        // ... and the peer, who writes half of it, hears it too
-            if (j == nsteps) { umma_commit<1>(g_full); umma_commit<1>(w_empty); }
+            if (j == nsteps + PLA - 1) { umma_commit<1>(g_full); umma_commit<1>(w_empty); }
           }
           __syncwarp();
           c2++;
@@ -263,9 +246,10 @@ fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_cons
     const int quarter = warp & 3;
     const int grp = e >> 2;                 // the two groups take alternate steps
     const int r = quarter * 32 + lane;
-    const uint32_t sw = (uint32_t)(r & 7);
+    const uint32_t sw = (uint32_t)((r >> 1) & 3);        // SWIZZLE_64B: 16-byte chunk index ^ address bits [7,8]
     const uint32_t lane_addr = (uint32_t)(quarter * 32) << 16;
-    const uint32_t q_peer = mapa(q_s, peer);
+    const uint32_t q_half = q_s + crank * QHALF_BYTES + quarter * (32 * PHN * 4);   // this warp's 32 rows of our half tile
+    const uint32_t q_half_peer = mapa(q_half, peer);
     uint32_t c = 0, rbc = 0;
     double kl = 0.0;
     for (int rb = cl_first; rb < p.n_blocks; rb += cl_step, rbc++) {
@@ -311,7 +295,7 @@ fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_cons
         const uint8_t *xrow = x_gen + xb * XHALF_BYTES + r * 64;
 #pragma unroll
         for (int i = 0; i < 4; i++) {
-          const float4 t = *reinterpret_cast<const float4 *>(xrow + 16 * i);
+          const float4 t = *reinterpret_cast<const float4 *>(xrow + ((((uint32_t)i) ^ sw) << 4));
           x[4 * i] = t.x; x[4 * i + 1] = t.y; x[4 * i + 2] = t.z; x[4 * i + 3] = t.w;
         }
         tmem_ld16w(v);
@@ -329,18 +313,17 @@ fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_cons
         kl_blk += part0 + part1;
         // both issuers are done with Q tile `grp` (ours and the peer's, of which we write half each)
         mbar_wait(q_empty(grp), ph2 ^ 1u, p.err, 11);
-        const uint32_t off = (uint32_t)(grp * QTILE_BYTES + r * 128);
+        const uint32_t off = (uint32_t)(grp * QTILE_BYTES + crank * QHALF_BYTES + r * 64);
 #pragma unroll
-        for (int i = 0; i < 4; i++) {
-          const uint32_t ch = (((uint32_t)(4 * crank + i)) ^ sw) << 4;      // 16-byte chunk inside the swizzled 128-byte row
-          *reinterpret_cast<float4 *>(q_gen + off + ch) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-          st_cluster_v4(q_peer + off + ch, x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-        }
-        fence_proxy_async_all();            // generic-proxy stores (local and remote) before the async-proxy reads of the MMAs
+        for (int i = 0; i < 4; i++)
+          *reinterpret_cast<float4 *>(q_gen + off + ((((uint32_t)i) ^ sw) << 4)) =
+              make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+        fence_proxy_async();                // generic-proxy stores before the async-proxy reads (our MMAs, the bulk copy)
         __syncwarp();
         if (lane == 0) {
-          mbar_arrive(q_full(grp));
-          mbar_arrive_cluster(mapa(q_full(grp), peer));
+          bulk_copy_to_peer(q_half_peer + grp * QTILE_BYTES, q_half + grp * QTILE_BYTES, 32 * PHN * 4, mapa(q_full(grp), peer));
+          if (quarter == 0) mbar_expect_tx(q_full(grp), QHALF_BYTES);   // arrives, and expects the peer's four copies
+          else mbar_arrive(q_full(grp));
         }
       }
       kl += (double)kl_blk;
@@ -411,7 +394,7 @@ int fused_coef_step256(klnmf_ctx *ctx, const FusedDesc &d, int *err_dev) {
   CUtensorMap tmHt, tmH, tmX;
   KL_TRY(make_map_ex(&tmHt, d.Ht, d.ldht, d.F, d.ldht, 32, PHN, CU_TENSOR_MAP_SWIZZLE_128B));   // 32 k x 16 feature rows
   KL_TRY(make_map_ex(&tmH, d.H, d.F, d.K, d.ldh, 32, PKH, CU_TENSOR_MAP_SWIZZLE_128B));          // 32 features x 128 rows
-  KL_TRY(make_map_ex(&tmX, d.X, d.F, d.M, d.ldx, PHN, PBM, CU_TENSOR_MAP_SWIZZLE_NONE));          // 16 features x 128 rows
+  KL_TRY(make_map_ex(&tmX, d.X, d.F, d.M, d.ldx, PHN, PBM, CU_TENSOR_MAP_SWIZZLE_64B));          // 16 features x 128 rows
   Fused256Params p{};
   p.M = d.M; p.F = d.F;
   p.n_blocks = (int)ceil_div(d.M, PBM);
