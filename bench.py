@@ -275,10 +275,13 @@ def phase_roofline(ms, cnt, n_local, f, k, kind, steps, peaks, mode):
     dom = max(names, key=lambda p: ms[p])
     launches = max(cnt[dom], 1)
     flops_per_launch = 2.0 * n_local * k * f * steps / launches        # each contraction is 2 n k f per iteration
-    fused = kind == "dense_transform" and mode == "tf32" and k <= 128 and os.environ.get("KLNMF_FUSED", "1") != "0"
+    fused = kind == "dense_transform" and mode == "tf32" and os.environ.get("KLNMF_FUSED", "1") != "0" and \
+        (k <= 128 or (k <= 256 and os.environ.get("KLNMF_FUSED256", "1") != "0"))
     if fused:
-        # one kernel per iteration does both contractions of the transform (dense_fused.cu): 4 n k f
-        names["ratio"] = "fused_coef_kernel<S=W.H -> Q=(X+eps)/(S+eps), KL -> G+=Q.H^T -> W'=W(.)G>"
+        # one kernel per iteration does both contractions of the transform (dense_fused.cu, k <= 128; on
+        # clusters of two CTAs for 128 < k <= 256, dense_fused256.cu): 4 n k f
+        names["ratio"] = ("fused_coef_kernel" if k <= 128 else "fused_coef256_kernel") + \
+            "<S=W.H -> Q=(X+eps)/(S+eps), KL -> G+=Q.H^T -> W'=W(.)G>"
         dom = "ratio"
         launches = max(cnt[dom], 1)
         flops_per_launch = 4.0 * n_local * k * f * steps / launches
@@ -289,7 +292,8 @@ def phase_roofline(ms, cnt, n_local, f, k, kind, steps, peaks, mode):
         peak = 40.0
     rows_per_launch = int(round(n_local * steps / float(launches)))
     r = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-         "traffic": ncu_traffic("fused" if fused else dom, rows_per_launch, f, k, mode), "rows_per_launch": rows_per_launch,
+         "traffic": ncu_traffic(("fused" if k <= 128 else "fused256") if fused else dom, rows_per_launch, f, k, mode),
+         "rows_per_launch": rows_per_launch,
          "kernel": names[dom], "avg_launch_ms": ms[dom] / launches, "launches": launches,
          "peak_source": ("TF32 = 1/2 x sustained cuBLAS bf16, " + peaks["source"]) if mode != "fp64" else "nominal B200 FP64",
          "phase_ms_per_step": {p: ms[p] / max(steps, 1) for p in ("ratio", "coefficient", "numerator", "dictionary", "allreduce")}}

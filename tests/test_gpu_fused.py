@@ -14,7 +14,7 @@ pytestmark = pytest.mark.gpu
 SHAPES_256 = [
     (128, 32, 130),      # one row block, one step, k just above the single-CTA limit
     (700, 1000, 200),    # ragged rows / features
-    (513, 333, 256),     # full k, features not a multiple of 32 (nor of the 16 per CTA)
+    (513, 333, 256),     # full k, features not a multiple of 64 (nor of the 32 per CTA)
     (4096, 2048, 256),   # many row blocks per cluster: barrier phases wrap
     (300, 4100, 160),
 ]

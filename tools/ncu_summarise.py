@@ -25,7 +25,7 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "sm__cycles_elapsed.max", "launch__registers_per_thread", "launch__grid_size", "launch__block_size",
         "smsp__inst_executed.sum"]
 MATCH = {"ratio": "tc_gemm_kernel<256, 0, 1, 0, 1", "coefficient": "tc_gemm_kernel<256, 0, 0, 0, 0",
-         "numerator": "tc_gemm_kernel<256, 1, 1, 0, 0", "fused": "fused_coef_kernel",
+         "numerator": "tc_gemm_kernel<256, 1, 1, 0, 0", "fused": "fused_coef_kernel", "fused256": "fused_coef256_kernel",
          "sparse_rows": "sparse_rows_kernel", "sparse_scatter": "sparse_numerator_bcsc_kernel"}
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 
