@@ -73,7 +73,7 @@ struct Fused256Params {
   double *kl;
   const int *stop;
   int *err;
-  int dbg;        // timing experiments only (KLNMF_F256_DBG): 1 no exchange, 2 no S MMAs, 4 no G MMAs, 8 no ratio math, 16 half the dictionary loads
+  int dbg;        // timing experiments only (KLNMF_F256_DBG): 1 no exchange, 2 no S MMAs, 4 no G MMAs, 8 no ratio math
 };
 
 // bulk copy from our shared memory into the peer's; the bytes complete on a barrier of the PEER (both shared::cluster addresses)
@@ -81,6 +81,12 @@ __device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t
   asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster),
                "r"(src_cta), "r"(bytes), "r"(bar_cluster)
                : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap *map, uint32_t bar, int32_t c0, int32_t c1, int32_t c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::"r"(dst),
+      "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
 }
 __device__ __forceinline__ void tmem_ld16i(uint32_t taddr, uint32_t v[16]) {
   asm volatile(
@@ -193,12 +199,10 @@ fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_cons
       for (int rb = cl_first; rb < p.n_blocks; rb += cl_step)
         for (int j = 0; j < nsteps; j++, hc++) {
           const uint32_t s = hc % PS1, ph = (hc / PS1) & 1u;
-          const int nld = (p.dbg & 16) ? nkb / 2 : nkb;
           mbar_wait(h1_empty(s), ph ^ 1u, p.err, 2);
-          mbar_expect_tx(h1_full(s), (uint32_t)nld * (PHN * 128));
-          const uint32_t dst = h1_s + s * PH1_BYTES;
-          for (int kb = 0; kb < nld; kb++)
-            tma_load_2d(dst + kb * (PHN * 128), &tmHt, h1_full(s), kb * 32, j * PBN + (int)crank * PHN);
+          mbar_expect_tx(h1_full(s), (uint32_t)nkb * (PHN * 128));
+          // one 3D box: 32 components x 32 feature rows x all K blocks (one instruction instead of eight)
+          tma_load_3d(h1_s + s * PH1_BYTES, &tmHt, h1_full(s), 0, j * PBN + (int)crank * PHN, 0);
         }
     }
   } else if (warp == 11) {
@@ -209,10 +213,10 @@ fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_cons
         for (int j = 0; j < nsteps; j++, hc++) {
           const uint32_t s = hc % PS2, ph = (hc / PS2) & 1u;
           mbar_wait(h2_empty(s), ph ^ 1u, p.err, 14);
-          mbar_expect_tx(h2_full(s), (p.dbg & 16) ? PH2_BYTES / 2 : PH2_BYTES);
+          mbar_expect_tx(h2_full(s), PH2_BYTES);
           const uint32_t dst = h2_s + s * PH2_BYTES;
           tma_load_2d(dst, &tmH, h2_full(s), j * PBN, (int)crank * PKH);
-          if (!(p.dbg & 16)) tma_load_2d(dst + PKH * 128, &tmH, h2_full(s), j * PBN + 32, (int)crank * PKH);
+          tma_load_2d(dst + PKH * 128, &tmH, h2_full(s), j * PBN + 32, (int)crank * PKH);
         }
     }
   } else if (warp == 1) {
@@ -459,7 +463,19 @@ int fused_coef_step256(klnmf_ctx *ctx, const FusedDesc &d, int *err_dev) {
   KL_CHECK(d.K <= PKP && d.ldw % 32 == 0 && d.ldht % 32 == 0 && d.Q == nullptr, KLNMF_EINVAL,
            "fused_coef_step256: k=%lld not supported", (long long)d.K);
   CUtensorMap tmHt, tmH, tmX;
-  KL_TRY(make_map_ex(&tmHt, d.Ht, d.ldht, d.F, d.ldht, 32, PHN, CU_TENSOR_MAP_SWIZZLE_128B));   // 32 k x 32 feature rows
+  {
+    // H^T (f x ldht) as a 3D tensor: 32 components (inner) x f feature rows x ldht/32 component blocks 128 B apart
+    EncodeTiledFn enc = get_encode();
+    KL_CHECK(enc != nullptr, KLNMF_ECUDA, "cuTensorMapEncodeTiled not available from the driver");
+    cuuint64_t dims[3] = {32u, (cuuint64_t)d.F, (cuuint64_t)(d.ldw / 32)};
+    cuuint64_t strides[2] = {(cuuint64_t)d.ldht * 4, 128u};
+    cuuint32_t box[3] = {32u, (cuuint32_t)PHN, (cuuint32_t)(d.ldw / 32)};
+    cuuint32_t estr[3] = {1u, 1u, 1u};
+    CUresult r = enc(&tmHt, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<void *>(d.Ht), dims, strides, box, estr,
+                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                     CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    KL_CHECK(r == CUDA_SUCCESS, KLNMF_ECUDA, "cuTensorMapEncodeTiled (3D H^T) failed with %d", (int)r);
+  }
   KL_TRY(make_map_ex(&tmH, d.H, d.F, d.K, d.ldh, 32, PKH, CU_TENSOR_MAP_SWIZZLE_128B));          // 32 features x 128 rows
   KL_TRY(make_map_ex(&tmX, d.X, d.F, d.M, d.ldx, PHN, PBM, CU_TENSOR_MAP_SWIZZLE_128B));         // 32 features x 128 rows
   Fused256Params p{};
