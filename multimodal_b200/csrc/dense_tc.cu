@@ -316,6 +316,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
   } else if (XT && warp == 10) {
     // =============================== X loader (ratio epilogue) ===============================
     // The ring of XBUFS chunks (16 KB each) covers the HBM latency by itself: 13 B/clk of X per SM x ~2000 clk.
+    // (A rolling chunk-wise L2 prefetch 4 / 8 / 16 chunks ahead was measured too: 4.44 -> 4.64 / 4.53 / 4.92 ms and
+    // 10.7 -> 14.5 GB of DRAM reads per launch at n = 262144, cfg5 shape -- profiles/r1_s4_run41_ratio_x_prefetch.log.)
     if (lane == 0) {
       auto x_tile = [&](int64_t u, int32_t &m0, int32_t &n0, int &nch) {
         int mi, ni, si;
