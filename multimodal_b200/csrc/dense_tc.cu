@@ -47,6 +47,7 @@ struct TcParams {
   uint32_t mn_lt, mn_lbo, mn_sbo, mn_kadv;   // MN-major descriptor parameters (bring-up overridable)
   int no_prefetch;                           // default 1; KLNMF_TC_PF=1 re-enables the L2 prefetch of the next X tile
   int relaxed;                               // accumulator hand-back with relaxed arrives (KLNMF_TC_RELAXED=0: release)
+  int dbg;                                   // timing experiments (KLNMF_TC_DBG): 1 no ratio math, 2 no Q store, 4 one MMA per K block only
   uint32_t k_lt;                             // K-major layout type: 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B (experiment)
 };
 
@@ -55,13 +56,15 @@ struct TcParams {
 // XB = X chunks in flight per CTA (XT only; their HBM latency is hidden by the L2 prefetch of the next tile,
 // so the ring covers L2 latency only).  Everything the X ring and the Q staging do not take goes to operand
 // stages: with K = 512 the ratio contraction is bound by the TMA latency of its operand ring, not by smem.
-template <int BN, bool SPLIT, bool XT = false, int CG = 1, int XB = 2>
+// QIP = the ratio is written back IN PLACE into the X chunk it was computed from and leaves by TMA store from
+// there: the 32 KB of Q staging boxes become two more X chunks in flight.
+template <int BN, bool SPLIT, bool XT = false, int CG = 1, int XB = 2, bool QIP = false>
 struct Cfg {
   static constexpr int A_BYTES = BM * BK * 4;
   static constexpr int B_BYTES = (BN / CG) * BK * 4;     // a CTA pair splits the B tile
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (SPLIT ? 2 : 1);
   static constexpr int XBUFS = XB;
-  static constexpr int XQ_BYTES = XT ? XB * XCHUNK_BYTES + EPI_WARPS * QWARP_BYTES : 0;
+  static constexpr int XQ_BYTES = XT ? XB * XCHUNK_BYTES + (QIP ? 0 : EPI_WARPS * QWARP_BYTES) : 0;
   static constexpr int STAGES = (XT ? (224 * 1024 - XQ_BYTES) : 192 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;   // power of two: 256 or 512
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + XQ_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -158,12 +161,12 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams &p, int64_t row, i
 // XT = true: the ratio contraction (EPI_RATIO, A K-major, B MN-major) with X streamed into a
 // 128B-swizzled smem ring by TMA (warp 10) and Q leaving through smem + TMA store, so that both
 // cross HBM as full 128-byte lines instead of one 16-byte piece per thread and row.
-template <int BN, bool A_MN, bool B_MN, bool SPLIT, bool XT, int CG, int XB>
+template <int BN, bool A_MN, bool B_MN, bool SPLIT, bool XT, int CG, int XB, bool QIP>
 __global__ void __launch_bounds__(XT ? NUM_THREADS_XT : NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQ, const TcParams p) {
-  using C = Cfg<BN, SPLIT, XT, CG, XB>;
+  using C = Cfg<BN, SPLIT, XT, CG, XB, QIP>;
   constexpr int STAGES = C::STAGES;
   constexpr int XBUFS = C::XBUFS;
   if (p.stop != nullptr && *p.stop != 0) return;
@@ -291,6 +294,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t al = a_lo0 + soff, bl = b_lo0 + soff;
 #pragma unroll
             for (int kk = 0; kk < BK / UMMA_K; kk++) {
+              if ((p.dbg & 4) && kk > 0) break;
               const uint64_t da = desc_pack(al + kk * a_kadv, a_hi);
               const uint64_t db = desc_pack(bl + kk * b_kadv, b_hi);
               const uint32_t first = (kb > 0 || kk > 0) ? 1u : 0u;
@@ -363,6 +367,16 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     int acc = 0; uint32_t acc_phase = 0;
     uint32_t gbase = 0;
     double kl = 0.0;
+    // QIP: the chunk whose Q store may still be reading its box; handed back to the X loader one chunk later
+    // (or at the end of the tile), when that read has long finished
+    bool pending = false;
+    uint32_t pend_b = 0;
+    auto release_pending = [&]() {
+      if (pending) {
+        if (lane == 0) { bulk_wait_read0(); mbar_arrive(xempty_bar(pend_b)); }
+        pending = false;
+      }
+    };
     for (int64_t u = u_first; u < total_units; u += u_step) {
       int mi, ni, si;
       decode(u, mi, ni, si);
@@ -378,6 +392,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + c * 32);
         uint32_t v[32];
         tmem_ld32_issue(taddr, v);
+        if (QIP) release_pending();
         mbar_wait(xfull_bar(b), ph, p.err, 6);
         float x[32];
         const uint8_t *xrow = xq_gen + b * XCHUNK_BYTES + r * 128;
@@ -388,11 +403,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         tmem_ld32_wait(v);
         __syncwarp();
-        if (lane == 0) mbar_arrive(xempty_bar(b));
+        if ((!QIP || p.only_kl) && lane == 0) mbar_arrive(xempty_bar(b));
         // rows >= M and columns >= N hold x = 0, s = 0 (TMA zero fill): q = 1, the term is exactly 0
         float part0 = 0.f, part1 = 0.f;
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
+          if (p.dbg & 1) break;
           float q0, q1;
           part0 += ratio_term<false>(x[j], __uint_as_float(v[j]), q0);
           part1 += ratio_term<false>(x[j + 1], __uint_as_float(v[j + 1]), q1);
@@ -400,17 +416,32 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         }
         kl_tile += part0 + part1;
         if (!p.only_kl) {
-          if (lane == 0) bulk_wait_read0();         // the previous store has finished reading the box
-          __syncwarp();
+          if (QIP) {
+            // in place: every thread overwrites the row of X it has just read; the warp's 32 rows are one 4 KB box
+            uint8_t *qrow = xq_gen + b * XCHUNK_BYTES + r * 128;
 #pragma unroll
-          for (int j = 0; j < 8; j++)
-            *reinterpret_cast<float4 *>(qst_gen + ((j ^ sw) << 4)) =
-                make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-          fence_proxy_async();
-          __syncwarp();
-          if (lane == 0) tma_store_2d(&tmQ, qst, n0 + 32 * c, m0 + quarter * 32);
+            for (int j = 0; j < 8; j++)
+              *reinterpret_cast<float4 *>(qrow + ((j ^ sw) << 4)) =
+                  make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && !(p.dbg & 2)) tma_store_2d(&tmQ, xq_base + b * XCHUNK_BYTES + quarter * QWARP_BYTES, n0 + 32 * c, m0 + quarter * 32);
+            pending = true;
+            pend_b = b;
+          } else {
+            if (lane == 0) bulk_wait_read0();         // the previous store has finished reading the box
+            __syncwarp();
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+              *reinterpret_cast<float4 *>(qst_gen + ((j ^ sw) << 4)) =
+                  make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            fence_proxy_async();
+            __syncwarp();
+            if (lane == 0 && !(p.dbg & 2)) tma_store_2d(&tmQ, qst, n0 + 32 * c, m0 + quarter * 32);
+          }
         }
       }
+      if (QIP) release_pending();
       gbase += (uint32_t)nch;
       kl += (double)kl_tile;
       tc_fence_before();
@@ -488,9 +519,9 @@ struct TcState {
   int *err_dev = nullptr;
 };
 
-template <int BN, bool A_MN, bool B_MN, bool SPLIT, bool XT = false, int CG = 1, int XB = 2>
+template <int BN, bool A_MN, bool B_MN, bool SPLIT, bool XT = false, int CG = 1, int XB = 2, bool QIP = false>
 int launch_cfg(klnmf_ctx *ctx, const GemmDesc &d, TcParams p) {
-  using C = Cfg<BN, SPLIT, XT, CG, XB>;
+  using C = Cfg<BN, SPLIT, XT, CG, XB, QIP>;
   static_assert(C::STAGES >= 2, "pipeline too shallow");
   static_assert(C::SMEM_BYTES <= 232448, "shared memory budget exceeded");
   CUtensorMap tmA, tmAlo, tmB, tmBlo, tmX, tmQ;
@@ -543,7 +574,7 @@ int launch_cfg(klnmf_ctx *ctx, const GemmDesc &d, TcParams p) {
   const int64_t units = (int64_t)p.m_tiles * p.n_tiles * p.splits;
   if (units == 0 || p.kb_total == 0) return KLNMF_OK;
   const int grid = (int)(units < slots ? units : slots) * CG;
-  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, SPLIT, XT, CG, XB>;
+  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, SPLIT, XT, CG, XB, QIP>;
   static bool attr_done = false;
   if (!attr_done) {
     KL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -613,6 +644,7 @@ int tc_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d) {
   p.mn_lt = 1; p.mn_lbo = 4096; p.mn_sbo = 512; p.mn_kadv = 1024;
   // measured (profiles/r1_dram_traffic_variants.log): cp.async.bulk.prefetch.tensor of the next X tile made the
   // kernel read X from HBM twice (8.6 GB instead of 4.6 GB at n = 131072) and 14 % slower -- off by default
+  p.dbg = getenv("KLNMF_TC_DBG") ? atoi(getenv("KLNMF_TC_DBG")) : 0;
   p.no_prefetch = !(getenv("KLNMF_TC_PF") && atoi(getenv("KLNMF_TC_PF")) == 1);
   p.relaxed = !(getenv("KLNMF_TC_RELAXED") && atoi(getenv("KLNMF_TC_RELAXED")) == 0);
   if (const char *o = getenv("KLNMF_TC_MN")) {   // "layout_type,lbo,sbo,kadv" (bring-up only)
@@ -626,11 +658,18 @@ int tc_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d) {
   // the ratio contraction of the loop: X and Q go through shared memory by TMA
   if (!a_mn && b_mn && epi == EPI_RATIO && !split && !narrow && !getenv("KLNMF_TC_NO_XT")) {
     if (getenv("KLNMF_TC_CG") && atoi(getenv("KLNMF_TC_CG")) == 1) return launch_cfg<256, false, true, false, true, 1, 4>(ctx, d, p);
-    // long contractions (k >= 512) are bound by the latency of the operand ring: 5 stages + an X ring of 2
-    // chunks; shorter ones consume X faster than operands: 4 stages + 4 chunks (measured on cfg5 / cfg3,
-    // profiles/r1_ratio_ring_balance.log).  KLNMF_TC_XB=2|4 forces one.
+    // Ring balance (profiles/r1_ratio_ring_balance.log, r1_s4_run42/43_*.log): k >= 512 wants 5 operand stages; the
+    // ratio is then written back IN PLACE into the X chunk it came from (QIP), which turns the 32 KB of Q staging boxes
+    // into two more X chunks in flight (4.51 -> 4.31 ms at n = 262144, cfg5 shape).  Shorter contractions consume X
+    // faster than operands: 4 stages + 4 chunks + staging boxes.  KLNMF_TC_XB / KLNMF_TC_QIP force a variant.
     int xb = d.K >= 512 ? 2 : 4;
+    bool qip = d.K >= 512;
     if (getenv("KLNMF_TC_XB")) xb = atoi(getenv("KLNMF_TC_XB"));
+    if (getenv("KLNMF_TC_QIP")) qip = atoi(getenv("KLNMF_TC_QIP")) == 1;
+    if (qip) {
+      if (xb == 6) return launch_cfg<256, false, true, false, true, 2, 6, true>(ctx, d, p);
+      return launch_cfg<256, false, true, false, true, 2, 4, true>(ctx, d, p);
+    }
     if (xb == 2) return launch_cfg<256, false, true, false, true, 2, 2>(ctx, d, p);
     return launch_cfg<256, false, true, false, true, 2, 4>(ctx, d, p);
   }
