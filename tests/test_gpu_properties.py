@@ -1,0 +1,171 @@
+"""-m gpu: size-independent properties of the KL-NMF path, checked where the float64 oracle is too slow to run:
+at the feature / component shapes of BASELINE.json's large configs (cfg3, cfg4, cfg5) and, for cfg3, at its
+full sample count.
+
+Properties (all follow from the reference's update rules, nmf.py:325-351, array_utils.py:19-22):
+  * rows are independent given the dictionary: transforming a subset of the samples gives the same coefficients
+    as the matching rows of the full transform (this is what sample sharding, SURVEY 8e, relies on);
+  * scale equivariance: X -> cX gives W -> cW and the same dictionary (W0 = X.H0^T scales, Q does not -- up to
+    eps = 1e-8 against the data);
+  * W >= 0, H >= 0, rows of H sum to 1 after a fit iteration, the objective never rises beyond the noise of the
+    mode, a transform leaves the dictionary untouched;
+  * the fused and the three-contraction form of an iteration agree (k <= 128, and the cluster kernel up to 256).
+"""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from multimodal_b200 import _native
+from multimodal_b200.lib.nmf import KLdivNMF
+from oracle import cases, klnmf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+NOISE = {"fp64": 1e-12, "tf32x3": 1e-6, "tf32": 1e-4}      # relative rise of the objective a mode may show
+
+
+def transform(X, H, iters, mode):
+    est = KLdivNMF(n_components=H.shape[0], max_iter=iters, tol=0, mode=mode)
+    est.components_ = H
+    return est.transform(X)
+
+
+@pytest.mark.parametrize("mode,k", [("tf32", 256), ("tf32", 100), ("tf32x3", 256), ("fp64", 64)])
+def test_transform_rows_are_independent(mode, k):
+    rs = np.random.RandomState(3)
+    n, f = 1500, 1024
+    X = rs.gamma(0.5, 1.0, size=(n, f))
+    np.random.seed(4)
+    H = O.init_dictionary(k, f)
+    W = transform(X, H, 6, mode)
+    idx = np.sort(rs.choice(n, 300, replace=False))
+    W_sub = transform(X[idx], H, 6, mode)
+    # same arithmetic per row whatever block the row sits in: only the position inside an MMA tile changes
+    assert cases.rel_fro(W_sub, W[idx]) < (1e-12 if mode == "fp64" else 1e-6)
+
+
+@pytest.mark.parametrize("sparse", [False, True], ids=["dense", "csr"])
+@pytest.mark.parametrize("mode", ["fp64", "tf32x3"])
+def test_scale_equivariance(mode, sparse):
+    rs = np.random.RandomState(8)
+    n, f, k, c = 400, 300, 12, 8.0              # a power of two: scaling commutes with every rounding
+    X = rs.gamma(0.7, 1.0, size=(n, f)) + 0.05
+    if sparse:
+        X[rs.random_sample((n, f)) < 0.9] = 0.0
+        X = sp.csr_matrix(X)
+    outs = []
+    for s in (1.0, c):
+        est = KLdivNMF(n_components=k, max_iter=8, tol=0, mode=mode)
+        np.random.seed(2)
+        W = est.fit_transform(X * s)
+        outs.append((W, est.components_))
+    # eps = 1e-8 sits on both sides of the ratio (nmf.py:336), so the equivariance holds to eps / min(x, s)
+    assert cases.rel_fro(outs[1][0], c * outs[0][0]) < 1e-5
+    assert cases.rel_fro(outs[1][1], outs[0][1]) < 1e-5
+
+
+def check_fit_state(W, H, errs, mode):
+    assert np.isfinite(W).all() and np.isfinite(H).all() and np.isfinite(errs).all()
+    assert (W >= 0).all() and (H >= 0).all()
+    np.testing.assert_allclose(H.sum(axis=1), 1.0, rtol=0, atol=1e-5)
+    rises = (errs[1:] - errs[:-1]) / np.abs(errs[:-1])
+    assert (rises < NOISE[mode]).all(), rises
+
+
+@pytest.mark.parametrize("mode", ["tf32", "tf32x3"])
+def test_cfg5_shape_fit_properties(mode):
+    """f = 8192, k = 512 (BASELINE.json configs[4]) on 32768 device-generated samples."""
+    n, f, k = 32768, 8192, 512
+    np.random.seed(11)
+    H0 = O.init_dictionary(k, f)
+    with _native.Engine(n, f, k, mode=mode) as e:
+        e.fill_dense_synthetic(5)
+        e.set_dictionary(H0)
+        e.init_coefficients()
+        errs, n_iter = e.run(6, 0.0, True)
+        W, H = e.get_coefficients(), e.get_dictionary()
+    assert n_iter == 6 and len(errs) == 6
+    check_fit_state(W, H, np.asarray(errs), mode)
+    assert errs[-1] < errs[0]
+
+
+def test_cfg5_shape_modes_agree():
+    n, f, k = 8192, 8192, 512
+    np.random.seed(11)
+    H0 = O.init_dictionary(k, f)
+    out = {}
+    for mode in ("tf32", "tf32x3", "fp64"):
+        with _native.Engine(n, f, k, mode=mode) as e:
+            e.fill_dense_synthetic(5)            # the same generator and seed in every mode
+            e.set_dictionary(H0)
+            e.init_coefficients()
+            errs, _ = e.run(4, 0.0, True)
+            out[mode] = (e.get_coefficients(), e.get_dictionary(), np.asarray(errs))
+    # The tensor core accumulates FP32 with truncation, and every term of an NMF contraction is non-negative: the
+    # coefficient contraction over f = 8192 features drifts by ~1e-8 f from float64 (measured 8.1e-5 in tf32x3, whose
+    # three MMAs per step truncate three times; 3.0e-5 in tf32 -- tools/accuracy_vs_shape.py).
+    # The normalised dictionary and the objective (a contraction over k only) keep the tolerances of the small cases.
+    tol_w = {"tf32x3": 2e-4, "tf32": 3e-3}
+    tol_h = {"tf32x3": 2e-5, "tf32": 3e-3}
+    tol_kl = {"tf32x3": 1e-4, "tf32": 1e-2}
+    for mode in ("tf32x3", "tf32"):
+        assert cases.rel_fro(out[mode][0], out["fp64"][0]) < tol_w[mode]
+        assert cases.rel_fro(out[mode][1], out["fp64"][1]) < tol_h[mode]
+        np.testing.assert_allclose(out[mode][2], out["fp64"][2], rtol=tol_kl[mode])
+
+
+def test_cfg4_shape_sparse_fit_properties():
+    """f = 50 000, k = 256, 250 stored entries per row (BASELINE.json configs[3]) on 65536 device-generated samples:
+    several row blocks of the blocked-CSC numerator."""
+    n, f, k = 65536, 50000, 256
+    np.random.seed(12)
+    H0 = O.init_dictionary(k, f)
+    res = {}
+    for mode in ("tf32", "fp64"):
+        with _native.Engine(n, f, k, mode=mode) as e:
+            e.fill_csr_synthetic(250, 9)
+            e.set_dictionary(H0)
+            e.init_coefficients()
+            errs, n_iter = e.run(5, 0.0, True)
+            res[mode] = (e.get_coefficients(), e.get_dictionary(), np.asarray(errs))
+        assert n_iter == 5
+        check_fit_state(res[mode][0], res[mode][1], res[mode][2], "tf32x3" if mode == "tf32" else mode)
+    # the sparse path computes in FP32 FMA in the tf32 modes: 2e-5 against its own float64 mode
+    assert cases.rel_fro(res["tf32"][0], res["fp64"][0]) < 2e-5
+    assert cases.rel_fro(res["tf32"][1], res["fp64"][1]) < 2e-5
+    np.testing.assert_allclose(res["tf32"][2], res["fp64"][2], rtol=2e-5)
+
+
+def run_cfg3(n, fused256):
+    f, k = 4096, 256
+    np.random.seed(13)
+    H = O.init_dictionary(k, f)
+    os.environ["KLNMF_FUSED256"] = "1" if fused256 else "0"
+    try:
+        with _native.Engine(n, f, k, mode="tf32") as e:
+            e.fill_dense_synthetic(6)
+            e.set_dictionary(H)
+            e.init_coefficients()
+            c0 = e.counters()["launches"]
+            errs, n_iter = e.run(4, 0.0, False)
+            launches = e.counters()["launches"] - c0
+            H_after = e.get_dictionary()
+            return e.get_coefficients(), np.asarray(errs), launches, H, H_after
+    finally:
+        os.environ.pop("KLNMF_FUSED256", None)
+
+
+def test_cfg3_full_size_transform_fused_equals_unfused():
+    """BASELINE.json configs[2] at its full size: 1 000 000 x 4096, k = 256 (16.4 GB of X generated on the device);
+    the cluster kernel (dense_fused256.cu) against the three-contraction form, plus the transform properties."""
+    n = 1000000
+    Wf, ef, lf, H, Hf = run_cfg3(n, True)
+    Wu, eu, lu, _, _ = run_cfg3(n, False)
+    assert lf < lu, "the cluster kernel must be the one that ran"
+    assert Wf.shape == (n, 256) and np.isfinite(Wf).all() and (Wf >= 0).all()
+    assert cases.rel_fro(Hf, H) < 1e-7            # a transform leaves the dictionary as it was (float32 storage)
+    assert ((ef[1:] - ef[:-1]) / ef[:-1] < NOISE["tf32"]).all() and ef[-1] < ef[0]
+    np.testing.assert_allclose(ef, eu, rtol=1e-4)
+    assert cases.rel_fro(Wf, Wu) < 1e-3
