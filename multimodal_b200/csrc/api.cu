@@ -98,6 +98,10 @@ int ensure_state(klnmf_ctx *ctx) {
   KL_CUDA(cudaMemsetAsync(ctx->dred, 0, ctx->dred_len * 8, ctx->stream));
   KL_TRY(dmalloc((void **)&ctx->rowsumH, (ctx->k + 1) * 8));
   KL_TRY(dmalloc((void **)&ctx->hsum, (ctx->k + 1) * 8));
+  KL_TRY(dmalloc((void **)&ctx->colsumW, (ctx->ldw + 32) * 8));
+  KL_CUDA(cudaMemsetAsync(ctx->colsumW, 0, (ctx->ldw + 32) * 8, ctx->stream));
+  KL_TRY(dmalloc((void **)&ctx->rsh32, (ctx->ldw + 32) * 4));
+  KL_CUDA(cudaMemsetAsync(ctx->rsh32, 0, (ctx->ldw + 32) * 4, ctx->stream));
   KL_CUDA(cudaMemsetAsync(ctx->rowsumH, 0, (ctx->k + 1) * 8, ctx->stream));
   if (!ctx->sparse) {
     const int64_t per_row = round_up(ctx->f, 32) * es * (ctx->split ? 2 : 1);
@@ -300,6 +304,19 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
   const int cur = ctx->cur, hc = ctx->hcur;
   const int *stop = only_error ? nullptr : ctx->flags + FL_STOP;
   const bool fused = !only_error && !dict_only && !ratio_host && fused_supported(ctx, fit) && ctx->n > 0;
+  // Centered ratio (split-TF32 mode, the iterations of klnmf_run): the panel holds Q - 1 instead of Q, so that the long
+  // contractions sum terms of both signs around zero instead of non-negative terms -- the tensor core accumulates FP32
+  // with truncation, which otherwise costs ~1e-8 f of relative error on W (8e-5 at f = 8192).  The
+  // missing parts are exact and cheap: G = (Q-1).H^T + rowsum(H) in the coefficient epilogue, N = W'^T.(Q-1) +
+  // colsum(W') in the dictionary update.  The parity hooks (_Q, _updated_H) and klnmf_error keep the plain form, and so
+  // does the one-pass tf32 mode: there the tensor core also truncates the operands themselves, a bias that cancels
+  // between S = W.H and G = Q.H^T in the plain form and would not in the centered one (measured 3e-5 -> 7e-4 on W).
+  const bool centered = dense_tc(ctx) && ctx->split && !only_error && !dict_only && !ratio_host &&
+                        !(getenv("KLNMF_CENTER") && atoi(getenv("KLNMF_CENTER")) == 0);
+  ctx->centered = centered;
+  const float qshift = centered ? 1.f : 0.f;
+  const float *colbias = centered ? ctx->rsh32 : nullptr;
+  if (centered) KL_TRY(launch_rsh32(ctx));
   if (fused) {
     // k <= 128 (fit, transform) / k <= 256 (transform): the coefficient half-step is one fused kernel, the ratio
     // never leaves the SM (dense_fused.cu, dense_fused256.cu)
@@ -325,6 +342,7 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
     d.X = ctx->X; d.ldx = ctx->ldx;
     d.Wout = ctx->W[cur ^ 1]; d.ldwo = ctx->ldw;
     d.kl = ctx->dred; d.stop = stop;
+    d.qshift = qshift; d.colbias = colbias;
     return fused_coef_step(ctx, d);
   }
   for (int64_t r0 = 0; r0 < ctx->n; r0 += ctx->panel_rows) {
@@ -344,6 +362,7 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
       d.Wout = Wn; d.ldwo = ctx->ldw;
       d.Q = ctx->Q; d.ldq = ctx->ldq;
       d.kl = ctx->dred; d.stop = stop;
+      d.qshift = qshift; d.colbias = colbias;
       KL_TRY(fused_coef_step(ctx, d));
     } else {  // ratio + objective: Q = (X+eps)/(W.H+eps)   (nmf.py:325-336, metrics.py:18-20)
       PhaseTimer t(ctx, prof, PH_RATIO);
@@ -354,6 +373,7 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
       d.out = ctx->Q; d.ldo = ctx->ldq; d.out_lo = ctx->Qlo;
       d.aux = (const char *)ctx->X + r0 * ctx->ldx * es; d.ldaux = ctx->ldx;
       d.kl = ctx->dred; d.stop = stop; d.only_kl = only_error ? 1 : 0;
+      d.qshift = qshift;
       KL_TRY(dense_gemm(ctx, EPI_RATIO, d));
     }
     if (ratio_host) {   // _Q parity hook: hand the ratio panel back to the host
@@ -372,6 +392,7 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
       d.out = Wn; d.ldo = ctx->ldw; d.out_lo = Wnlo;
       d.aux = Wc; d.ldaux = ctx->ldw; d.aux_lo = Wclo;
       d.stop = stop;
+      d.colbias = colbias;
       KL_TRY(dense_gemm(ctx, EPI_MULW, d));
     }
     if (fit) {  // dictionary numerator: N += W'^T.Q  (stale Q, new W: nmf.py:345-349)
@@ -386,6 +407,8 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
       KL_TRY(dense_gemm(ctx, EPI_ACC, d));
     }
   }
+  // colsum(W') of this rank joins the all-reduced doubles (slots the sparse objective uses for colsum(W))
+  if (fit && centered) KL_TRY(launch_colsum_w(ctx, ctx->W[cur ^ 1], ctx->split ? ctx->Wlo[cur ^ 1] : nullptr, ctx->dred + 2));
   return KLNMF_OK;
 }
 
@@ -473,7 +496,7 @@ int klnmf_destroy(klnmf_ctx *ctx) {
     if (ctx->Wlo[i]) cudaFree(ctx->Wlo[i]);
     if (ctx->Hlo[i]) cudaFree(ctx->Hlo[i]);
   }
-  void *ptrs[] = {ctx->num, ctx->rowsumH, ctx->hsum, ctx->dred, ctx->stage, ctx->Q, ctx->Qlo,
+  void *ptrs[] = {ctx->num, ctx->rowsumH, ctx->hsum, ctx->colsumW, ctx->rsh32, ctx->dred, ctx->stage, ctx->Q, ctx->Qlo,
                   ctx->dscal, ctx->flags, ctx->errors_dev};
   for (void *p : ptrs)
     if (p) cudaFree(p);
@@ -787,9 +810,9 @@ int klnmf_run(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, double *err
       PhaseTimer t(ctx, prof, PH_DICT);
       const int hc = ctx->hcur;
       rc = ctx->sparse ? launch_dict_update_t(ctx, ctx->H[hc], ctx->H[hc ^ 1])
-                       : launch_dict_update(ctx, ctx->H[hc], ctx->H[hc ^ 1], ctx->split ? ctx->Hlo[hc ^ 1] : nullptr);
+                       : launch_dict_update(ctx, ctx->H[hc], ctx->H[hc ^ 1], ctx->split ? ctx->Hlo[hc ^ 1] : nullptr,
+                                            ctx->centered ? ctx->colsumW : nullptr);
       ctx->hcur ^= 1;
-  ctx->ht_stale = true;
       ctx->ht_stale = true;
     }
     ctx->cur ^= 1;

@@ -85,7 +85,9 @@ struct klnmf_ctx {
   void *Hlo[2] = {nullptr, nullptr};
   void *num = nullptr;         // numerator accumulator, same layout as H
   double *rowsumH = nullptr;   // k   (sum over f of H, used by the sparse objective)
-  double *colsumW = nullptr;   // k
+  double *colsumW = nullptr;   // k   (dense, centered ratio: column sums of the new coefficients, all ranks)
+  float *rsh32 = nullptr;      // ldw + 32 floats: rowsumH as FP32, zero beyond k (bias of the centered coefficient update)
+  bool centered = false;       // this iteration's ratio panel holds Q - 1 (see dense_iteration)
   double *hsum = nullptr;      // k   scratch of the normaliser
   double *dred = nullptr;      // [kl, sum(X.data), colsum(W)[0..ldw)] : the doubles that are all-reduced
   int64_t dred_len = 0;
@@ -142,6 +144,8 @@ struct GemmDesc {
   const int *stop;                       // device stop flag: kernel exits when *stop != 0
   int splitk;                            // EPI_ACC only
   int only_kl;                           // EPI_RATIO: do not write out (klnmf_error)
+  float qshift;                          // EPI_RATIO: the stored ratio is q - qshift (1 = centered, 0 = plain)
+  const float *colbias;                  // EPI_MULW: out = aux * (C + colbias[col]) (nullptr: no bias)
   // split-TF32 residual arrays (same layout as their high parts); nullptr unless ctx->split
   const void *A_lo; const void *B_lo; void *out_lo; const void *aux_lo;
 };
@@ -164,6 +168,8 @@ struct FusedDesc {
   double *kl;                        // objective accumulator or nullptr
   const int *stop;
   int only_kl;
+  float qshift;                      // the ratio tile holds q - qshift
+  const float *colbias;              // W' = W (.) (G + colbias[component]) (nullptr: no bias)
 };
 bool fused_supported(const klnmf_ctx *ctx, int fit);
 int fused_coef_step256(klnmf_ctx *ctx, const FusedDesc &d, int *err_dev);   // 128 < k <= 256, transform, CTA pairs
@@ -171,7 +177,9 @@ int fused_coef_step(klnmf_ctx *ctx, const FusedDesc &d);
 void fused_release(klnmf_ctx *ctx);
 
 // ---- elementwise / reductions: elementwise.cu ----------------------------------------------------
-int launch_dict_update(klnmf_ctx *ctx, const void *H_old, void *H_new, void *Hlo_new);
+int launch_dict_update(klnmf_ctx *ctx, const void *H_old, void *H_new, void *Hlo_new, const double *rowadd = nullptr);
+int launch_rsh32(klnmf_ctx *ctx);           // rsh32 <- rowsumH (FP32, zero padded)
+int launch_colsum_w(klnmf_ctx *ctx, const void *W, const void *Wlo, double *out);   // out[a] += sum_i W[i,a]
 int launch_dict_update_t(klnmf_ctx *ctx, const void *Ht_old, void *Ht_new);     // sparse: f x k layout
 int launch_decide(klnmf_ctx *ctx, int iter_index);
 int launch_split(klnmf_ctx *ctx, const float *src, float *hi, float *lo, int64_t rows, int64_t cols, int64_t ld);

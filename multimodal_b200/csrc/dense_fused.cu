@@ -66,6 +66,8 @@ struct FusedParams {
   const int *stop;
   int *err;
   int only_kl;
+  float qshift;            // the ratio tile holds q - qshift (centered ratio, api.cu)
+  const float *colbias;    // W' = W (.) (G + colbias[component])
   int lookahead;           // steps the first contraction runs ahead of the second one (1 or 2)
 };
 
@@ -327,7 +329,7 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
           float q0, q1;
           part0 += ratio_term<false>(x[i], __uint_as_float(v[i]), q0);
           part1 += ratio_term<false>(x[i + 1], __uint_as_float(v[i + 1]), q1);
-          x[i] = q0; x[i + 1] = q1;
+          x[i] = q0 - p.qshift; x[i + 1] = q1 - p.qshift;
         }
         kl_blk += part0 + part1;
         if (!p.only_kl) {
@@ -374,9 +376,11 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 #pragma unroll
           for (int i = 0; i < 4; i++) {
             const float4 w = __ldg(reinterpret_cast<const float4 *>(wi + 4 * i));
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.colbias) b = __ldg(reinterpret_cast<const float4 *>(p.colbias + col0 + 4 * i));
             *reinterpret_cast<float4 *>(wo + 4 * i) =
-                make_float4(w.x * __uint_as_float(v[4 * i]), w.y * __uint_as_float(v[4 * i + 1]),
-                            w.z * __uint_as_float(v[4 * i + 2]), w.w * __uint_as_float(v[4 * i + 3]));
+                make_float4(w.x * (__uint_as_float(v[4 * i]) + b.x), w.y * (__uint_as_float(v[4 * i + 1]) + b.y),
+                            w.z * (__uint_as_float(v[4 * i + 2]) + b.z), w.w * (__uint_as_float(v[4 * i + 3]) + b.w));
           }
         }
       }
@@ -464,6 +468,7 @@ int fused_coef_step(klnmf_ctx *ctx, const FusedDesc &d) {
   p.Wout = (float *)d.Wout; p.ldwo = d.ldwo;
   p.w_cols = d.ldw < d.ldwo ? d.ldw : d.ldwo;
   p.kl = d.kl; p.stop = d.stop; p.err = st->err_dev; p.only_kl = d.only_kl;
+  p.qshift = d.qshift; p.colbias = d.colbias;
   // default: W block in TMEM ("TS" form of tcgen05.mma); KLNMF_FUSED_TS=0 keeps it in shared memory
   const bool ts = !(getenv("KLNMF_FUSED_TS") && atoi(getenv("KLNMF_FUSED_TS")) == 0);
   const int v = getenv("KLNMF_FUSED_V") ? atoi(getenv("KLNMF_FUSED_V")) : 0;

@@ -73,6 +73,8 @@ struct Fused256Params {
   double *kl;
   const int *stop;
   int *err;
+  float qshift;   // the ratio tile holds q - qshift (centered ratio, api.cu)
+  const float *colbias;   // W' = W (.) (G + colbias[component])
   int dbg;        // timing experiments only (KLNMF_F256_DBG): 1 no exchange, 2 no S MMAs, 4 no G MMAs, 8 no ratio math
 };
 
@@ -380,7 +382,7 @@ fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_cons
           float q0, q1;
           part0 += ratio_term<false>(x[i], __uint_as_float(v[i]), q0);
           part1 += ratio_term<false>(x[i + 1], __uint_as_float(v[i + 1]), q1);
-          x[i] = q0; x[i + 1] = q1;
+          x[i] = q0 - p.qshift; x[i + 1] = q1 - p.qshift;
         }
         kl_blk += part0 + part1;
         // both issuers are done with Q tile `grp` (ours and the peer's, of which we write half each)
@@ -413,10 +415,13 @@ fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_cons
         if (row < p.M && col0 < p.w_cols) {
           float *wo = p.Wout + row * p.ldwo + col0;
 #pragma unroll
-          for (int i = 0; i < 4; i++)
+          for (int i = 0; i < 4; i++) {
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.colbias) b = __ldg(reinterpret_cast<const float4 *>(p.colbias + col0 + 4 * i));
             *reinterpret_cast<float4 *>(wo + 4 * i) =
-                make_float4(__uint_as_float(w[4 * i]) * __uint_as_float(v[4 * i]), __uint_as_float(w[4 * i + 1]) * __uint_as_float(v[4 * i + 1]),
-                            __uint_as_float(w[4 * i + 2]) * __uint_as_float(v[4 * i + 2]), __uint_as_float(w[4 * i + 3]) * __uint_as_float(v[4 * i + 3]));
+                make_float4(__uint_as_float(w[4 * i]) * (__uint_as_float(v[4 * i]) + b.x), __uint_as_float(w[4 * i + 1]) * (__uint_as_float(v[4 * i + 1]) + b.y),
+                            __uint_as_float(w[4 * i + 2]) * (__uint_as_float(v[4 * i + 2]) + b.z), __uint_as_float(w[4 * i + 3]) * (__uint_as_float(v[4 * i + 3]) + b.w));
+          }
         }
       }
       tc_fence_before();
@@ -487,6 +492,7 @@ int fused_coef_step256(klnmf_ctx *ctx, const FusedDesc &d, int *err_dev) {
   p.Wout = (float *)d.Wout; p.ldwo = d.ldwo;
   p.w_cols = d.ldw < d.ldwo ? d.ldw : d.ldwo;
   p.kl = d.kl; p.stop = d.stop; p.err = err_dev;
+  p.qshift = d.qshift; p.colbias = d.colbias;
   p.dbg = getenv("KLNMF_F256_DBG") ? atoi(getenv("KLNMF_F256_DBG")) : 0;
   if (p.n_blocks == 0 || p.n_steps == 0) return KLNMF_OK;
   const int clusters = p.n_blocks < ctx->sm_count / 2 ? p.n_blocks : ctx->sm_count / 2;

@@ -202,6 +202,7 @@ int launch_t(klnmf_ctx *ctx, int epi, const GemmDesc &d) {
 }  // namespace
 
 int generic_gemm(klnmf_ctx *ctx, int es, int epi, const GemmDesc &d) {
+  KL_CHECK(d.qshift == 0.f && d.colbias == nullptr, KLNMF_EINVAL, "generic_gemm: the centered ratio is a tcgen05-engine feature");
   if (d.M <= 0 || d.N <= 0) return KLNMF_OK;
   return es == 8 ? launch_t<double>(ctx, epi, d) : launch_t<float>(ctx, epi, d);
 }

@@ -47,6 +47,8 @@ struct TcParams {
   uint32_t mn_lt, mn_lbo, mn_sbo, mn_kadv;   // MN-major descriptor parameters (bring-up overridable)
   int no_prefetch;                           // default 1; KLNMF_TC_PF=1 re-enables the L2 prefetch of the next X tile
   int relaxed;                               // accumulator hand-back with relaxed arrives (KLNMF_TC_RELAXED=0: release)
+  float qshift;                              // EPI_RATIO: the stored ratio is q - qshift (centered ratio, api.cu)
+  const float *colbias;                      // EPI_MULW: out = aux * (acc + colbias[col])
   int dbg;                                   // timing experiments (KLNMF_TC_DBG): 1 no ratio math, 2 no Q store, 4 one MMA per K block only
   uint32_t k_lt;                             // K-major layout type: 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B (experiment)
 };
@@ -115,6 +117,8 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams &p, int64_t row, i
     // columns >= N hold x = 0, s = 0: q = 1, the term is exactly 0
     kl += (double)part;
     if (!p.only_kl) {
+#pragma unroll
+      for (int j = 0; j < 32; j++) q[j] -= p.qshift;
       if (SPLIT && p.out_lo) {
         float lo[32];
 #pragma unroll
@@ -133,6 +137,13 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams &p, int64_t row, i
       ld_row32(p.aux_lo + row * p.ldaux + col0, wl);
 #pragma unroll
       for (int j = 0; j < 32; j++) w[j] += wl[j];
+    }
+    if (p.colbias) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        const float4 b = __ldg(reinterpret_cast<const float4 *>(p.colbias + col0 + 4 * j));
+        acc[4 * j] += b.x; acc[4 * j + 1] += b.y; acc[4 * j + 2] += b.z; acc[4 * j + 3] += b.w;
+      }
     }
 #pragma unroll
     for (int j = 0; j < 32; j++) w[j] *= acc[j];
@@ -412,7 +423,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           float q0, q1;
           part0 += ratio_term<false>(x[j], __uint_as_float(v[j]), q0);
           part1 += ratio_term<false>(x[j + 1], __uint_as_float(v[j + 1]), q1);
-          x[j] = q0; x[j + 1] = q1;
+          x[j] = q0 - p.qshift; x[j + 1] = q1 - p.qshift;
         }
         kl_tile += part0 + part1;
         if (!p.only_kl) {
@@ -630,6 +641,7 @@ int tc_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d) {
   TcParams p{};
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.epi = epi; p.only_kl = d.only_kl;
+  p.qshift = d.qshift; p.colbias = d.colbias;
   if (epi == EPI_STORE && getenv("KLNMF_BENCH_NOSTORE")) p.only_kl = 1;
   p.accurate = ctx->mode == KLNMF_MODE_TF32X3 ? 1 : 0;
   p.out = (float *)d.out; p.out_lo = (float *)d.out_lo; p.ldo = d.ldo;

@@ -38,24 +38,28 @@ template <typename T>
 __global__ void __launch_bounds__(512) dict_update_kernel(const T *__restrict__ H, const T *__restrict__ Hlo,
                                                           const T *__restrict__ num, T *__restrict__ Hn,
                                                           T *__restrict__ Hnlo, int64_t f, int64_t ld,
-                                                          double *__restrict__ rowsum, const int *stop) {
+                                                          double *__restrict__ rowsum, const double *__restrict__ rowadd,
+                                                          const int *stop) {
   if (*stop != 0) return;
   __shared__ double red[32];
   const int64_t a = blockIdx.x;
   const T *h = H + a * ld, *nm = num + a * ld;
   const T *hl = Hlo ? Hlo + a * ld : nullptr;
+  // centered ratio (api.cu, dense_iteration): num holds W'^T.(Q - 1); the missing W'^T.1 = colsum(W') is the same
+  // for every feature of a dictionary row
+  const T add = rowadd ? (T)rowadd[a] : (T)0;
   double s = 0.0;
   for (int64_t j = threadIdx.x; j < f; j += blockDim.x) {
     T v = h[j];
     if (hl) v += hl[j];
-    s += (double)(v * nm[j]);
+    s += (double)(v * (nm[j] + add));
   }
   s = block_sum(s, red);
   const double inv = 1.0 / (KL_NORM_EPS + s);
   for (int64_t j = threadIdx.x; j < f; j += blockDim.x) {
     T v = h[j];
     if (hl) v += hl[j];
-    T r = (T)((double)(v * nm[j]) * inv);
+    T r = (T)((double)(v * (nm[j] + add)) * inv);
     if (Hnlo) {
       float hi = tf32_hi((float)r);
       Hn[a * ld + j] = (T)hi;
@@ -101,7 +105,7 @@ __global__ void __launch_bounds__(256) dict_scale_t_kernel(const T *__restrict__
 
 // The reference's stopping test on the device (nmf.py:214-220).  dred = [kl, sum(X.data), colsum(W)...]
 __global__ void decide_kernel(double *dred, double *dscal, int *flags, double *errors, int errors_cap,
-                              const double *rowsumH, int64_t k, int sparse) {
+                              const double *rowsumH, int64_t k, int sparse, double *colsum_out) {
   if (threadIdx.x != 0 || blockIdx.x != 0) return;
   double e = dred[0];
   if (sparse) {
@@ -125,7 +129,54 @@ __global__ void decide_kernel(double *dred, double *dscal, int *flags, double *e
   dscal[DS_KL] = e;
   dred[0] = 0.0;
   dred[1] = dscal[DS_SUMX];
-  for (int64_t a = 0; a < k; a++) dred[2 + a] = 0.0;
+  for (int64_t a = 0; a < k; a++) {
+    if (colsum_out) colsum_out[a] = dred[2 + a];     // colsum(W') of all ranks, for the dictionary update
+    dred[2 + a] = 0.0;
+  }
+}
+
+__global__ void rsh32_kernel(const double *__restrict__ rowsumH, float *__restrict__ out, int64_t k, int64_t len) {
+  for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < len; a += (int64_t)gridDim.x * blockDim.x)
+    out[a] = a < k ? (float)rowsumH[a] : 0.f;
+}
+
+// out[a] += sum_i W[i,a] (+ Wlo): a warp reads whole rows (up to 512 columns per sweep), FP64 accumulation
+template <typename T>
+__global__ void __launch_bounds__(256) colsum_w_kernel(const T *__restrict__ W, const T *__restrict__ Wlo, int64_t n,
+                                                       int64_t k, int64_t ld, double *__restrict__ out, const int *stop) {
+  if (*stop != 0) return;
+  __shared__ double red[8][32];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  for (int64_t cb = 0; cb < k; cb += 512) {
+    double acc[16];
+#pragma unroll
+    for (int m = 0; m < 16; m++) acc[m] = 0.0;
+    for (int64_t i = (int64_t)blockIdx.x * 8 + ty; i < n; i += (int64_t)gridDim.x * 8) {
+      const T *w = W + i * ld + cb;
+      const T *wl = Wlo ? Wlo + i * ld + cb : nullptr;
+#pragma unroll
+      for (int m = 0; m < 16; m++) {
+        const int64_t c = cb + 32 * m + tx;
+        if (c < k) {
+          acc[m] += (double)w[32 * m + tx];
+          if (wl) acc[m] += (double)wl[32 * m + tx];
+        }
+      }
+    }
+#pragma unroll
+    for (int m = 0; m < 16; m++) {
+      const int64_t c = cb + 32 * m + tx;
+      red[ty][tx] = acc[m];
+      __syncthreads();
+      if (ty == 0 && c < k) {
+        double t = 0.0;
+#pragma unroll
+        for (int r = 0; r < 8; r++) t += red[r][tx];
+        atomicAdd(&out[c], t);
+      }
+      __syncthreads();
+    }
+  }
 }
 
 __global__ void split_kernel(const float *__restrict__ src, float *__restrict__ hi, float *__restrict__ lo,
@@ -225,16 +276,16 @@ inline int grid_for(klnmf_ctx *ctx, int64_t total, int threads) {
 
 }  // namespace
 
-int launch_dict_update(klnmf_ctx *ctx, const void *H_old, void *H_new, void *Hlo_new) {
+int launch_dict_update(klnmf_ctx *ctx, const void *H_old, void *H_new, void *Hlo_new, const double *rowadd) {
   const int cur = ctx->hcur;
   if (ctx->es == 8) {
     dict_update_kernel<double><<<(unsigned)ctx->k, 512, 0, ctx->stream>>>(
         (const double *)H_old, nullptr, (const double *)ctx->num, (double *)H_new, nullptr, ctx->f, ctx->ldh,
-        ctx->rowsumH, ctx->flags + FL_STOP);
+        ctx->rowsumH, rowadd, ctx->flags + FL_STOP);
   } else {
     dict_update_kernel<float><<<(unsigned)ctx->k, 512, 0, ctx->stream>>>(
         (const float *)H_old, (const float *)ctx->Hlo[cur], (const float *)ctx->num, (float *)H_new,
-        (float *)Hlo_new, ctx->f, ctx->ldh, ctx->rowsumH, ctx->flags + FL_STOP);
+        (float *)Hlo_new, ctx->f, ctx->ldh, ctx->rowsumH, rowadd, ctx->flags + FL_STOP);
   }
   ctx->n_launch++;
   KL_CUDA(cudaGetLastError());
@@ -268,7 +319,30 @@ int launch_dict_update_t(klnmf_ctx *ctx, const void *Ht_old, void *Ht_new) {
 
 int launch_decide(klnmf_ctx *ctx, int /*iter_index*/) {
   decide_kernel<<<1, 32, 0, ctx->stream>>>(ctx->dred, ctx->dscal, ctx->flags, ctx->errors_dev, ctx->errors_cap,
-                                           ctx->rowsumH, ctx->k, ctx->sparse ? 1 : 0);
+                                           ctx->rowsumH, ctx->k, ctx->sparse ? 1 : 0, ctx->colsumW);
+  ctx->n_launch++;
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
+int launch_rsh32(klnmf_ctx *ctx) {
+  const int64_t len = ctx->ldw + 32;
+  rsh32_kernel<<<(unsigned)ceil_div(len, 256), 256, 0, ctx->stream>>>(ctx->rowsumH, ctx->rsh32, ctx->k, len);
+  ctx->n_launch++;
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
+int launch_colsum_w(klnmf_ctx *ctx, const void *W, const void *Wlo, double *out) {
+  if (ctx->n == 0) return KLNMF_OK;
+  const int64_t want = ceil_div(ctx->n, 8 * 16);
+  const int grid = (int)(want < (int64_t)ctx->sm_count * 4 ? (want > 0 ? want : 1) : (int64_t)ctx->sm_count * 4);
+  if (ctx->es == 8)
+    colsum_w_kernel<double><<<grid, 256, 0, ctx->stream>>>((const double *)W, (const double *)Wlo, ctx->n, ctx->k, ctx->ldw, out,
+                                                           ctx->flags + FL_STOP);
+  else
+    colsum_w_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float *)W, (const float *)Wlo, ctx->n, ctx->k, ctx->ldw, out,
+                                                          ctx->flags + FL_STOP);
   ctx->n_launch++;
   KL_CUDA(cudaGetLastError());
   return KLNMF_OK;

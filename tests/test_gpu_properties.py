@@ -103,11 +103,12 @@ def test_cfg5_shape_modes_agree():
             e.init_coefficients()
             errs, _ = e.run(4, 0.0, True)
             out[mode] = (e.get_coefficients(), e.get_dictionary(), np.asarray(errs))
-    # The tensor core accumulates FP32 with truncation, and every term of an NMF contraction is non-negative: the
-    # coefficient contraction over f = 8192 features drifts by ~1e-8 f from float64 (measured 8.1e-5 in tf32x3, whose
-    # three MMAs per step truncate three times; 3.0e-5 in tf32 -- tools/accuracy_vs_shape.py).
-    # The normalised dictionary and the objective (a contraction over k only) keep the tolerances of the small cases.
-    tol_w = {"tf32x3": 2e-4, "tf32": 3e-3}
+    # The tensor core accumulates FP32 with truncation, and every term of an NMF contraction is non-negative: a plain
+    # coefficient contraction over f = 8192 features drifts by ~1e-8 f from float64 (8.1e-5 on W in tf32x3).  The
+    # split mode therefore contracts the CENTERED ratio Q - 1 (api.cu, dense_iteration): measured 5.4e-6 here
+    # (tools/accuracy_vs_shape.py).  The objective is a contraction over k = 512 non-negative
+    # terms that cannot be centered: 4.2e-5.
+    tol_w = {"tf32x3": 2e-5, "tf32": 3e-3}
     tol_h = {"tf32x3": 2e-5, "tf32": 3e-3}
     tol_kl = {"tf32x3": 1e-4, "tf32": 1e-2}
     for mode in ("tf32x3", "tf32"):
