@@ -66,7 +66,9 @@ struct Cfg {
   static constexpr int B_BYTES = (BN / CG) * BK * 4;     // a CTA pair splits the B tile
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (SPLIT ? 2 : 1);
   static constexpr int XBUFS = XB;
-  static constexpr int XQ_BYTES = XT ? XB * XCHUNK_BYTES + (QIP ? 0 : EPI_WARPS * QWARP_BYTES) : 0;
+  // split-TF32 contractions (no XT form): one 32 x 32 transpose box per epilogue warp, so that X arrives and the
+  // (hi, lo) ratio leaves as full 128-byte lines (epilogue_ratio_staged)
+  static constexpr int XQ_BYTES = XT ? XB * XCHUNK_BYTES + (QIP ? 0 : EPI_WARPS * QWARP_BYTES) : (SPLIT ? EPI_WARPS * QWARP_BYTES : 0);
   static constexpr int STAGES = (XT ? (224 * 1024 - XQ_BYTES) : 192 * 1024) / STAGE_BYTES;
   static constexpr int TMEM_COLS = 2 * BN;   // power of two: 256 or 512
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + XQ_BYTES + 1024 /*align*/ + 256 /*barriers*/;
@@ -164,6 +166,79 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams &p, int64_t row, i
                    "f"(acc[4 * j + 1]), "f"(acc[4 * j + 2]), "f"(acc[4 * j + 3])
                    : "memory");
   }
+}
+
+// The ratio epilogue of the split-TF32 mode on one 32-row x 32-column block of a warp.  The row-owning thread
+// layout of tcgen05.ld makes every direct global access a 16-byte piece per row; here the block goes through a
+// warp-private 4 KB box (16-byte chunks XOR-swizzled by the row): X is read and Q_hi / Q_lo are written as
+// four full 128-byte lines per instruction, and the box is read / written by the row owners without bank conflicts.
+template <bool SPLIT>
+__device__ __forceinline__ void epilogue_ratio_staged(const TcParams &p, int64_t row0, int lane, int64_t col0,
+                                                      const uint32_t acc_u[32], double &kl, uint8_t *box) {
+  if (col0 >= p.n_store) return;                 // warp-uniform
+  const int lr = lane >> 3, lc = lane & 7;       // coalesced phase: 4 rows x 8 chunks of 16 bytes per instruction
+  const uint32_t sw = (uint32_t)(lane & 7);
+  uint8_t *mine = box + lane * 128;
+#pragma unroll
+  for (int it = 0; it < 8; it++) {
+    const int r = 4 * it + lr;
+    float4 t = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (row0 + r < p.M) t = __ldg(reinterpret_cast<const float4 *>(p.aux + (row0 + r) * p.ldaux + col0 + 4 * lc));
+    *reinterpret_cast<float4 *>(box + r * 128 + ((lc ^ (r & 7)) << 4)) = t;
+  }
+  __syncwarp();
+  float q[32];
+  float part = 0.f;
+  if (p.accurate) {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float4 t = *reinterpret_cast<const float4 *>(mine + ((j ^ sw) << 4));
+      part += ratio_term<true>(t.x, __uint_as_float(acc_u[4 * j]), q[4 * j]);
+      part += ratio_term<true>(t.y, __uint_as_float(acc_u[4 * j + 1]), q[4 * j + 1]);
+      part += ratio_term<true>(t.z, __uint_as_float(acc_u[4 * j + 2]), q[4 * j + 2]);
+      part += ratio_term<true>(t.w, __uint_as_float(acc_u[4 * j + 3]), q[4 * j + 3]);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      const float4 t = *reinterpret_cast<const float4 *>(mine + ((j ^ sw) << 4));
+      part += ratio_term<false>(t.x, __uint_as_float(acc_u[4 * j]), q[4 * j]);
+      part += ratio_term<false>(t.y, __uint_as_float(acc_u[4 * j + 1]), q[4 * j + 1]);
+      part += ratio_term<false>(t.z, __uint_as_float(acc_u[4 * j + 2]), q[4 * j + 2]);
+      part += ratio_term<false>(t.w, __uint_as_float(acc_u[4 * j + 3]), q[4 * j + 3]);
+    }
+  }
+  // rows >= M hold x = 0 against an accumulator of 0: q = 1, the term is exactly 0
+  kl += (double)part;
+  if (p.only_kl) return;                         // warp-uniform
+#pragma unroll
+  for (int j = 0; j < 32; j++) q[j] -= p.qshift;
+  const bool two = SPLIT && p.out_lo != nullptr;
+#pragma unroll 1
+  for (int part_i = 0; part_i < (two ? 2 : 1); part_i++) {
+    // pass 0: the TF32-exact high part (or the plain value), pass 1: the residual
+    __syncwarp();                                // the coalesced reads of the previous pass are done
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+      float4 t;
+      if (two && part_i == 0) {
+        t = make_float4(tf32_round(q[4 * j]), tf32_round(q[4 * j + 1]), tf32_round(q[4 * j + 2]), tf32_round(q[4 * j + 3]));
+        q[4 * j] -= t.x; q[4 * j + 1] -= t.y; q[4 * j + 2] -= t.z; q[4 * j + 3] -= t.w;
+      } else {
+        t = make_float4(q[4 * j], q[4 * j + 1], q[4 * j + 2], q[4 * j + 3]);
+      }
+      *reinterpret_cast<float4 *>(mine + ((j ^ sw) << 4)) = t;
+    }
+    __syncwarp();
+    float *dst = part_i == 0 ? p.out : p.out_lo;
+#pragma unroll
+    for (int it = 0; it < 8; it++) {
+      const int r = 4 * it + lr;
+      const float4 t = *reinterpret_cast<const float4 *>(box + r * 128 + ((lc ^ (r & 7)) << 4));
+      if (row0 + r < p.M) *reinterpret_cast<float4 *>(dst + (row0 + r) * p.ldo + col0 + 4 * lc) = t;
+    }
+  }
+  __syncwarp();                                  // the box is free for the next block
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -493,7 +568,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col_in_tile);
         uint32_t v[32];
         tmem_ld32(taddr, v);
-        epilogue_chunk<SPLIT>(p, row, (int64_t)ni * BN + col_in_tile, v, kl);
+        if (SPLIT && p.epi == EPI_RATIO)
+          epilogue_ratio_staged<SPLIT>(p, row - lane, lane, (int64_t)ni * BN + col_in_tile, v, kl,
+                                       smem_gen + STAGES * C::STAGE_BYTES + e * QWARP_BYTES);
+        else
+          epilogue_chunk<SPLIT>(p, row, (int64_t)ni * BN + col_in_tile, v, kl);
       }
       tc_fence_before();
       __syncwarp();
@@ -643,7 +722,11 @@ int tc_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d) {
   p.epi = epi; p.only_kl = d.only_kl;
   p.qshift = d.qshift; p.colbias = d.colbias;
   if (epi == EPI_STORE && getenv("KLNMF_BENCH_NOSTORE")) p.only_kl = 1;
-  p.accurate = ctx->mode == KLNMF_MODE_TF32X3 ? 1 : 0;
+  // The staged split-TF32 ratio epilogue uses the MUFU forms too: rcp.approx / lg2.approx are good to ~1e-7, and the
+  // measured accuracy of the mode against FP64 is the same to three digits with either (profiles/r1_s4_run50_*.log) while
+  // IEEE division + logf made the epilogue, not the three MMAs per step, the pace of the ratio contraction
+  // (cfg3 shape: 21.1 -> 15.8 ms).  KLNMF_TC_FASTMATH=0 restores the IEEE forms.
+  p.accurate = (getenv("KLNMF_TC_FASTMATH") && atoi(getenv("KLNMF_TC_FASTMATH")) == 0) ? 1 : 0;
   p.out = (float *)d.out; p.out_lo = (float *)d.out_lo; p.ldo = d.ldo;
   p.n_store = round_up(d.N, 32);
   KL_CHECK(epi == EPI_RATIO && d.only_kl ? true : p.n_store <= d.ldo, KLNMF_EINVAL,

@@ -148,6 +148,21 @@ def test_mid_size_dense_vs_oracle(mode):
     np.testing.assert_allclose(errs, er, rtol=TOL_KL[mode])
 
 
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("n,f", [(391, 1000), (1030, 333)])
+def test_k512_ragged_dense_vs_oracle(mode, n, f):
+    """k = 512 (cfg5's component count) on ragged rows / features: the ratio contraction takes its in-place form
+    (the ratio overwrites the X chunk in shared memory, dense_tc.cu) for k >= 512, and tf32x3 the centered ratio."""
+    rs = np.random.RandomState(n + f)
+    X = rs.gamma(0.5, 1.0, size=(n, f))
+    X[rs.random_sample((n, f)) < 0.25] = 0.0
+    np.random.seed(21)
+    Wr, Hr, er, _ = O.fit_transform(X, k=512, max_iter=10, tol=0)
+    est, W, errs = fit(X, 512, 10, 21, mode)
+    assert cases.rel_fro(W, Wr) < TOL_WH[mode] and cases.rel_fro(est.components_, Hr) < TOL_WH[mode]
+    np.testing.assert_allclose(errs, er, rtol=max(TOL_KL[mode], 1e-4 if mode == "tf32x3" else 0))
+
+
 def test_multi_panel_equals_single_panel():
     """Row panels (the ratio scratch) must not change the result."""
     from multimodal_b200 import _native
