@@ -310,6 +310,15 @@ def run_e2e(args, n_local, f, k, kind, mode, local, rank, world, dist, X_host, H
     est._init_dictionary = H0
     if kind == "dense_transform":
         est.components_ = H0
+    # one untimed warm-up call on a small slice: the process-wide pinned staging buffers, kernel attributes and the
+    # allocator are set up once per process, not once per call
+    if world == 1:
+        warm = KLdivNMF(n_components=k, max_iter=2, tol=0, mode=mode, device=local)
+        warm._init_dictionary = H0
+        warm.components_ = H0
+        nw = min(X_host.shape[0], 65536)
+        (warm.transform if kind == "dense_transform" else warm.fit_transform)(X_host[:nw])
+        del warm
     barrier(dist, local)
     t0 = time.perf_counter()
     if world > 1:
@@ -413,7 +422,7 @@ def run_ours(args):
             e2e = {"value": args.steps / dt * scale, "unit": "iterations/s",
                    "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
                    "seconds": dt, "rows_per_rank": rows,
-                   "note": "one KLdivNMF.fit_transform call of %d iterations on a host scipy CSR matrix (pinned arrays); "
+                   "note": "one KLdivNMF.fit_transform call of %d iterations on a host scipy CSR matrix (pinned arrays; after an untimed warm-up call on a 65536-row slice); "
                            "the CSR crosses PCIe once per call, so per-step bytes are the call's bytes / steps" % args.steps +
                            ("" if rows == n_local else "; measured on %d rows and scaled linearly in n" % rows)}
             del Xs, ind, val, ptr
@@ -433,7 +442,8 @@ def run_ours(args):
             e2e = {"value": args.steps / dt * scale, "unit": "iterations/s",
                    "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
                    "seconds": dt, "rows_per_rank": rows,
-                   "note": ("one KLdivNMF.%s call of %d iterations on a pinned host float32 array; X crosses PCIe once "
+                   "note": ("one KLdivNMF.%s call of %d iterations on a pinned host float32 array (after an untimed "
+                            "warm-up call on a 65536-row slice); X crosses PCIe once "
                             "per call, so per-step bytes are the call's bytes / steps" %
                             ("transform" if not fit else "fit_transform", args.steps)) +
                            ("" if rows == n_local else "; host RAM too small for the full shard: measured on %d rows and "
