@@ -193,10 +193,10 @@ __device__ __forceinline__ void epilogue_ratio_staged(const TcParams &p, int64_t
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       const float4 t = *reinterpret_cast<const float4 *>(mine + ((j ^ sw) << 4));
-      part += ratio_term<true>(t.x, __uint_as_float(acc_u[4 * j]), q[4 * j]);
-      part += ratio_term<true>(t.y, __uint_as_float(acc_u[4 * j + 1]), q[4 * j + 1]);
-      part += ratio_term<true>(t.z, __uint_as_float(acc_u[4 * j + 2]), q[4 * j + 2]);
-      part += ratio_term<true>(t.w, __uint_as_float(acc_u[4 * j + 3]), q[4 * j + 3]);
+      part += ratio_term_cf(t.x, __uint_as_float(acc_u[4 * j]), q[4 * j]);
+      part += ratio_term_cf(t.y, __uint_as_float(acc_u[4 * j + 1]), q[4 * j + 1]);
+      part += ratio_term_cf(t.z, __uint_as_float(acc_u[4 * j + 2]), q[4 * j + 2]);
+      part += ratio_term_cf(t.w, __uint_as_float(acc_u[4 * j + 3]), q[4 * j + 3]);
     }
   } else {
 #pragma unroll
@@ -722,11 +722,11 @@ int tc_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d) {
   p.epi = epi; p.only_kl = d.only_kl;
   p.qshift = d.qshift; p.colbias = d.colbias;
   if (epi == EPI_STORE && getenv("KLNMF_BENCH_NOSTORE")) p.only_kl = 1;
-  // The split-TF32 ratio epilogue keeps IEEE division + logf.  With the MUFU forms (KLNMF_TC_FASTMATH=1) W and H come
-  // out the same to three digits and the ratio contraction is 1.2-1.3x faster (cfg3 shape: 21.1 -> 15.8 ms; the
-  // epilogue, not the three MMAs per step, paces it), but lg2.approx is off by ~2e-7 of sum(X) in the objective, which
-  // shows once a fit has converged: 1.5e-4 on the 200-iteration golden case against the stated 2e-5
-  // (profiles/r1_s4_run50_*.log, r1_s4_run52_*.log).
+  // The split-TF32 ratio epilogue evaluates the objective in its cancellation-free form (ratio_term_cf, tc_ptx.cuh): no
+  // IEEE division, no logf, and more accurate than both once a fit has converged (cfg3 shape: 21.1 -> 17.8 ms; the
+  // epilogue, not the three MMAs per step, paces this contraction).  The plain MUFU forms (KLNMF_TC_FASTMATH=1, 15.8 ms)
+  // give the same W and H to three digits, but lg2.approx is off by ~2e-7 of sum(X) in the objective: 1.5e-4 on the
+  // 200-iteration golden case against the stated 2e-5 (profiles/r1_s4_run50_*.log, r1_s4_run52_*.log, r1_s4_run56_*.log).
   p.accurate = ctx->mode == KLNMF_MODE_TF32X3 ? 1 : 0;
   if (getenv("KLNMF_TC_FASTMATH") && atoi(getenv("KLNMF_TC_FASTMATH")) == 1) p.accurate = 0;
   p.out = (float *)d.out; p.out_lo = (float *)d.out_lo; p.ldo = d.ldo;

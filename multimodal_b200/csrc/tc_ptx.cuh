@@ -231,6 +231,33 @@ __device__ __forceinline__ float ratio_term(float x, float s, float &q) {
   q = (x + (float)KL_EPS) * rcp_approx(s + (float)KL_EPS);
   return fmaf(x * 0.69314718055994531f, lg2_approx(q), s - x);
 }
+// The same element in a form that needs no accurate logarithm (split-TF32 epilogue).  With d = s + eps,
+// u = (x - s)/d = q - 1 and P(u) = log1p(u) - u:
+//     x log(q) - x + s  =  x P(u) + (x - s)(x - s - eps)/d
+// -- every product on the right is small when the fit has converged, where the left side cancels x log(q) against
+// s - x.  P(u) is a short polynomial for |u| < 1/4 (truncation 3.5e-7 u^2) and ln2 * lg2.approx(q) - u beyond, where
+// |P| >= 0.023 makes the 1e-7 of the MUFU harmless.  q = (x + eps) * rcp(d) with one Newton step on the reciprocal.
+__device__ __forceinline__ float ratio_term_cf(float x, float s, float &q) {
+  const float d = s + (float)KL_EPS;
+  float r = rcp_approx(d);
+  r = fmaf(fmaf(-d, r, 1.f), r, r);
+  q = (x + (float)KL_EPS) * r;
+  const float xs = x - s;
+  const float u = xs * r;
+  float R = -0.1f;
+  R = fmaf(R, u, 1.f / 9.f);
+  R = fmaf(R, u, -0.125f);
+  R = fmaf(R, u, 1.f / 7.f);
+  R = fmaf(R, u, -1.f / 6.f);
+  R = fmaf(R, u, 0.2f);
+  R = fmaf(R, u, -0.25f);
+  R = fmaf(R, u, 1.f / 3.f);
+  R = fmaf(R, u, -0.5f);
+  const float p_small = u * u * R;
+  const float p_large = fmaf(0.69314718055994531f, lg2_approx(fmaxf(q, 1e-37f)), -u);
+  const float P = fabsf(u) < 0.25f ? p_small : p_large;
+  return fmaf(x, P, xs * (xs - (float)KL_EPS) * r);
+}
 __device__ __forceinline__ float tf32_round(float v) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));
