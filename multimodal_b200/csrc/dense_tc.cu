@@ -168,6 +168,8 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams &p, int64_t row, i
   }
 }
 
+// (Fetching the X block one piece ahead into registers was measured: 168 registers with spills, ratio contraction
+// 11.6 -> 14.9 ms at the cfg5 shape -- dropped.)
 // The ratio epilogue of the split-TF32 mode on one 32-row x 32-column block of a warp.  The row-owning thread
 // layout of tcgen05.ld makes every direct global access a 16-byte piece per row; here the block goes through a
 // warp-private 4 KB box (16-byte chunks XOR-swizzled by the row): X is read and Q_hi / Q_lo are written as
