@@ -88,3 +88,13 @@ def rel_fro(a, b):
     a = np.asarray(a, dtype=np.float64)
     b = np.asarray(b, dtype=np.float64)
     return np.linalg.norm(a - b) / max(np.linalg.norm(b), 1e-300)
+
+
+def store_dictionaries():
+    """Two small row-normalised dictionaries (4 x 9) for the logger-store fixtures (oracle/make_store_golden.py)."""
+    rs = np.random.RandomState(42)
+    out = []
+    for _ in range(2):
+        d = rs.random_sample((4, 9)) + .01
+        out.append(d / d.sum(axis=1, keepdims=True))
+    return out
