@@ -74,6 +74,14 @@ int klnmf_set_scratch_limit(klnmf_ctx *ctx, int64_t bytes);
  * reference does it; klnmf_check_input offers the same test on the device copy. */
 int klnmf_set_dense_host(klnmf_ctx *ctx, const void *X, int dtype, int64_t ld);
 int klnmf_set_dense_device(klnmf_ctx *ctx, const void *X_dev, int dtype, int64_t ld);
+/* The scaled concatenation of modalities, safe_hstack([coef_m * X_m]) of MultimodalLearner.stack_data
+ * (learner.py:53-56, array_utils.py:5-9), formed on the device: block b (n x cols[b], row pitch lds[b], host memory)
+ * lands in columns [sum(cols[:b]), +cols[b]) of X multiplied by scales[b].  The product is formed in double and
+ * rounded once, like numpy's float64 product -- or in float where product_f32[b] != 0, which is what numpy does for a
+ * float32 block with a float32 (or Python float) coefficient; product_f32 may be NULL.  sum(cols) must equal f.
+ * No stacked copy is ever made on the host. */
+int klnmf_set_dense_blocks_host(klnmf_ctx *ctx, int n_blocks, const void *const *X, const int *dtypes,
+                                const int64_t *lds, const int64_t *cols, const double *scales, const int *product_f32);
 /* CSR with sorted-or-not column indices, no duplicate entries, explicit zeros already
  * removed (the reference calls eliminate_zeros() on the caller's matrix, nmf.py:66). */
 int klnmf_set_csr_host(klnmf_ctx *ctx, const int64_t *indptr, const int32_t *indices,

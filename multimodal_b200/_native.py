@@ -33,6 +33,7 @@ PROTOTYPES = {
     "klnmf_set_scratch_limit": (_c_int, [_c_vp, _c_i64]),
     "klnmf_set_dense_host": (_c_int, [_c_vp, _c_vp, _c_int, _c_i64]),
     "klnmf_set_dense_device": (_c_int, [_c_vp, _c_vp, _c_int, _c_i64]),
+    "klnmf_set_dense_blocks_host": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "klnmf_set_csr_host": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_i64]),
     "klnmf_set_csr_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_i64]),
     "klnmf_check_input": (_c_int, [_c_vp, ctypes.POINTER(ctypes.c_int32)]),
@@ -177,6 +178,30 @@ class Engine(object):
             X = np.ascontiguousarray(X)
         assert X.shape == (self.n, self.f)
         _check(self.lib.klnmf_set_dense_host(self.h, _ptr(X), dt, X.strides[0] // X.itemsize if self.n > 1 else self.f))
+
+    def set_dense_blocks(self, blocks, scales):
+        """safe_hstack([c * m]) of learner.stack_data (learner.py:53-56) formed on the device: `blocks` are host
+        ndarrays (n, f_b), `scales` the modality coefficients; no stacked host copy is made."""
+        mats, f32 = [], []
+        for m, c in zip(blocks, scales):
+            m = np.asarray(m)
+            # numpy's promotion of `c * m` decides in which precision the reference forms the product
+            f32.append(1 if (c * m[:0, :0]).dtype == np.float32 else 0)
+            if m.dtype not in (np.float32, np.float64):
+                m = m.astype(np.float64)
+            if not m.flags.c_contiguous:
+                m = np.ascontiguousarray(m)
+            assert m.ndim == 2 and m.shape[0] == self.n, (m.shape, self.n)
+            mats.append(m)
+        nb = len(mats)
+        assert sum(m.shape[1] for m in mats) == self.f
+        ptrs = (ctypes.c_void_p * nb)(*[m.ctypes.data for m in mats])
+        dts = (ctypes.c_int * nb)(*[F32 if m.dtype == np.float32 else F64 for m in mats])
+        lds = (ctypes.c_int64 * nb)(*[(m.strides[0] // m.itemsize) if self.n > 1 else m.shape[1] for m in mats])
+        cols = (ctypes.c_int64 * nb)(*[m.shape[1] for m in mats])
+        scl = (ctypes.c_double * nb)(*[float(s) for s in scales])
+        pf = (ctypes.c_int * nb)(*f32)
+        _check(self.lib.klnmf_set_dense_blocks_host(self.h, nb, ptrs, dts, lds, cols, scl, pf))
 
     def set_dense_device(self, ptr, dtype, ld, keepalive=None):
         self._keep.append(keepalive)

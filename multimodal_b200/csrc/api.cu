@@ -141,13 +141,13 @@ int kind_guard(klnmf_ctx *ctx, bool sparse) {
 
 // host (row-major, ld elements, dtype) -> device (es, dst_ld), optional transpose
 int upload_matrix(klnmf_ctx *ctx, const void *src, int dtype, int64_t ld, void *dst, int64_t dst_ld, int64_t rows,
-                  int64_t cols, bool transpose) {
+                  int64_t cols, bool transpose, double scale = 1.0, int scale_f32 = 0) {
   if (rows <= 0 || cols <= 0) return KLNMF_OK;
   const int64_t ses = dtype == KLNMF_F64 ? 8 : 4;
   if (!transpose && ses == ctx->es) {
     KL_CUDA(cudaMemcpy2DAsync(dst, dst_ld * ses, src, ld * ses, cols * ses, rows, cudaMemcpyHostToDevice, ctx->stream));
     ctx->bytes_h2d += rows * cols * ses;
-    return KLNMF_OK;
+    return launch_scale_block(ctx, dst, dst_ld, rows, cols, scale, scale_f32);     // in place
   }
   int64_t chunk = kStageBytes / (cols * ses);
   if (chunk < 1) chunk = 1;
@@ -157,7 +157,7 @@ int upload_matrix(klnmf_ctx *ctx, const void *src, int dtype, int64_t ld, void *
     KL_CUDA(cudaMemcpy2DAsync(ctx->stage, cols * ses, (const char *)src + r0 * ld * ses, ld * ses, cols * ses, r,
                               cudaMemcpyHostToDevice, ctx->stream));
     void *d = transpose ? (void *)((char *)dst + r0 * ctx->es) : (void *)((char *)dst + r0 * dst_ld * ctx->es);
-    KL_TRY(launch_convert(ctx, ctx->stage, nullptr, dtype, cols, d, ctx->es, dst_ld, r, cols, transpose));
+    KL_TRY(launch_convert(ctx, ctx->stage, nullptr, dtype, cols, d, ctx->es, dst_ld, r, cols, transpose, scale, scale_f32));
     KL_CUDA(cudaStreamSynchronize(ctx->stream));   // staging buffer is reused
     ctx->bytes_h2d += r * cols * ses;
   }
@@ -544,6 +544,38 @@ int klnmf_set_dense_host(klnmf_ctx *ctx, const void *X, int dtype, int64_t ld) {
   ctx->x_owned = true;
   if (ctx->ldx != ctx->f) KL_CUDA(cudaMemsetAsync(ctx->X, 0, bytes, ctx->stream));
   KL_TRY(upload_matrix(ctx, X, dtype, ld, ctx->X, ctx->ldx, ctx->n, ctx->f, false));
+  KL_TRY(ensure_state(ctx));
+  ctx->have_x = true;
+  return KLNMF_OK;
+}
+
+int klnmf_set_dense_blocks_host(klnmf_ctx *ctx, int n_blocks, const void *const *X, const int *dtypes,
+                                const int64_t *lds, const int64_t *cols, const double *scales, const int *product_f32) {
+  KL_CHECK(ctx && n_blocks >= 1 && X && dtypes && lds && cols && scales, KLNMF_EINVAL, "set_dense_blocks_host: NULL argument");
+  int64_t total = 0;
+  for (int b = 0; b < n_blocks; b++) {
+    KL_CHECK(cols[b] >= 0 && lds[b] >= cols[b] && (X[b] || ctx->n == 0 || cols[b] == 0), KLNMF_EINVAL,
+             "set_dense_blocks_host: bad block %d (cols %lld, ld %lld)", b, (long long)cols[b], (long long)lds[b]);
+    KL_CHECK(dtypes[b] == KLNMF_F32 || dtypes[b] == KLNMF_F64, KLNMF_EINVAL, "set_dense_blocks_host: bad dtype of block %d", b);
+    total += cols[b];
+  }
+  KL_CHECK(total == ctx->f, KLNMF_EINVAL, "set_dense_blocks_host: the blocks have %lld columns, the context %lld",
+           (long long)total, (long long)ctx->f);
+  KL_CUDA(cudaSetDevice(ctx->device));
+  KL_TRY(kind_guard(ctx, false));
+  release_data(ctx);
+  ctx->ldx = round_up(ctx->f, 32);
+  const int64_t bytes = (ctx->n > 0 ? ctx->n : 1) * ctx->ldx * ctx->es;
+  KL_TRY(dmalloc(&ctx->X, bytes));
+  ctx->x_owned = true;
+  if (ctx->ldx != ctx->f) KL_CUDA(cudaMemsetAsync(ctx->X, 0, bytes, ctx->stream));
+  int64_t off = 0;
+  for (int b = 0; b < n_blocks; b++) {
+    char *dst = (char *)ctx->X + off * ctx->es;
+    KL_TRY(upload_matrix(ctx, X[b], dtypes[b], lds[b], dst, ctx->ldx, ctx->n, cols[b], false, scales[b],
+                         product_f32 && product_f32[b] && dtypes[b] == KLNMF_F32 ? 1 : 0));
+    off += cols[b];
+  }
   KL_TRY(ensure_state(ctx));
   ctx->have_x = true;
   return KLNMF_OK;

@@ -178,6 +178,7 @@ void fused_release(klnmf_ctx *ctx);
 
 // ---- elementwise / reductions: elementwise.cu ----------------------------------------------------
 int launch_dict_update(klnmf_ctx *ctx, const void *H_old, void *H_new, void *Hlo_new, const double *rowadd = nullptr);
+int launch_scale_block(klnmf_ctx *ctx, void *X, int64_t ld, int64_t rows, int64_t cols, double scale, int f32 = 0);   // X[:, :cols] *= scale
 int launch_rsh32(klnmf_ctx *ctx);           // rsh32 <- rowsumH (FP32, zero padded)
 int launch_colsum_w(klnmf_ctx *ctx, const void *W, const void *Wlo, double *out);   // out[a] += sum_i W[i,a]
 int launch_dict_update_t(klnmf_ctx *ctx, const void *Ht_old, void *Ht_new);     // sparse: f x k layout
@@ -185,7 +186,7 @@ int launch_decide(klnmf_ctx *ctx, int iter_index);
 int launch_split(klnmf_ctx *ctx, const float *src, float *hi, float *lo, int64_t rows, int64_t cols, int64_t ld);
 // dst = (src [+ src_lo]) converted; optional transpose
 int launch_convert(klnmf_ctx *ctx, const void *src, const void *src_lo, int src_dtype, int64_t src_ld, void *dst,
-                   int dst_es, int64_t dst_ld, int64_t rows, int64_t cols, bool transpose);
+                   int dst_es, int64_t dst_ld, int64_t rows, int64_t cols, bool transpose, double scale = 1.0, int scale_f32 = 0);
 int launch_zero(klnmf_ctx *ctx, void *p, int64_t bytes);
 int launch_fill_uniform(klnmf_ctx *ctx, void *p, int es, int64_t rows, int64_t cols, int64_t ld, uint64_t seed);
 int launch_check(klnmf_ctx *ctx, const void *p, int es, int64_t rows, int64_t cols, int64_t ld);

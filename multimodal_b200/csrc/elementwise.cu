@@ -135,6 +135,15 @@ __global__ void decide_kernel(double *dred, double *dscal, int *flags, double *e
   }
 }
 
+template <typename T>
+__global__ void scale_block_kernel(T *__restrict__ p, int64_t rows, int64_t cols, int64_t ld, double scale, int f32) {
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    p[r * ld + c] = f32 ? (T)((float)p[r * ld + c] * (float)scale) : (T)((double)p[r * ld + c] * scale);
+  }
+}
+
 __global__ void rsh32_kernel(const double *__restrict__ rowsumH, float *__restrict__ out, int64_t k, int64_t len) {
   for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < len; a += (int64_t)gridDim.x * blockDim.x)
     out[a] = a < k ? (float)rowsumH[a] : 0.f;
@@ -194,12 +203,15 @@ __global__ void split_kernel(const float *__restrict__ src, float *__restrict__ 
 
 template <typename S, typename D>
 __global__ void convert_kernel(const S *__restrict__ src, const S *__restrict__ src_lo, int64_t src_ld,
-                               D *__restrict__ dst, int64_t dst_ld, int64_t rows, int64_t cols, int transpose) {
+                               D *__restrict__ dst, int64_t dst_ld, int64_t rows, int64_t cols, int transpose,
+                               double scale, int scale_f32) {
   const int64_t total = rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (int64_t)gridDim.x * blockDim.x) {
     int64_t r = i / cols, c = i - r * cols;
-    D v = (D)src[r * src_ld + c];
+    D v = scale == 1.0 ? (D)src[r * src_ld + c]
+                       : (scale_f32 ? (D)((float)src[r * src_ld + c] * (float)scale)           // numpy's float32 product
+                                    : (D)((double)src[r * src_ld + c] * scale));             // float64 product, one rounding
     if (src_lo) v += (D)src_lo[r * src_ld + c];
     if (transpose) dst[c * dst_ld + r] = v; else dst[r * dst_ld + c] = v;
   }
@@ -325,6 +337,16 @@ int launch_decide(klnmf_ctx *ctx, int /*iter_index*/) {
   return KLNMF_OK;
 }
 
+int launch_scale_block(klnmf_ctx *ctx, void *X, int64_t ld, int64_t rows, int64_t cols, double scale, int f32) {
+  if (rows * cols == 0 || scale == 1.0) return KLNMF_OK;
+  const int g = grid_for(ctx, rows * cols, 256);
+  if (ctx->es == 8) scale_block_kernel<double><<<g, 256, 0, ctx->stream>>>((double *)X, rows, cols, ld, scale, f32);
+  else scale_block_kernel<float><<<g, 256, 0, ctx->stream>>>((float *)X, rows, cols, ld, scale, f32);
+  ctx->n_launch++;
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
 int launch_rsh32(klnmf_ctx *ctx) {
   const int64_t len = ctx->ldw + 32;
   rsh32_kernel<<<(unsigned)ceil_div(len, 256), 256, 0, ctx->stream>>>(ctx->rowsumH, ctx->rsh32, ctx->k, len);
@@ -357,18 +379,18 @@ int launch_split(klnmf_ctx *ctx, const float *src, float *hi, float *lo, int64_t
 }
 
 int launch_convert(klnmf_ctx *ctx, const void *src, const void *src_lo, int src_dtype, int64_t src_ld, void *dst,
-                   int dst_es, int64_t dst_ld, int64_t rows, int64_t cols, bool transpose) {
+                   int dst_es, int64_t dst_ld, int64_t rows, int64_t cols, bool transpose, double scale, int scale_f32) {
   if (rows * cols == 0) return KLNMF_OK;
   const int g = grid_for(ctx, rows * cols, 256);
   const int t = transpose ? 1 : 0;
   if (src_dtype == KLNMF_F32 && dst_es == 4)
-    convert_kernel<float, float><<<g, 256, 0, ctx->stream>>>((const float *)src, (const float *)src_lo, src_ld, (float *)dst, dst_ld, rows, cols, t);
+    convert_kernel<float, float><<<g, 256, 0, ctx->stream>>>((const float *)src, (const float *)src_lo, src_ld, (float *)dst, dst_ld, rows, cols, t, scale, scale_f32);
   else if (src_dtype == KLNMF_F32 && dst_es == 8)
-    convert_kernel<float, double><<<g, 256, 0, ctx->stream>>>((const float *)src, (const float *)src_lo, src_ld, (double *)dst, dst_ld, rows, cols, t);
+    convert_kernel<float, double><<<g, 256, 0, ctx->stream>>>((const float *)src, (const float *)src_lo, src_ld, (double *)dst, dst_ld, rows, cols, t, scale, scale_f32);
   else if (src_dtype == KLNMF_F64 && dst_es == 4)
-    convert_kernel<double, float><<<g, 256, 0, ctx->stream>>>((const double *)src, (const double *)src_lo, src_ld, (float *)dst, dst_ld, rows, cols, t);
+    convert_kernel<double, float><<<g, 256, 0, ctx->stream>>>((const double *)src, (const double *)src_lo, src_ld, (float *)dst, dst_ld, rows, cols, t, scale, scale_f32);
   else
-    convert_kernel<double, double><<<g, 256, 0, ctx->stream>>>((const double *)src, (const double *)src_lo, src_ld, (double *)dst, dst_ld, rows, cols, t);
+    convert_kernel<double, double><<<g, 256, 0, ctx->stream>>>((const double *)src, (const double *)src_lo, src_ld, (double *)dst, dst_ld, rows, cols, t, scale, scale_f32);
   ctx->n_launch++;
   KL_CUDA(cudaGetLastError());
   return KLNMF_OK;

@@ -10,7 +10,7 @@ import numpy as np
 
 from . import _native
 from .lib.nmf import KLdivNMF as NMF
-from .lib.array_utils import safe_hstack
+from .lib.array_utils import safe_hstack, StackedBlocks
 
 
 def fit_coefficients(data_obs, dictionary, iter_nmf=100, verbose=False, mode=None, device=0):
@@ -62,6 +62,9 @@ class MultimodalLearner(object):
     def stack_data(self, modalities, data_matrices):
         """Scaled concatenation (learner.py:53-56); one sparse block makes the stack sparse."""
         coefs = [self.coef[self.get_index(mod)] for mod in modalities]
+        if len(data_matrices) > 1 and all(isinstance(m, np.ndarray) and m.ndim == 2 for m in data_matrices):
+            # all modalities dense: the scaled concatenation is formed on the device, block by block
+            return StackedBlocks(data_matrices, coefs)
         return safe_hstack([c * m
                             for m, c in zip(data_matrices, coefs)])
 

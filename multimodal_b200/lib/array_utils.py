@@ -12,6 +12,31 @@ def safe_hstack(blocks):
         return np.hstack(blocks)
 
 
+class StackedBlocks(object):
+    """safe_hstack([c * m for m, c in zip(blocks, coefs)]) of dense modalities, NOT yet formed: the estimator uploads the
+    blocks one by one and scales them on the device (klnmf_set_dense_blocks_host), so that the stacked matrix -- 131 GB
+    for three modalities of 4 million samples -- never exists on the host.  Anything else that wants the matrix gets it
+    from `toarray()` / `np.asarray(...)`, which is exactly what the reference's stack_data returns (learner.py:53-56)."""
+
+    def __init__(self, blocks, coefs):
+        self.blocks = [np.asarray(b) for b in blocks]
+        self.coefs = list(coefs)            # kept as given: numpy's promotion rules see np.float32 / Python floats
+        assert len(self.blocks) == len(self.coefs) and len(self.blocks) > 0
+        n = self.blocks[0].shape[0]
+        assert all(b.ndim == 2 and b.shape[0] == n for b in self.blocks)
+        self.shape = (n, sum(b.shape[1] for b in self.blocks))
+        self.ndim = 2
+        self.dtype = np.result_type(np.float64, *[b.dtype for b in self.blocks]) \
+            if any(b.dtype != np.float32 for b in self.blocks) else np.dtype(np.float32)
+
+    def toarray(self):
+        return np.hstack([c * b for b, c in zip(self.blocks, self.coefs)])
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.toarray()
+        return a if dtype is None else a.astype(dtype)
+
+
 def normalize_sum(a, axis=0, eps=1.e-16):
     """a / (eps + sum(a, axis)) (reference array_utils.py:19-22)."""
     if axis >= len(a.shape):

@@ -16,7 +16,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from .. import _native
-from .array_utils import normalize_sum
+from .array_utils import normalize_sum, StackedBlocks
 from .sklearn_utils import atleast2d_or_csr
 
 _EPS = 1.e-8      # the loop's literal eps (nmf.py:232, 297, 325); the kernels hard-wire it
@@ -60,7 +60,9 @@ def _engine_for(X, k, mode, device):
     n, f = X.shape
     eng = _native.Engine(n, f, k, mode=mode, device=device)
     try:
-        if sp.issparse(X):
+        if isinstance(X, StackedBlocks):
+            eng.set_dense_blocks(X.blocks, X.coefs)
+        elif sp.issparse(X):
             eng.set_csr(X)
         else:
             eng.set_dense(X)
@@ -73,11 +75,12 @@ def _engine_for(X, k, mode, device):
 def _validated(X, whom, mode, device, k):
     """atleast2d_or_csr + check_non_negative (nmf.py:193-194), with the O(n f) scans run
     on the device copy.  Returns (X, engine)."""
-    X = atleast2d_or_csr(X, check_finite=False)
-    if sp.issparse(X):
-        X = _canonical_csr(X)
-    elif X.dtype not in (np.float32, np.float64):
-        X = X.astype(np.float64)
+    if not isinstance(X, StackedBlocks):
+        X = atleast2d_or_csr(X, check_finite=False)
+        if sp.issparse(X):
+            X = _canonical_csr(X)
+        elif X.dtype not in (np.float32, np.float64):
+            X = X.astype(np.float64)
     eng = _engine_for(X, k, mode, device)
     neg, bad = eng.check_input()
     if bad or neg:
@@ -153,7 +156,7 @@ class KLdivNMF(object):
         `y`, `weights` and `scale_W` are accepted and ignored exactly as in the
         reference (nmf.py:222 never forwards scale_W).
         """
-        Xv = atleast2d_or_csr(X, check_finite=False)
+        Xv = X if isinstance(X, StackedBlocks) else atleast2d_or_csr(X, check_finite=False)
         n_samples, n_features = Xv.shape
         if not self.n_components:
             self.n_components = n_features

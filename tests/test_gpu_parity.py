@@ -202,3 +202,31 @@ def test_cfg2_full_shapes_learner_vs_oracle():
     snd = lr.reconstruct_modality('sound', internal)
     assert snd.shape == (40, 110000)
     assert cases.rel_fro(snd, internal_ref.dot(ref.get_dico('sound'))) < 5e-4
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_learner_dense_stack_formed_on_the_device(mode):
+    """Three dense modalities (float64, float32, integer counts): learner.stack_data hands the estimator the blocks
+    and klnmf_set_dense_blocks_host scales and concatenates them on the device; same dictionary as the reference
+    formula safe_hstack([c * m]) (learner.py:53-56) fed to the estimator, and as the float64 oracle."""
+    rs = np.random.RandomState(17)
+    n = 300
+    mats = [rs.gamma(0.5, 1.0, size=(n, 70)), rs.random_sample((n, 45)).astype(np.float32),
+            rs.poisson(1.5, size=(n, 33))]
+    mods, dims = ['sound', 'image', 'motion'], [70, 45, 33]
+    coefs = [1. / np.mean(np.sum(m, axis=1)) for m in mats]          # experiment.py:70-72
+    lr = MultimodalLearner(mods, dims, coefs, 9, mode=mode)
+    np.random.seed(4)
+    lr.train(mats, 10)
+    V = np.hstack([c * m for m, c in zip(mats, coefs)])
+    est = KLdivNMF(n_components=9, max_iter=10, tol=0, mode=mode)
+    np.random.seed(4)
+    est.fit(V)
+    assert cases.rel_fro(lr.dico, est.components_) < (1e-12 if mode == "fp64" else 1e-6)
+    ref = O.Learner(mods, dims, coefs, 9)
+    np.random.seed(4)
+    ref.train(mats, 10)
+    assert cases.rel_fro(lr.dico, ref.dico) < TOL_WH[mode]
+    internal = lr.reconstruct_internal_multi(['sound', 'motion'], [mats[0][:50], mats[2][:50]], 10)
+    internal_ref = ref.reconstruct_internal_multi(['sound', 'motion'], [mats[0][:50], mats[2][:50]], 10)
+    assert cases.rel_fro(internal, internal_ref) < TOL_WH[mode]

@@ -145,3 +145,20 @@ def test_evaluation_label_bookkeeping():
     assert conf[0, 0] == 1 and conf[1, 1] == 1                                 # repeated pairs count once (reference quirk)
     with pytest.raises(TypeError):
         E._measure_key(lambda a, b, axis=-1: 0)
+
+
+def test_stack_data_of_dense_modalities_is_lazy_and_equals_the_reference_formula():
+    # learner.py:53-56: safe_hstack([c * m]); dense-only stacks are formed on the device (StackedBlocks)
+    from multimodal_b200.learner import MultimodalLearner
+    from multimodal_b200.lib.array_utils import StackedBlocks
+    rs = np.random.RandomState(0)
+    a, b, c = rs.random_sample((7, 3)), rs.random_sample((7, 5)).astype(np.float32), rs.randint(0, 4, (7, 2))
+    lr = MultimodalLearner(['a', 'b', 'c'], [3, 5, 2], [2., .5, 3.], 4)
+    st = lr.stack_data(['a', 'b', 'c'], [a, b, c])
+    assert isinstance(st, StackedBlocks) and st.shape == (7, 10) and st.dtype == np.float64
+    np.testing.assert_array_equal(np.asarray(st), np.hstack([2. * a, .5 * b, 3. * c]))
+    sub = lr.stack_data(['c', 'a'], [c, a])                      # modality order of the call, coefficients by name
+    np.testing.assert_array_equal(sub.toarray(), np.hstack([3. * c, 2. * a]))
+    assert isinstance(lr.stack_data(['b'], [b]), np.ndarray)     # one modality: a plain scaled copy, as before
+    mixed = lr.stack_data(['a', 'b'], [a, sp.csr_matrix(b)])     # any sparse block makes the stack sparse
+    assert sp.issparse(mixed) and mixed.shape == (7, 8)
