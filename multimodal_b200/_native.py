@@ -189,9 +189,9 @@ class Engine(object):
             f32.append(1 if (c * m[:0, :0]).dtype == np.float32 else 0)
             if m.dtype not in (np.float32, np.float64):
                 m = m.astype(np.float64)
-            if not m.flags.c_contiguous:
-                m = np.ascontiguousarray(m)
             assert m.ndim == 2 and m.shape[0] == self.n, (m.shape, self.n)
+            if m.strides[1] != m.itemsize or m.strides[0] < m.shape[1] * m.itemsize:
+                m = np.ascontiguousarray(m)          # column slices of one array (row pitch > width) go as they are
             mats.append(m)
         nb = len(mats)
         assert sum(m.shape[1] for m in mats) == self.f

@@ -177,7 +177,8 @@ class KLdivNMF(object):
                 raise NameError("name 'n_iter' is not defined (max_iter < 1)")
             tol = self.tol * n_samples * n_features
             errors, n_iter = eng.run(self.max_iter, tol, _fit)
-            W = eng.get_coefficients()
+            # fit() throws the coefficients away (nmf.py:259-273): do not bring them back from the device for that
+            W = None if getattr(self, "_discard_coefficients", False) else eng.get_coefficients()
             if _fit:
                 self.components_ = eng.get_dictionary()
         finally:
@@ -208,7 +209,11 @@ class KLdivNMF(object):
         return W
 
     def fit(self, X, y=None, **params):
-        self.fit_transform(X, **params)
+        self._discard_coefficients = True
+        try:
+            self.fit_transform(X, **params)
+        finally:
+            self._discard_coefficients = False
         return self
 
     def transform(self, X, **params):
