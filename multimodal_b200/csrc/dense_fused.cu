@@ -301,8 +301,19 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(w_full);
       }
+      const int j_pf = nsteps > 8 ? nsteps - 8 : 0;
 #pragma unroll 1
       for (int j = 0; j < nsteps; j++, c++) {
+        if (TSW && j == j_pf) {
+          // the next row block's coefficients are pulled into L2 a few steps before this warp copies them to TMEM
+          const int64_t prow = (int64_t)(rb + gridDim.x) * FBM + r;
+          if (rb + (int)gridDim.x < p.n_blocks && prow < p.M) {
+#pragma unroll
+            for (int i = 0; i < KP / 64; i++)
+              if (grp * (KP / 2) + 32 * i < p.ldw)
+                asm volatile("prefetch.global.L2 [%0];" ::"l"(p.W + prow * p.ldw + grp * (KP / 2) + 32 * i));
+          }
+        }
         if ((int)(c & 1u) != grp) continue;
         const uint32_t ph2 = (c >> 1) & 1u, xb = c % XB, phx = (c / XB) & 1u;
         mbar_wait(s_full(grp), ph2, p.err, 9);
@@ -367,15 +378,20 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
 #pragma unroll 1
       for (int cc = 0; cc < KP / 32; cc++) {
         const int col0 = grp * (KP / 2) + cc * 16;
-        uint32_t v[16];
+        uint32_t v[16], wt[16];
         tmem_ld16_issue(g_tmem + lane_addr + col0, v);
+        if (TSW) tmem_ld16_issue(w_tmem + lane_addr + col0, wt);    // W is still in its TMEM block (it left L2 long ago)
         tmem_ld16_wait(v);
+        if (TSW) tmem_ld16_wait(wt);
         if (!p.only_kl && row < p.M && col0 < p.w_cols) {
           const float *wi = p.W + row * p.ldw + col0;
           float *wo = p.Wout + row * p.ldwo + col0;
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            const float4 w = __ldg(reinterpret_cast<const float4 *>(wi + 4 * i));
+            float4 w;
+            if (TSW) w = make_float4(__uint_as_float(wt[4 * i]), __uint_as_float(wt[4 * i + 1]), __uint_as_float(wt[4 * i + 2]),
+                                     __uint_as_float(wt[4 * i + 3]));
+            else w = __ldg(reinterpret_cast<const float4 *>(wi + 4 * i));
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
             if (p.colbias) b = __ldg(reinterpret_cast<const float4 *>(p.colbias + col0 + 4 * i));
             *reinterpret_cast<float4 *>(wo + 4 * i) =
