@@ -49,8 +49,8 @@ def parse():
     ap.add_argument("--k", type=int, default=0, help="override the number of components (development only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--alt-mode", default=os.environ.get("KLNMF_BENCH_ALT", "tf32x3"),
-                    help="second arithmetic mode reported under alt_modes ('' to skip)")
+    ap.add_argument("--alt-mode", default=os.environ.get("KLNMF_BENCH_ALT", "tf32r,tf32x3"),
+                    help="further arithmetic modes reported under alt_modes, comma separated ('' to skip)")
     return ap.parse_args()
 
 
@@ -476,12 +476,14 @@ def run_ours(args):
         pass
 
     alt = {}
-    if args.alt_mode and args.alt_mode != args.mode:
-        e2, t2, ms2, cnt2, l2, _, _ = one_mode(args.alt_mode, False)
+    for am in [m for m in (args.alt_mode or "").split(",") if m and m != args.mode]:
+        if kind == "sparse_fit" and am != "fp64":
+            continue                      # the sparse path computes in FP32 FMA in every TF32 mode
+        e2, t2, ms2, cnt2, l2, _, _ = one_mode(am, False)
         e2.close()
-        r2 = phase_roofline(ms2, cnt2, n_local, f, k, kind, args.steps, peaks, args.alt_mode)
-        alt[args.alt_mode] = {"value": args.steps / (t2 * 1e-3), "ms_per_step": t2 / args.steps, "roofline_frac": r2["frac"],
-                              "roofline_achieved": r2["achieved"], "kernel": r2["kernel"]}
+        r2 = phase_roofline(ms2, cnt2, n_local, f, k, kind, args.steps, peaks, am)
+        alt[am] = {"value": args.steps / (t2 * 1e-3), "ms_per_step": t2 / args.steps, "roofline_frac": r2["frac"],
+                   "roofline_achieved": r2["achieved"], "kernel": r2["kernel"]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

@@ -47,6 +47,7 @@ extern "C" {
 #define KLNMF_MODE_TF32     0   /* tcgen05 kind::tf32, one pass                      */
 #define KLNMF_MODE_TF32X3   1   /* tcgen05 split-TF32 (hi*hi + hi*lo + lo*hi)        */
 #define KLNMF_MODE_FP64     2   /* DMMA (mma.sync m8n8k4.f64)                        */
+#define KLNMF_MODE_TF32R    3   /* one pass on round-to-nearest TF32 copies of W, H, Q-1; FP32 state (hi, lo) */
 
 /* element types of user buffers */
 #define KLNMF_F32 0

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libklnmf.so")
 
 MODE_TF32, MODE_TF32X3, MODE_FP64 = 0, 1, 2
-MODES = {"tf32": MODE_TF32, "tf32x3": MODE_TF32X3, "fp64": MODE_FP64}
+MODES = {"tf32": MODE_TF32, "tf32x3": MODE_TF32X3, "fp64": MODE_FP64, "tf32r": 3}
 F32, F64 = 0, 1
 
 _c_i64 = ctypes.c_int64

@@ -316,6 +316,9 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
   ctx->centered = centered;
   const float qshift = centered ? 1.f : 0.f;
   const float *colbias = centered ? ctx->rsh32 : nullptr;
+  // TF32R: one MMA per step on the round-to-nearest TF32 halves of W, H and Q - 1 (the _Q parity hook and the
+  // stand-alone objective, KLdivNMF.error, keep the split form: they are not on the loop)
+  const int single = ctx->single_pass && !ratio_host && !only_error ? 1 : 0;
   if (centered) KL_TRY(launch_rsh32(ctx));
   if (fused) {
     // k <= 128 (fit, transform) / k <= 256 (transform): the coefficient half-step is one fused kernel, the ratio
@@ -374,6 +377,7 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
       d.aux = (const char *)ctx->X + r0 * ctx->ldx * es; d.ldaux = ctx->ldx;
       d.kl = ctx->dred; d.stop = stop; d.only_kl = only_error ? 1 : 0;
       d.qshift = qshift;
+      d.single_pass = single; d.round_out = single;
       KL_TRY(dense_gemm(ctx, EPI_RATIO, d));
     }
     if (ratio_host) {   // _Q parity hook: hand the ratio panel back to the host
@@ -393,6 +397,7 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
       d.aux = Wc; d.ldaux = ctx->ldw; d.aux_lo = Wclo;
       d.stop = stop;
       d.colbias = colbias;
+      d.single_pass = single;
       KL_TRY(dense_gemm(ctx, EPI_MULW, d));
     }
     if (fit) {  // dictionary numerator: N += W'^T.Q  (stale Q, new W: nmf.py:345-349)
@@ -404,6 +409,7 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
       d.B = ctx->Q; d.b_sk = ctx->ldq; d.b_sn = 1; d.B_lo = ctx->Qlo;
       d.out = ctx->num; d.ldo = ctx->ldh;
       d.stop = stop;
+      d.single_pass = single;
       KL_TRY(dense_gemm(ctx, EPI_ACC, d));
     }
   }
@@ -443,7 +449,7 @@ int klnmf_create(klnmf_ctx **out, int device, int64_t n_local, int64_t f, int64_
   *out = nullptr;
   KL_CHECK(n_local >= 0 && f > 0 && k > 0, KLNMF_EINVAL, "klnmf_create: bad shape n=%lld f=%lld k=%lld",
            (long long)n_local, (long long)f, (long long)k);
-  KL_CHECK(mode == KLNMF_MODE_TF32 || mode == KLNMF_MODE_TF32X3 || mode == KLNMF_MODE_FP64, KLNMF_EINVAL,
+  KL_CHECK(mode == KLNMF_MODE_TF32 || mode == KLNMF_MODE_TF32X3 || mode == KLNMF_MODE_FP64 || mode == KLNMF_MODE_TF32R, KLNMF_EINVAL,
            "klnmf_create: unknown mode %d", mode);
   const int ndev = klnmf_device_count();
   KL_CHECK(ndev > 0, KLNMF_ENODEVICE, "no CUDA device: libklnmf has no CPU path");
@@ -460,7 +466,8 @@ int klnmf_create(klnmf_ctx **out, int device, int64_t n_local, int64_t f, int64_
   ctx->sm_count = prop.multiProcessorCount;
   const char *dbg = getenv("KLNMF_DEBUG_ENGINE");
   ctx->debug_simt = dbg && strcmp(dbg, "simt") == 0;
-  ctx->split = (mode == KLNMF_MODE_TF32X3) && !ctx->debug_simt;
+  ctx->split = (mode == KLNMF_MODE_TF32X3 || mode == KLNMF_MODE_TF32R) && !ctx->debug_simt;
+  ctx->single_pass = mode == KLNMF_MODE_TF32R && !ctx->debug_simt;
   const char *pf = getenv("KLNMF_PROFILE");
   ctx->profile = pf && pf[0] == '1';
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) {
@@ -744,6 +751,7 @@ int klnmf_init_coefficients(klnmf_ctx *ctx) {
     d.B = ctx->H[hc]; d.b_sk = 1; d.b_sn = ctx->ldh; d.B_lo = ctx->split ? ctx->Hlo[hc] : nullptr;
     d.out = (char *)ctx->W[cur] + r0 * ctx->ldw * es; d.ldo = ctx->ldw;
     d.out_lo = ctx->split ? (char *)ctx->Wlo[cur] + r0 * ctx->ldw * es : nullptr;
+    d.single_pass = ctx->single_pass ? 1 : 0;
     KL_TRY(dense_gemm(ctx, EPI_STORE, d));
   }
   ctx->have_w = true;
@@ -800,7 +808,7 @@ int klnmf_run(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, double *err
   // reference then breaks only if the objective RISES.  Objective noise of the reduced-precision
   // contractions must not trigger that break, so the rise has to exceed the mode's noise floor.
   double slack = 0.0;
-  if (tol_abs == 0.0) slack = ctx->mode == KLNMF_MODE_FP64 ? 0.0 : (ctx->mode == KLNMF_MODE_TF32X3 ? 1e-6 : 1e-4);
+  if (tol_abs == 0.0) slack = ctx->mode == KLNMF_MODE_FP64 ? 0.0 : (ctx->mode == KLNMF_MODE_TF32X3 ? 1e-6 : (ctx->mode == KLNMF_MODE_TF32R ? 1e-5 : 1e-4));
   double *hp = ctx->pinned;
   hp[DS_KL] = 0.0; hp[DS_PREV] = INFINITY; hp[DS_WHSUM] = slack; hp[DS_TOL] = tol_abs;
   KL_CUDA(cudaMemcpyAsync(ctx->dscal + DS_KL, hp + DS_KL, 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -1221,7 +1229,7 @@ const char *klnmf_engine_name(klnmf_ctx *ctx) {
   if (!ctx) return "none";
   if (ctx->es == 8) return "dmma_f64";
   if (ctx->debug_simt) return "simt_f32_debug";
-  return ctx->mode == KLNMF_MODE_TF32X3 ? "tcgen05_tf32x3" : "tcgen05_tf32";
+  return ctx->mode == KLNMF_MODE_TF32X3 ? "tcgen05_tf32x3" : (ctx->mode == KLNMF_MODE_TF32R ? "tcgen05_tf32r" : "tcgen05_tf32");
 }
 
 }  // extern "C"

@@ -88,6 +88,7 @@ struct klnmf_ctx {
   double *colsumW = nullptr;   // k   (dense, centered ratio: column sums of the new coefficients, all ranks)
   float *rsh32 = nullptr;      // ldw + 32 floats: rowsumH as FP32, zero beyond k (bias of the centered coefficient update)
   bool centered = false;       // this iteration's ratio panel holds Q - 1 (see dense_iteration)
+  bool single_pass = false;    // TF32R: (hi, lo) state like TF32X3, but the contractions of the loop multiply the hi parts only
   double *hsum = nullptr;      // k   scratch of the normaliser
   double *dred = nullptr;      // [kl, sum(X.data), colsum(W)[0..ldw)] : the doubles that are all-reduced
   int64_t dred_len = 0;
@@ -145,6 +146,8 @@ struct GemmDesc {
   int splitk;                            // EPI_ACC only
   int only_kl;                           // EPI_RATIO: do not write out (klnmf_error)
   float qshift;                          // EPI_RATIO: the stored ratio is q - qshift (1 = centered, 0 = plain)
+  int single_pass;                       // multiply the hi parts only (A_lo, B_lo ignored); out_lo / aux_lo still honoured
+  int round_out;                         // EPI_RATIO without out_lo: store the ratio rounded to nearest TF32
   const float *colbias;                  // EPI_MULW: out = aux * (C + colbias[col]) (nullptr: no bias)
   // split-TF32 residual arrays (same layout as their high parts); nullptr unless ctx->split
   const void *A_lo; const void *B_lo; void *out_lo; const void *aux_lo;

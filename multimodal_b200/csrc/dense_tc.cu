@@ -48,6 +48,7 @@ struct TcParams {
   int no_prefetch;                           // default 1; KLNMF_TC_PF=1 re-enables the L2 prefetch of the next X tile
   int relaxed;                               // accumulator hand-back with relaxed arrives (KLNMF_TC_RELAXED=0: release)
   float qshift;                              // EPI_RATIO: the stored ratio is q - qshift (centered ratio, api.cu)
+  int round_out;                             // EPI_RATIO (TMA-staged form): store the ratio rounded to nearest TF32
   const float *colbias;                      // EPI_MULW: out = aux * (acc + colbias[col])
   int dbg;                                   // timing experiments (KLNMF_TC_DBG): 1 no ratio math, 2 no Q store, 4 one MMA per K block only
   uint32_t k_lt;                             // K-major layout type: 2 = SWIZZLE_128B, 1 = SWIZZLE_128B_BASE32B (experiment)
@@ -100,7 +101,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams &p, int64_t row, i
   const int epi = p.epi;
   if (epi == EPI_STORE) {
     if (p.only_kl) return;     // diagnostic (KLNMF_BENCH_NOSTORE): contraction without the output traffic
-    if (SPLIT && p.out_lo) {
+    if (p.out_lo) {
       float hi[32], lo[32];
 #pragma unroll
       for (int j = 0; j < 32; j++) { hi[j] = tf32_round(acc[j]); lo[j] = acc[j] - hi[j]; }
@@ -121,7 +122,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams &p, int64_t row, i
     if (!p.only_kl) {
 #pragma unroll
       for (int j = 0; j < 32; j++) q[j] -= p.qshift;
-      if (SPLIT && p.out_lo) {
+      if (p.out_lo) {
         float lo[32];
 #pragma unroll
         for (int j = 0; j < 32; j++) { float h = tf32_round(q[j]); lo[j] = q[j] - h; q[j] = h; }
@@ -134,7 +135,7 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams &p, int64_t row, i
   } else if (epi == EPI_MULW) {
     float w[32];
     ld_row32(p.aux + row * p.ldaux + col0, w);
-    if (SPLIT && p.aux_lo) {
+    if (p.aux_lo) {
       float wl[32];
       ld_row32(p.aux_lo + row * p.ldaux + col0, wl);
 #pragma unroll
@@ -144,12 +145,15 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams &p, int64_t row, i
 #pragma unroll
       for (int j = 0; j < 8; j++) {
         const float4 b = __ldg(reinterpret_cast<const float4 *>(p.colbias + col0 + 4 * j));
-        acc[4 * j] += b.x; acc[4 * j + 1] += b.y; acc[4 * j + 2] += b.z; acc[4 * j + 3] += b.w;
+        // Q.H^T is a sum of non-negative terms; its centered form (Q-1).H^T + rowsum(H) can come out a rounding error
+        // below zero where the ratio vanishes (all-zero samples), and a negative coefficient would poison log(W.H)
+        acc[4 * j] = fmaxf(acc[4 * j] + b.x, 0.f); acc[4 * j + 1] = fmaxf(acc[4 * j + 1] + b.y, 0.f);
+        acc[4 * j + 2] = fmaxf(acc[4 * j + 2] + b.z, 0.f); acc[4 * j + 3] = fmaxf(acc[4 * j + 3] + b.w, 0.f);
       }
     }
 #pragma unroll
     for (int j = 0; j < 32; j++) w[j] *= acc[j];
-    if (SPLIT && p.out_lo) {
+    if (p.out_lo) {
       float lo[32];
 #pragma unroll
       for (int j = 0; j < 32; j++) { float h = tf32_round(w[j]); lo[j] = w[j] - h; w[j] = h; }
@@ -498,9 +502,18 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int j = 0; j < 32; j += 2) {
           if (p.dbg & 1) break;
           float q0, q1;
-          part0 += ratio_term<false>(x[j], __uint_as_float(v[j]), q0);
-          part1 += ratio_term<false>(x[j + 1], __uint_as_float(v[j + 1]), q1);
+          if (p.accurate) {      // TF32R: the objective in its cancellation-free form (tc_ptx.cuh)
+            part0 += ratio_term_cf(x[j], __uint_as_float(v[j]), q0);
+            part1 += ratio_term_cf(x[j + 1], __uint_as_float(v[j + 1]), q1);
+          } else {
+            part0 += ratio_term<false>(x[j], __uint_as_float(v[j]), q0);
+            part1 += ratio_term<false>(x[j + 1], __uint_as_float(v[j + 1]), q1);
+          }
           x[j] = q0 - p.qshift; x[j + 1] = q1 - p.qshift;
+        }
+        if (p.round_out) {     // TF32R: the consumers multiply exactly what is stored (the tensor core would truncate)
+#pragma unroll
+          for (int j = 0; j < 32; j++) x[j] = tf32_round(x[j]);
         }
         kl_tile += part0 + part1;
         if (!p.only_kl) {
@@ -717,19 +730,19 @@ int tc_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d) {
     cudaMemsetAsync(st->err_dev, 0, 4, ctx->stream);
     ctx->tc = st;
   }
-  const bool split = ctx->split && d.A_lo != nullptr && d.B_lo != nullptr;
-  KL_CHECK(!ctx->split || split, KLNMF_EINVAL, "tc_gemm: split-TF32 mode needs (hi, lo) operands");
+  const bool split = ctx->split && !d.single_pass && d.A_lo != nullptr && d.B_lo != nullptr;
+  KL_CHECK(!ctx->split || split || d.single_pass, KLNMF_EINVAL, "tc_gemm: split-TF32 mode needs (hi, lo) operands");
   TcParams p{};
   p.M = d.M; p.N = d.N; p.K = d.K;
   p.epi = epi; p.only_kl = d.only_kl;
-  p.qshift = d.qshift; p.colbias = d.colbias;
+  p.qshift = d.qshift; p.colbias = d.colbias; p.round_out = d.round_out;
   if (epi == EPI_STORE && getenv("KLNMF_BENCH_NOSTORE")) p.only_kl = 1;
   // The split-TF32 ratio epilogue evaluates the objective in its cancellation-free form (ratio_term_cf, tc_ptx.cuh): no
   // IEEE division, no logf, and more accurate than both once a fit has converged (cfg3 shape: 21.1 -> 17.8 ms; the
   // epilogue, not the three MMAs per step, paces this contraction).  The plain MUFU forms (KLNMF_TC_FASTMATH=1, 15.8 ms)
   // give the same W and H to three digits, but lg2.approx is off by ~2e-7 of sum(X) in the objective: 1.5e-4 on the
   // 200-iteration golden case against the stated 2e-5 (profiles/r1_s4_run50_*.log, r1_s4_run52_*.log, r1_s4_run56_*.log).
-  p.accurate = ctx->mode == KLNMF_MODE_TF32X3 ? 1 : 0;
+  p.accurate = (ctx->mode == KLNMF_MODE_TF32X3 || ctx->mode == KLNMF_MODE_TF32R) ? 1 : 0;
   if (getenv("KLNMF_TC_FASTMATH") && atoi(getenv("KLNMF_TC_FASTMATH")) == 1) p.accurate = 0;
   p.out = (float *)d.out; p.out_lo = (float *)d.out_lo; p.ldo = d.ldo;
   p.n_store = round_up(d.N, 32);

@@ -52,14 +52,14 @@ __global__ void __launch_bounds__(512) dict_update_kernel(const T *__restrict__ 
   for (int64_t j = threadIdx.x; j < f; j += blockDim.x) {
     T v = h[j];
     if (hl) v += hl[j];
-    s += (double)(v * (nm[j] + add));
+    s += (double)(v * (rowadd ? fmax(nm[j] + add, (T)0) : nm[j]));
   }
   s = block_sum(s, red);
   const double inv = 1.0 / (KL_NORM_EPS + s);
   for (int64_t j = threadIdx.x; j < f; j += blockDim.x) {
     T v = h[j];
     if (hl) v += hl[j];
-    T r = (T)((double)(v * (nm[j] + add)) * inv);
+    T r = (T)((double)(v * (rowadd ? fmax(nm[j] + add, (T)0) : nm[j])) * inv);   // the centered numerator, clamped like G
     if (Hnlo) {
       float hi = tf32_hi((float)r);
       Hn[a * ld + j] = (T)hi;

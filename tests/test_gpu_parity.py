@@ -5,6 +5,9 @@ Stated tolerances (norm-relative on W, H after 10 iterations; relative on the KL
     fp64    1e-9            DMMA float64, only the summation order differs
     tf32x3  2e-5 / 2e-5     split-TF32 contractions are FP32-grade (measured ~1e-7 in emulation)
     tf32    3e-3 / 1e-2     one-pass TF32 (measured 1.5e-4 / 3e-3 in emulation)
+    tf32r   5e-4 / 5e-4 (1e-3 on a converged fit)  one pass on round-to-nearest TF32 copies, centered ratio, cancellation-free objective
+                            (measured 1.3e-5..3.9e-5 / 3e-6..2.8e-5 against the FP64 mode at k, f >= 64,
+                            tools/accuracy_vs_shape.py; the 2^-12 operand rounding does not average out at k = 2)
 """
 import numpy as np
 import pytest
@@ -17,9 +20,9 @@ from oracle import klnmf_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-MODES = ["fp64", "tf32x3", "tf32"]
-TOL_WH = {"fp64": 1e-9, "tf32x3": 2e-5, "tf32": 3e-3}
-TOL_KL = {"fp64": 1e-9, "tf32x3": 2e-5, "tf32": 1e-2}
+MODES = ["fp64", "tf32x3", "tf32r", "tf32"]
+TOL_WH = {"fp64": 1e-9, "tf32x3": 2e-5, "tf32r": 5e-4, "tf32": 3e-3}
+TOL_KL = {"fp64": 1e-9, "tf32x3": 2e-5, "tf32r": 5e-4, "tf32": 1e-2}
 
 
 def fit(X, k, iters, seed, mode, tol=0, **kw):
@@ -35,8 +38,11 @@ def test_kat_dense(golden, mode):
     est, W, errs = fit(cases.kat_dense(), 2, 10, 0, mode)
     assert cases.rel_fro(W, g["W"]) < TOL_WH[mode]
     assert cases.rel_fro(est.components_, g["H"]) < TOL_WH[mode]
-    np.testing.assert_allclose(errs, g["errors"], rtol=TOL_KL[mode] * 10)
-    np.testing.assert_allclose(est.error(cases.kat_dense(), W), g["after"], rtol=TOL_KL[mode] * 10)
+    # a 6 x 2 matrix with k = 2: nothing averages the 2^-12 operand rounding of the one-pass modes, and the objective
+    # after 10 iterations (0.185, from 5.75) magnifies the resulting 2e-4 on W
+    kl_tol = 1e-2 if mode == "tf32r" else TOL_KL[mode] * 10
+    np.testing.assert_allclose(errs, g["errors"], rtol=kl_tol)
+    np.testing.assert_allclose(est.error(cases.kat_dense(), W), g["after"], rtol=kl_tol)
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -48,7 +54,7 @@ def test_kat_csr(golden, mode):
     np.testing.assert_allclose(errs, g["errors"], rtol=tol)
     # and the dense path on the same matrix is the reference's OTHER algorithm (eps at X == 0)
     est, W, errs = fit(cases.kat_csr().toarray(), 2, 10, 0, mode)
-    np.testing.assert_allclose(errs, g["errors_densepath"], rtol=TOL_KL[mode] * 10)
+    np.testing.assert_allclose(errs, g["errors_densepath"], rtol=1e-2 if mode == "tf32r" else TOL_KL[mode] * 10)   # k = 2
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -67,9 +73,11 @@ def test_dense_fit_golden(golden, mode, name, maker, k, seed, long_iters):
     np.testing.assert_allclose(errs, g["errors10"], rtol=TOL_KL[mode])
     est, W, errs = fit(maker(), k, long_iters, seed, mode)
     assert len(errs) == long_iters
-    assert abs(errs[-1] - g["errors_long"][-1]) <= TOL_KL[mode] * abs(g["errors_long"][-1])
+    # on a converged fit the objective is small against sum(X) and follows the 1e-5..1e-4 of W and H: tf32r states 1e-3
+    tol_long = 1e-3 if mode == "tf32r" else TOL_KL[mode]
+    assert abs(errs[-1] - g["errors_long"][-1]) <= tol_long * abs(g["errors_long"][-1])
     final = est.error(maker(), W)
-    assert abs(final - g["final_error"]) <= TOL_KL[mode] * abs(g["final_error"])
+    assert abs(final - g["final_error"]) <= tol_long * abs(g["final_error"])
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -222,7 +230,7 @@ def test_learner_dense_stack_formed_on_the_device(mode):
     est = KLdivNMF(n_components=9, max_iter=10, tol=0, mode=mode)
     np.random.seed(4)
     est.fit(V)
-    assert cases.rel_fro(lr.dico, est.components_) < (1e-12 if mode == "fp64" else 1e-6)
+    assert cases.rel_fro(lr.dico, est.components_) < (1e-12 if mode == "fp64" else (1e-5 if mode == "tf32r" else 1e-6))
     ref = O.Learner(mods, dims, coefs, 9)
     np.random.seed(4)
     ref.train(mats, 10)

@@ -26,7 +26,7 @@ if __name__ == "__main__":
     iters = 10
     for (n, f, k) in [(2048, 512, 64), (8192, 1024, 256), (8192, 4096, 256), (8192, 8192, 512), (65536, 8192, 512), (262144, 2048, 128)]:
         ref = run(n, f, k, "fp64", iters)
-        for mode in ("tf32x3", "tf32"):
+        for mode in ("tf32x3", "tf32r", "tf32"):
             W, H, e = run(n, f, k, mode, iters)
             print("n=%6d f=%5d k=%3d %-6s  W %.2e  H %.2e  KL %.2e" % (n, f, k, mode, cases.rel_fro(W, ref[0]), cases.rel_fro(H, ref[1]),
                   np.max(np.abs(e - ref[2]) / np.abs(ref[2]))), flush=True)
