@@ -1,113 +1,110 @@
 # encoding: utf-8
-"""Learning from multiple modalities with one KL-NMF dictionary, B200-native.
+"""One KL-NMF dictionary over several modalities, B200-native.
 
-Drop-in for `multimodal/learner.py` of omangin/multimodal (94 lines there): the same
-functions, class, method names, argument meaning, assertions and state (`dico`,
-`nmf_train`); the NMF fit / transform and the reconstruction product run on the GPU
-through `multimodal_b200.lib.nmf.KLdivNMF` and libklnmf.
+Drop-in for `multimodal/learner.py` of omangin/multimodal: `fit_coefficients` and `MultimodalLearner` keep the
+reference's names, argument meaning, assertions and state (`mod`, `dim`, `coef`, `k`, `dico`, `nmf_train`), so callers
+(`experiment.py:154-180, 274, 365`, the samples) work unchanged.  The arithmetic is not here: fitting, inferring
+coefficients and the reconstruction product run on the GPU through `KLdivNMF` / libklnmf, and a stack of dense
+modalities is scaled and concatenated on the device (`StackedBlocks`), never on the host.
+
+Column layout of the dictionary (learner.py:43-65): modality i owns columns [sum(dim[:i]), sum(dim[:i]) + dim[i]).
 """
 import numpy as np
 
 from . import _native
+from .lib.array_utils import StackedBlocks, safe_hstack
 from .lib.nmf import KLdivNMF as NMF
-from .lib.array_utils import safe_hstack, StackedBlocks
 
 
 def fit_coefficients(data_obs, dictionary, iter_nmf=100, verbose=False, mode=None, device=0):
-    """Coefficients of `data_obs` on a fixed dictionary (learner.py:11-15): tol=0, so exactly
-    `iter_nmf` transform iterations unless the objective rises."""
-    nmf_obs = NMF(n_components=dictionary.shape[0], max_iter=iter_nmf, tol=0, mode=mode, device=device)
-    nmf_obs.components_ = dictionary
-    coefficients = nmf_obs.transform(data_obs, scale_W=True)
-    return coefficients
+    """Coefficients of `data_obs` on a FIXED dictionary (learner.py:11-15).  tol=0 means: exactly `iter_nmf`
+    transform iterations unless the objective rises; `scale_W` is passed and ignored, as in the reference."""
+    estimator = NMF(n_components=dictionary.shape[0], max_iter=iter_nmf, tol=0, mode=mode, device=device)
+    estimator.components_ = dictionary
+    return estimator.transform(data_obs, scale_W=True)
 
 
 class MultimodalLearner(object):
+    """Joint dictionary of several modalities (learner.py:18-94)."""
 
     def __init__(self, modalities, dimensions, coefficients, k,
                  sparseness=None, sp_coef=.1, mode=None, device=0):
-        self.mod = modalities  # Names of the modalities
-        self.dim = dimensions  # Dimensions of modalities
-        self.coef = coefficients  # Coefficients used to compensate between modalities
+        self.mod = modalities            # names
+        self.dim = dimensions            # feature counts
+        self.coef = coefficients         # weights that balance the modalities in the stack
         self.k = k
-        self.sparseness = sparseness  # data, components, None
+        self.sparseness = sparseness     # 'data' / 'components' / None in the reference; only None is implemented there
         self.sp_coef = sp_coef
-        self.dico = None  # None means not trained yet
-        self.mode = mode
+        self.dico = None                 # k x sum(dim) once trained (or assigned by the caller)
+        self.mode = mode                 # arithmetic mode of libklnmf (not in the reference)
         self.device = device
 
-    def train(self, data_matrices, iterations):
-        """learner.py:31-41."""
-        n_samples = data_matrices[0].shape[0]
-        for m, d in zip(data_matrices, self.dim):
-            assert(m.shape == (n_samples, d))
-        Vtrain = self.stack_data(self.mod, data_matrices)
-        if self.sparseness is not None:
-            raise NotImplemented          # noqa: F901  (the reference raises exactly this)
-        self.nmf_train = NMF(n_components=self.k, max_iter=iterations, tol=0,
-                             mode=self.mode, device=self.device)
-        self.nmf_train.fit(Vtrain, scale_W=True)
-        self.dico = self.nmf_train.components_
+    # ---- layout ---------------------------------------------------------------------------------------------
+    def get_index(self, modality):
+        return self.mod.index(modality)
+
+    def get_axis_range(self, modality):
+        """(start, stop) of the modality's columns in the stacked data / dictionary (learner.py:58-62)."""
+        position = self.get_index(modality)
+        first = int(np.sum(self.dim[:position], dtype=np.int64)) if position else 0
+        return (first, first + self.dim[position])
 
     def get_dico(self, modality=None):
         if modality is None:
             return self.dico
-        else:
-            start, stop = self.get_axis_range(modality)
-            return self.dico[:, start:stop]
+        first, last = self.get_axis_range(modality)
+        return self.dico[:, first:last]
 
     def get_stacked_dicos(self, modalities):
-        return safe_hstack([self.get_dico(modality=m) for m in modalities])
+        return safe_hstack([self.get_dico(modality=name) for name in modalities])
 
     def stack_data(self, modalities, data_matrices):
-        """Scaled concatenation (learner.py:53-56); one sparse block makes the stack sparse."""
-        coefs = [self.coef[self.get_index(mod)] for mod in modalities]
-        if len(data_matrices) > 1 and all(isinstance(m, np.ndarray) and m.ndim == 2 for m in data_matrices):
-            # all modalities dense: the scaled concatenation is formed on the device, block by block
-            return StackedBlocks(data_matrices, coefs)
-        return safe_hstack([c * m
-                            for m, c in zip(data_matrices, coefs)])
+        """coef-weighted concatenation in the order of `modalities` (learner.py:53-56).  A sparse block makes the
+        whole stack sparse (array_utils.py:5-9); several dense blocks stay apart until the device has them."""
+        weights = [self.coef[self.get_index(name)] for name in modalities]
+        all_dense = all(isinstance(block, np.ndarray) and block.ndim == 2 for block in data_matrices)
+        if all_dense and len(data_matrices) > 1:
+            return StackedBlocks(data_matrices, weights)
+        return safe_hstack([w * block for block, w in zip(data_matrices, weights)])
 
-    def get_axis_range(self, modality):
-        idx = self.get_index(modality)
-        start = sum(self.dim[:idx])
-        stop = start + self.dim[idx]
-        return (start, stop)
+    # ---- training (learner.py:31-41) --------------------------------------------------------------------------
+    def train(self, data_matrices, iterations):
+        n_samples = data_matrices[0].shape[0]
+        for block, width in zip(data_matrices, self.dim):
+            assert(block.shape == (n_samples, width))
+        stacked = self.stack_data(self.mod, data_matrices)
+        if self.sparseness is not None:
+            raise NotImplemented          # noqa: F901  (the reference raises exactly this object)
+        self.nmf_train = NMF(n_components=self.k, max_iter=iterations, tol=0,
+                             mode=self.mode, device=self.device)
+        self.nmf_train.fit(stacked, scale_W=True)
+        self.dico = self.nmf_train.components_
 
-    def get_index(self, modality):
-        return self.mod.index(modality)
+    # ---- inference (learner.py:67-94) -------------------------------------------------------------------------
+    def reconstruct_internal_multi(self, orig_mods, test_data, iterations):
+        """Internal coefficients of samples observed through a subset of the modalities."""
+        for name, block in zip(orig_mods, test_data):
+            assert(block.shape[1] == self.dim[self.get_index(name)])
+        return fit_coefficients(self.stack_data(orig_mods, test_data), self.get_stacked_dicos(orig_mods),
+                                iter_nmf=iterations, mode=self.mode, device=self.device)
 
     def reconstruct_internal(self, orig_mod, test_data, iterations):
-        return self.reconstruct_internal_multi([orig_mod], [test_data],
-                                               iterations)
-
-    def reconstruct_internal_multi(self, orig_mods, test_data, iterations):
-        """learner.py:71-78."""
-        for mod, data in zip(orig_mods, test_data):
-            assert(data.shape[1] == self.dim[self.get_index(mod)])
-        stacked_dico = self.get_stacked_dicos(orig_mods)
-        stacked_data = self.stack_data(orig_mods, test_data)
-        internal = fit_coefficients(stacked_data, stacked_dico,
-                                    iter_nmf=iterations, mode=self.mode, device=self.device)
-        return internal
+        return self.reconstruct_internal_multi([orig_mod], [test_data], iterations)
 
     def _dot(self, internal, dico):
-        """internal.dot(dico) on the device (learner.py:81,84)."""
+        """internal.dot(dico) on the device (learner.py:81, 84)."""
         return _native.contract(np.asarray(internal, dtype=np.float64), np.asarray(dico, dtype=np.float64),
                                 self.mode, device=self.device)
-
-    def reconstruct_modality(self, dest_mod, internal):
-        return self._dot(internal, self.get_dico(dest_mod))
 
     def reconstruct_modalities(self, dest_mods, internal):
         return self._dot(internal, self.get_stacked_dicos(dest_mods))
 
-    def modality_to_modality(self, orig_mod, dest_mod, test_data, iterations):
-        return self.modalities_to_modalities([orig_mod], [dest_mod],
-                                             [test_data], iterations)
+    def reconstruct_modality(self, dest_mod, internal):
+        return self._dot(internal, self.get_dico(dest_mod))
 
-    def modalities_to_modalities(self, orig_mods, dest_mods, test_data,
-                                 iterations):
-        internal = self.reconstruct_internal_multi(orig_mods, test_data,
-                                                   iterations)
-        return self.reconstruct_modalities(dest_mods, internal)
+    def modalities_to_modalities(self, orig_mods, dest_mods, test_data, iterations):
+        hidden = self.reconstruct_internal_multi(orig_mods, test_data, iterations)
+        return self.reconstruct_modalities(dest_mods, hidden)
+
+    def modality_to_modality(self, orig_mod, dest_mod, test_data, iterations):
+        return self.modalities_to_modalities([orig_mod], [dest_mod], [test_data], iterations)
