@@ -212,3 +212,66 @@ def test_sharded_update_equals_unsharded():
     Ws, Hs = O.sharded_update([X[b[i]:b[i + 1]] for i in range(3)],
                               [W[b[i]:b[i + 1]] for i in range(3)], H)
     assert cases.rel_fro(np.vstack(Ws), Wref) < 1e-14 and cases.rel_fro(Hs, Href) < 1e-13
+
+
+# ---- the size-independent properties tests/test_gpu_properties.py relies on, established on the oracle itself ----
+@pytest.mark.parametrize("sparse", [False, True], ids=["dense", "csr"])
+def test_oracle_scale_equivariance(sparse):
+    # X -> cX gives W -> cW and the same dictionary (W0 = X.H0^T scales, the ratio does not, up to eps)
+    rs = np.random.RandomState(8)
+    X = rs.gamma(0.7, 1.0, size=(60, 40)) + 0.05
+    if sparse:
+        X[rs.random_sample(X.shape) < 0.8] = 0.0
+        X = sp.csr_matrix(X)
+    outs = []
+    for c in (1.0, 8.0):
+        np.random.seed(2)
+        W, H, _, _ = O.fit_transform(X * c, k=5, max_iter=8, tol=0)
+        outs.append((np.asarray(W), np.asarray(H)))
+    assert cases.rel_fro(outs[1][0], 8.0 * outs[0][0]) < 1e-6
+    assert cases.rel_fro(outs[1][1], outs[0][1]) < 1e-6
+
+
+def test_oracle_rows_are_independent_given_the_dictionary():
+    # what sample sharding and the row-subset GPU test rest on
+    rs = np.random.RandomState(3)
+    X = rs.gamma(0.5, 1.0, size=(90, 30))
+    np.random.seed(4)
+    H = O.init_dictionary(6, 30)
+    W = np.asarray(X.dot(H.T))
+    Wsub = W[10:40].copy()
+    for _ in range(6):
+        W, _ = O.update(X, W, H, fit=False)
+        Wsub, _ = O.update(X[10:40], Wsub, H, fit=False)
+    np.testing.assert_allclose(Wsub, W[10:40], rtol=1e-12)
+
+
+def test_oracle_centered_ratio_identities():
+    # the algebra behind the centered ratio of the split-TF32 modes:
+    #   Q.H^T = (Q-1).H^T + rowsum(H)   and   W'^T.Q = W'^T.(Q-1) + colsum(W')
+    rs = np.random.RandomState(5)
+    X = rs.gamma(0.5, 1.0, size=(50, 35))
+    np.random.seed(6)
+    H = O.init_dictionary(4, 35)
+    W = np.asarray(X.dot(H.T))
+    Q = np.asarray(O.ratio(X, W, H))
+    G = Q.dot(H.T)
+    np.testing.assert_allclose((Q - 1.0).dot(H.T) + H.sum(axis=1), G, rtol=1e-12)
+    Wn = W * G
+    np.testing.assert_allclose(Wn.T.dot(Q - 1.0) + Wn.sum(axis=0)[:, None], Wn.T.dot(Q), rtol=1e-12)
+    assert (G >= 0).all()          # a sum of non-negative terms: what the clamp in the centered epilogue restores
+
+
+def test_oracle_cancellation_free_objective():
+    # x log q - x + s  ==  x P(u) + (x - s)(x - s - eps)/d,  u = (x - s)/d,  d = s + eps,  P(u) = log1p(u) - u
+    rs = np.random.RandomState(7)
+    x = rs.gamma(0.5, 1.0, size=5000)
+    x[rs.random_sample(x.size) < 0.3] = 0.0
+    s = x * np.exp(rs.normal(0, 0.5, x.size)) + rs.random_sample(x.size) * 1e-3
+    eps = O.EPS
+    d = s + eps
+    u = (x - s) / d
+    lhs = x * np.log((x + eps) / d) - x + s
+    rhs = x * (np.log1p(u) - u) + (x - s) * (x - s - eps) / d
+    np.testing.assert_allclose(rhs, lhs, rtol=1e-9, atol=1e-12)
+    assert abs(rhs.sum() - O.generalized_KL(x, s)) < 1e-9 * abs(lhs.sum())
