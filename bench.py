@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- KL-NMF iterations/sec on the BASELINE.json workload (see DESIGN.md "Measurement").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode tf32x3|tf32|fp64]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--mode tf32r|tf32|tf32x3|fp64]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
@@ -14,7 +14,10 @@ Prints ONE JSON line on rank 0.  `value` = iterations/s with X resident in HBM (
 CUDA events on the engine's stream, max over ranks); `e2e` = the same metric through the
 public API (KLdivNMF.fit_transform on a pinned HOST array: H2D of X and D2H of W inside the
 timed region); `roofline` = the dominant contraction kernel against the measured TF32 peak;
-`cpu_baseline` = the float64 numpy oracle on this box's host cores on a bounded row-subsample.
+`cpu_baseline` = the reference itself (baseline/_ref, installed by baseline/install_reference.sh; the float64 oracle
+port when that directory is absent) on this box's host cores on a bounded row-subsample; `workloads` = the other two
+large configs (cfg3 transform, cfg4 sparse fit) measured the same way in the same run.  The arithmetic mode is the
+library's default (`_native.DEFAULT_MODE`); `alt_modes` carries the others.
 """
 import argparse
 import json
@@ -43,15 +46,22 @@ def parse():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--mode", default=os.environ.get("KLNMF_BENCH_MODE", "tf32"))
+    ap.add_argument("--mode", default=os.environ.get("KLNMF_BENCH_MODE", ""), help="default: the library's default mode")
     ap.add_argument("--workload", default=os.environ.get("KLNMF_BENCH_WORKLOAD", "cfg5"), choices=sorted(WORKLOADS))
     ap.add_argument("--n", type=int, default=0, help="override the total sample count (development only)")
     ap.add_argument("--k", type=int, default=0, help="override the number of components (development only)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
-    ap.add_argument("--alt-mode", default=os.environ.get("KLNMF_BENCH_ALT", "tf32r,tf32x3"),
+    ap.add_argument("--alt-mode", default=os.environ.get("KLNMF_BENCH_ALT", "tf32,tf32x3"),
                     help="further arithmetic modes reported under alt_modes, comma separated ('' to skip)")
-    return ap.parse_args()
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg3 / cfg4 entries under `workloads`")
+    ap.add_argument("--e2e-iters", type=int, default=50,
+                    help="second end-to-end call at the reference's iteration count (experiment.py:20-25); 0 to skip")
+    args = ap.parse_args()
+    if not args.mode:
+        from multimodal_b200 import _native
+        args.mode = _native.DEFAULT_MODE
+    return args
 
 
 # ------------------------------------------------------------------------------------------------
@@ -104,6 +114,21 @@ def measured_peaks():
 # ------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the float64 numpy oracle on host cores, bounded row-subsample
 # ------------------------------------------------------------------------------------------------
+def load_reference():
+    """The UNMODIFIED reference estimator from baseline/_ref (baseline/install_reference.sh), or None."""
+    ref = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref, "multimodal")):
+        return None
+    np.Inf = np.inf                    # numpy >= 2: nmf.py:206 says np.Inf
+    if ref not in sys.path:
+        sys.path.insert(0, ref)
+    try:
+        from multimodal.lib.nmf import KLdivNMF
+        return KLdivNMF
+    except Exception:
+        return None
+
+
 def cpu_sample(workload, n_total, f, k, kind, steps, warmup):
     from oracle import klnmf_oracle as O
     import scipy.sparse as sp
@@ -125,17 +150,37 @@ def cpu_sample(workload, n_total, f, k, kind, steps, warmup):
         sample = "dense n_cpu=%d of n=%d rows, f=%d, k=%d" % (n_cpu, n_total, f, k)
     np.random.seed(0)
     H = O.init_dictionary(k, f)
-    W = np.asarray(X.dot(H.T))
     fit = kind != "dense_transform"
-    times = []
-    for it in range(warmup + steps):
-        t0 = time.perf_counter()
-        O.error(X, W, H)                      # the reference computes the objective every iteration (nmf.py:214)
-        W, H = O.update(X, W, H, fit=fit)
-        dt = time.perf_counter() - t0
-        if it >= warmup:
-            times.append(dt)
-    t_step = float(np.mean(times))
+    Ref = load_reference()
+    if Ref is not None:
+        # the reference's own public API and stock code path: KLdivNMF(...).fit_transform / transform, tol = 0 as the
+        # learner passes it (learner.py:12,39); one call of `warmup` iterations, then one timed call of `steps`
+        def call(iters):
+            est = Ref(n_components=k, max_iter=iters, tol=0)
+            est._init_dictionary = H
+            est.components_ = H
+            t0 = time.perf_counter()
+            W, errs = est.fit_transform(X, _fit=fit, return_errors=True)
+            dt = time.perf_counter() - t0
+            assert len(errs) == iters, "the reference stopped early (%d of %d iterations)" % (len(errs), iters)
+            return dt
+        if warmup > 0:
+            call(warmup)
+        t_step = call(steps) / steps
+        times = [t_step] * steps
+        kind_name = "reference"
+    else:
+        W = np.asarray(X.dot(H.T))
+        times = []
+        for it in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.error(X, W, H)                      # the reference computes the objective every iteration (nmf.py:214)
+            W, H = O.update(X, W, H, fit=fit)
+            dt = time.perf_counter() - t0
+            if it >= warmup:
+                times.append(dt)
+        t_step = float(np.mean(times))
+        kind_name = "port"
     # cost is exactly linear in n at fixed f, k: extrapolate to the full workload
     value = (1.0 / t_step) * (n_cpu / float(n_total))
     cores = os.cpu_count()
@@ -146,8 +191,10 @@ def cpu_sample(workload, n_total, f, k, kind, steps, warmup):
             cores = max(nth)
     except Exception:
         pass
-    return {"value": value, "unit": "iterations/s", "cores": cores, "kind": "port",
-            "sample": sample + ", %d timed iterations, %.2f s each, extrapolated linearly in n" % (len(times), t_step)}, t_step
+    return {"value": value, "unit": "iterations/s", "cores": cores, "kind": kind_name,
+            "sample": sample + ", %d timed iterations, %.2f s each, extrapolated linearly in n" % (len(times), t_step) +
+            ("; the unmodified reference KLdivNMF from baseline/_ref, one fit_transform call (W0 = X.H0^T included)"
+             if kind_name == "reference" else "; float64 numpy port (oracle/klnmf_oracle.py): baseline/_ref is absent")}, t_step
 
 
 def run_reference(args):
@@ -162,8 +209,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": "KL-NMF iterations/sec", "value": base["value"], "unit": "iterations/s",
             "n_gpus": args.gpus, "steps": steps, "warmup": warmup, "ms_per_step": 1e3 / base["value"],
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": desc, "n": n_total, "f": f, "k": k, "note": "float64 numpy restatement of the "
-                       "reference (oracle/klnmf_oracle.py) on host cores; bounded row-subsample extrapolated in n"},
+            "config": {"workload": desc, "n": n_total, "f": f, "k": k, "note":
+                       ("the unmodified reference (baseline/_ref: multimodal.lib.nmf.KLdivNMF, float64 numpy/scipy)"
+                        if base["kind"] == "reference" else "float64 numpy restatement of the reference "
+                        "(oracle/klnmf_oracle.py)") + " on host cores; bounded row-subsample extrapolated in n"},
             "cpu_baseline": base,
             "e2e": {"value": base["value"], "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -226,8 +275,7 @@ def make_engine(_native, n_local, f, k, kind, mode, local, rank, world, H0, scra
         eng.fill_dense_synthetic(1234 + rank)
     if world > 1:
         from multimodal_b200 import distributed as D
-        _native.nccl_load()
-        eng.comm_init(D.broadcast_unique_id(), rank, world)
+        eng.comm_attach(D.rank_comm(local))
     eng.set_dictionary(H0)
     eng.init_coefficients()
     return eng
@@ -308,7 +356,7 @@ def modality_dims(f):
     return [a, b, f - a - b]
 
 
-def run_e2e(args, n_local, f, k, kind, mode, local, rank, world, dist, X_host, H0, steps):
+def run_e2e(args, n_local, f, k, kind, mode, local, rank, world, dist, X_host, H0, steps, warm=True):
     """The public API on HOST data: H2D of X, `steps` iterations, D2H of the result, all timed.
     Dense fit on one GPU goes through MultimodalLearner.train on three modality blocks (column ranges of the pinned
     array, one coefficient each: the scaled concatenation is formed on the device) and reads the dictionary back;
@@ -333,17 +381,24 @@ def run_e2e(args, n_local, f, k, kind, mode, local, rank, world, dist, X_host, H
             return est.transform(X)
         return est.fit_transform(X)
 
-    # one untimed warm-up call on a small slice: the process-wide pinned staging buffers, kernel attributes and the
-    # allocator are set up once per process, not once per call
-    if world == 1:
-        call(X_host[:min(X_host.shape[0], 65536)], 2)
+    def call_sharded(X, iters):
+        from multimodal_b200 import distributed as D
+        sh = D.ShardedNMF(k, max_iter=iters, tol=0, mode=mode, device=local)
+        sh.components_ = H0
+        return sh.fit_transform(X, X.shape[0] * world, H0=H0, fit=(kind != "dense_transform"))
+
+    # one untimed warm-up call on a small slice: the process-wide pinned staging buffers, kernel attributes, the
+    # allocator and (several ranks) the NCCL communicator are set up once per process, not once per call
+    if warm:
+        small = X_host[:min(X_host.shape[0], 65536)]
+        if world == 1:
+            call(small, 2)
+        else:
+            call_sharded(small, 2)
     barrier(dist, local)
     t0 = time.perf_counter()
     if world > 1:
-        from multimodal_b200 import distributed as D
-        sh = D.ShardedNMF(k, max_iter=steps, tol=0, mode=mode, device=local)
-        sh.components_ = H0
-        out = sh.fit_transform(X_host, n_local * world, H0=H0, fit=(kind != "dense_transform"))
+        out = call_sharded(X_host, steps)
     else:
         out = call(X_host, steps)
     barrier(dist, local)
@@ -357,44 +412,75 @@ def run_e2e(args, n_local, f, k, kind, mode, local, rank, world, dist, X_host, H
     return dt, h2d, d2h, learner_path
 
 
-def run_ours(args):
-    rank, world, local, dist = dist_setup(args)
-    os.environ.setdefault("KLNMF_PROFILE", "1")
-    from multimodal_b200 import _native
-    from multimodal_b200 import distributed as D
-    n_total, f, k, kind, desc = WORKLOADS[args.workload]
-    if args.n:
-        n_total = args.n
-        desc += " [n overridden to %d]" % n_total
-    if args.k:
-        k = args.k
-        desc += " [k overridden to %d]" % k
+def gather_phases(dist, local, ms, steps):
+    """Per-phase ms per step as {phase: [min over ranks, max over ranks]} -- rank skew (compute) and wire time
+    (all-reduce) separate in the record: a rank that waits in the all-reduce shows a short compute and a long wait."""
+    names = ["ratio", "coefficient", "numerator", "dictionary", "allreduce", "total"]
+    vals = [ms[n] / max(steps, 1) for n in names]
+    if dist is None:
+        return {n: [v, v] for n, v in zip(names, vals)}
+    import torch
+    t = torch.tensor(vals, dtype=torch.float64, device="cuda:%d" % local)
+    allv = [torch.zeros_like(t) for _ in range(dist.get_world_size())]
+    dist.all_gather(allv, t)
+    m = torch.stack(allv).cpu().numpy()
+    return {n: [float(m[:, i].min()), float(m[:, i].max())] for i, n in enumerate(names)}
+
+
+def measure_workload(args, name, mode, ctx, with_clocks, keep_engine=False, steps=None, warmup=None):
+    """One workload, one arithmetic mode: W warm-up iterations, K timed ones, device time, max over ranks."""
+    _native, D, rank, world, local, dist, peaks = ctx
+    n_total, f, k, kind, desc = WORKLOADS[name]
+    if name == args.workload:
+        if args.n:
+            n_total = args.n
+            desc += " [n overridden to %d]" % n_total
+        if args.k:
+            k = args.k
+            desc += " [k overridden to %d]" % k
+    steps = args.steps if steps is None else steps
+    warmup = args.warmup if warmup is None else warmup
     bounds = D.shard_bounds(n_total, world)
     n_local = bounds[rank + 1] - bounds[rank]
     fit = kind != "dense_transform"
-    peaks = measured_peaks()
-
     np.random.seed(0)
     H0 = np.abs(np.random.random((k, f))) + .01
     H0 = H0 / (1.e-16 + H0.sum(axis=1, keepdims=True))
     if dist is not None:
         H0 = D.broadcast_object(H0, 0)
+    x_bytes = n_local * f * (8 if mode == "fp64" else 4)
+    # leave room for X + the W ping-pong (+ lo parts) on a 192 GB part
+    scratch = (8 << 30) if x_bytes > (100 << 30) else (16 << 30)
+    eng = make_engine(_native, n_local, f, k, kind, mode, local, rank, world, H0, scratch)
+    sampler = ClockSampler(local) if with_clocks else None
+    if sampler:
+        sampler.start()
+    total_ms, ms, cnt, launches, errs = timed_run(eng, steps, warmup, fit, dist, local)
+    clocks = sampler.stop() if sampler else None
+    roof = phase_roofline(ms, cnt, n_local, f, k, kind, steps, peaks, mode)
+    roof["phase_ms_per_step_min_max_over_ranks"] = gather_phases(dist, local, ms, steps)
+    out = {"value": steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps, "steps": steps, "warmup": warmup,
+           "launches": int(launches), "roofline": roof, "clocks": clocks, "desc": desc, "n_total": n_total, "f": f, "k": k,
+           "kind": kind, "n_local": n_local, "H0": H0, "errs": errs}
+    if keep_engine:
+        out["engine"] = eng
+    else:
+        eng.close()
+    return out
 
-    def one_mode(mode, with_clocks):
-        x_bytes = n_local * f * (8 if mode == "fp64" else 4)
-        # leave room for X + the W ping-pong (+ lo parts) on a 192 GB part
-        scratch = (8 << 30) if x_bytes > (100 << 30) else (16 << 30)
-        eng = make_engine(_native, n_local, f, k, kind, mode, local, rank, world, H0, scratch)
-        sampler = ClockSampler(local) if with_clocks else None
-        if sampler:
-            sampler.start()
-        total_ms, ms, cnt, launches, errs = timed_run(eng, args.steps, args.warmup, fit, dist, local)
-        clocks = sampler.stop() if sampler else None
-        return eng, total_ms, ms, cnt, launches, errs, clocks
 
-    eng, total_ms, ms, cnt, launches, errs, clocks = one_mode(args.mode, True)
-    value = args.steps / (total_ms * 1e-3)
-    roof = phase_roofline(ms, cnt, n_local, f, k, kind, args.steps, peaks, args.mode)
+def run_ours(args):
+    rank, world, local, dist = dist_setup(args)
+    os.environ.setdefault("KLNMF_PROFILE", "1")
+    from multimodal_b200 import _native
+    from multimodal_b200 import distributed as D
+    peaks = measured_peaks()
+    ctx = (_native, D, rank, world, local, dist, peaks)
+
+    main = measure_workload(args, args.workload, args.mode, ctx, True, keep_engine=True)
+    eng = main.pop("engine")
+    n_total, f, k, kind, n_local, H0, errs = (main[x] for x in ("n_total", "f", "k", "kind", "n_local", "H0", "errs"))
+    fit = kind != "dense_transform"
 
     # ---- end-to-end leg through the public API on host buffers ---------------------------------
     e2e = None
@@ -413,6 +499,7 @@ def run_ours(args):
         if kind != "sparse_fit" and x_bytes * 2.5 > avail:
             rows = max(1024, int(avail / 2.5 / (f * 4)) // 1024 * 1024)
         rows = min(rows, n_local)
+        iters_list = [args.steps] + ([args.e2e_iters] if args.e2e_iters and args.e2e_iters != args.steps else [])
         if kind == "sparse_fit":
             # host scipy CSR (same stratified pattern as the device generator), pinned arrays; bounded row count,
             # scaled linearly in n (cost is exactly linear in the rows of a shard)
@@ -434,16 +521,8 @@ def run_ours(args):
                 ind[r0 * m:r1 * m] = (lo[None, :] + (u * width[None, :]).astype(np.int64)).astype(np.int32).ravel()
                 val[r0 * m:r1 * m] = (1.0 - rs.random_sample((r1 - r0) * m)).astype(np.float32)
             ptr[:] = np.arange(rows + 1, dtype=np.int64) * m
-            Xs = sp.csr_matrix((val, ind, ptr), shape=(rows, f), copy=False)
-            dt, h2d, d2h, _ = run_e2e(args, rows, f, k, kind, args.mode, local, rank, world, dist, Xs, H0, args.steps)
-            scale = rows / float(n_local)
-            e2e = {"value": args.steps / dt * scale, "unit": "iterations/s",
-                   "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
-                   "seconds": dt, "rows_per_rank": rows,
-                   "note": "one KLdivNMF.fit_transform call of %d iterations on a host scipy CSR matrix (pinned arrays; after an untimed warm-up call on a 65536-row slice); "
-                           "the CSR crosses PCIe once per call, so per-step bytes are the call's bytes / steps" % args.steps +
-                           ("" if rows == n_local else "; measured on %d rows and scaled linearly in n" % rows)}
-            del Xs, ind, val, ptr
+            Xh = sp.csr_matrix((val, ind, ptr), shape=(rows, f), copy=False)
+            what = "KLdivNMF.fit_transform on a host scipy CSR matrix (pinned arrays)"
         else:
             import torch
             Xh = torch.empty((rows, f), dtype=torch.float32, pin_memory=True).numpy()
@@ -455,21 +534,28 @@ def run_ours(args):
                 with _native.Engine(rows, f, k, mode=args.mode, device=local) as e2:
                     e2.fill_dense_synthetic(1234 + rank)
                     e2.get_dense(Xh)
-            dt, h2d, d2h, via_learner = run_e2e(args, rows, f, k, kind, args.mode, local, rank, world, dist, Xh, H0, args.steps)
-            scale = rows / float(n_local)
-            e2e = {"value": args.steps / dt * scale, "unit": "iterations/s",
-                   "h2d_bytes_per_step": int(h2d / args.steps), "d2h_bytes_per_step": int(d2h / args.steps),
-                   "seconds": dt, "rows_per_rank": rows,
-                   "note": ("one %s call of %d iterations on a pinned host float32 array (after an untimed "
-                            "warm-up call on a 65536-row slice); X crosses PCIe once "
-                            "per call, so per-step bytes are the call's bytes / steps" %
-                            (("MultimodalLearner.train (three modality blocks of %s columns scaled and concatenated on "
-                              "the device; the dictionary is read back)" % "+".join(str(d) for d in modality_dims(f)))
-                             if via_learner else ("KLdivNMF.transform" if not fit else "KLdivNMF.fit_transform"),
-                             args.steps)) +
-                           ("" if rows == n_local else "; host RAM too small for the full shard: measured on %d rows and "
-                            "scaled linearly in n" % rows)}
-            del Xh
+            what = None
+        scale = rows / float(n_local)
+        legs = []
+        for it_n in iters_list:
+            dt, h2d, d2h, via_learner = run_e2e(args, rows, f, k, kind, args.mode, local, rank, world, dist, Xh, H0, it_n,
+                                                warm=(it_n == iters_list[0]))
+            legs.append({"value": it_n / dt * scale, "unit": "iterations/s", "iterations": it_n,
+                         "h2d_bytes_per_step": int(h2d / it_n), "d2h_bytes_per_step": int(d2h / it_n), "seconds": dt,
+                         "rows_per_rank": rows})
+        if what is None:
+            what = ("MultimodalLearner.train (three modality blocks of %s columns scaled and concatenated on the "
+                    "device; the dictionary is read back)" % "+".join(str(d) for d in modality_dims(f))) if via_learner \
+                else ("KLdivNMF.transform" if not fit else "KLdivNMF.fit_transform") + " on a pinned host float32 array"
+        e2e = legs[0]
+        e2e["note"] = ("one %s call of %d iterations (after an untimed warm-up call on a 65536-row slice); X crosses PCIe "
+                       "once per call, so per-step bytes are the call's bytes / steps" % (what, args.steps)) + \
+            ("; %d ranks, each through distributed.ShardedNMF on its own pinned shard" % world if world > 1 else "") + \
+            ("" if rows == n_local else "; host RAM too small for the full shard: measured on %d rows and scaled "
+             "linearly in n" % rows)
+        if len(legs) > 1:
+            e2e["at_reference_iterations"] = legs[1]     # the reference's 50 iterations (experiment.py:20-25)
+        del Xh
     try:
         eng.close()
     except Exception:
@@ -479,26 +565,35 @@ def run_ours(args):
     for am in [m for m in (args.alt_mode or "").split(",") if m and m != args.mode]:
         if kind == "sparse_fit" and am != "fp64":
             continue                      # the sparse path computes in FP32 FMA in every TF32 mode
-        e2, t2, ms2, cnt2, l2, _, _ = one_mode(am, False)
-        e2.close()
-        r2 = phase_roofline(ms2, cnt2, n_local, f, k, kind, args.steps, peaks, am)
-        alt[am] = {"value": args.steps / (t2 * 1e-3), "ms_per_step": t2 / args.steps, "roofline_frac": r2["frac"],
-                   "roofline_achieved": r2["achieved"], "kernel": r2["kernel"]}
+        r = measure_workload(args, args.workload, am, ctx, False)
+        alt[am] = {"value": r["value"], "ms_per_step": r["ms_per_step"], "roofline_frac": r["roofline"]["frac"],
+                   "roofline_achieved": r["roofline"]["achieved"], "kernel": r["roofline"]["kernel"],
+                   "phase_ms_per_step": r["roofline"].get("phase_ms_per_step")}
+
+    # ---- the other two large configs, driver-timed in the same run ----------------------------------------------
+    extra = {}
+    if not args.no_extra and args.workload == "cfg5" and not args.n and not args.k:
+        for name in ("cfg3", "cfg4"):
+            r = measure_workload(args, name, args.mode, ctx, True, steps=max(args.steps, 5), warmup=max(args.warmup, 3))
+            extra[name] = {"workload": r["desc"], "value": r["value"], "unit": "iterations/s", "ms_per_step": r["ms_per_step"],
+                           "steps": r["steps"], "warmup": r["warmup"], "rows_per_rank": r["n_local"], "mode": args.mode,
+                           "gpu_launches": r["launches"], "roofline": r["roofline"], "clocks": r["clocks"]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         cpu, _ = cpu_sample(args.workload, n_total, f, k, kind, 4, 1)
 
     if rank == 0:
-        line = {"metric": "KL-NMF iterations/sec", "value": value, "unit": "iterations/s", "n_gpus": world,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": total_ms / args.steps,
+        line = {"metric": "KL-NMF iterations/sec", "value": main["value"], "unit": "iterations/s", "n_gpus": world,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": main["ms_per_step"],
                 "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": args.mode,
                 "data": "synthetic",
-                "config": {"workload": desc, "n": n_total, "f": f, "k": k, "mode": args.mode,
+                "config": {"workload": main["desc"], "n": n_total, "f": f, "k": k, "mode": args.mode,
+                           "mode_is_library_default": args.mode == _native.DEFAULT_MODE,
                            "rows_per_rank": n_local, "l2": "inputs (%.1f GB per rank) are larger than the 126 MB L2"
                            % (n_local * f * 4 / 1e9), "objective_first_last": [float(errs[0]), float(errs[-1])]},
-                "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof,
-                "cpu_baseline": cpu, "alt_modes": alt}
+                "clocks": main["clocks"], "e2e": e2e, "gpu_launches": main["launches"], "roofline": main["roofline"],
+                "cpu_baseline": cpu, "alt_modes": alt, "workloads": extra}
         print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

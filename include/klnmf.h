@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KLNMF_ABI_VERSION 1
+#define KLNMF_ABI_VERSION 2   /* bumped whenever a symbol or an argument list changes */
 
 /* error codes */
 #define KLNMF_OK            0
@@ -134,7 +134,14 @@ int klnmf_reconstruct_host(klnmf_ctx *ctx, const double *H_dest, int64_t f_dest,
 /* ---- multi-GPU: rows sharded, one all-reduce of the k x f numerator ---------- */
 int klnmf_nccl_load(const char *libnccl_path);              /* dlopen; NULL = default search   */
 int klnmf_nccl_unique_id(void *id128);                      /* 128-byte ncclUniqueId           */
-int klnmf_comm_init(klnmf_ctx *ctx, const void *id128, int rank, int world);
+int klnmf_comm_init(klnmf_ctx *ctx, const void *id128, int rank, int world);   /* communicator owned by the context */
+/* A communicator that outlives contexts: ncclCommInitRank costs 0.2-1 s, a context is created per fit / transform
+ * call (nmf.py:159-230 keeps no state between calls either).  klnmf_comm_create is collective over the `world` ranks
+ * (processes, or threads of one process with one device each); klnmf_comm_attach lends it to a context, which then
+ * all-reduces its numerator and objective partials over it and does NOT destroy it. */
+int klnmf_comm_create(void **comm, int device, const void *id128, int rank, int world);
+int klnmf_comm_attach(klnmf_ctx *ctx, void *comm, int rank, int world);
+int klnmf_comm_destroy(void *comm);
 
 /* ---- measurement support ------------------------------------------------------------------ */
 /* synthetic non-negative data generated in place on the device (counter-based hash,

@@ -14,7 +14,12 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(HERE, "csrc", "libklnmf.so")
 
 MODE_TF32, MODE_TF32X3, MODE_FP64 = 0, 1, 2
-MODES = {"tf32": MODE_TF32, "tf32x3": MODE_TF32X3, "fp64": MODE_FP64, "tf32r": 3}
+MODE_TF32R = 3
+MODES = {"tf32": MODE_TF32, "tf32x3": MODE_TF32X3, "fp64": MODE_FP64, "tf32r": MODE_TF32R}
+# The one default of the library, the tests and bench.py: one tcgen05 pass on round-to-nearest TF32 copies of W, H and
+# the centered ratio, FP32 state, cancellation-free FP64-accumulated objective.
+DEFAULT_MODE = "tf32r"
+ABI_VERSION = 2
 F32, F64 = 0, 1
 
 _c_i64 = ctypes.c_int64
@@ -56,6 +61,9 @@ PROTOTYPES = {
     "klnmf_nccl_load": (_c_int, [ctypes.c_char_p]),
     "klnmf_nccl_unique_id": (_c_int, [_c_vp]),
     "klnmf_comm_init": (_c_int, [_c_vp, _c_vp, _c_int, _c_int]),
+    "klnmf_comm_create": (_c_int, [ctypes.POINTER(_c_vp), _c_int, _c_vp, _c_int, _c_int]),
+    "klnmf_comm_attach": (_c_int, [_c_vp, _c_vp, _c_int, _c_int]),
+    "klnmf_comm_destroy": (_c_int, [_c_vp]),
     "klnmf_fill_dense_synthetic": (_c_int, [_c_vp, ctypes.c_uint64]),
     "klnmf_fill_csr_synthetic": (_c_int, [_c_vp, _c_i64, ctypes.c_uint64]),
     "klnmf_get_dense_host": (_c_int, [_c_vp, _c_vp, _c_int, _c_i64]),
@@ -77,20 +85,25 @@ class KlnmfError(RuntimeError):
 
 
 def load():
-    """dlopen libklnmf.so (building it first when the sources are newer and nvcc exists)."""
+    """dlopen libklnmf.so.  With nvcc on the machine the library is (re)built first whenever it is missing or older
+    than any source or header (build.is_stale()); without nvcc (the GPU box) the shipped binary is used as it is, and
+    the ABI version below catches a header / binary mismatch."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        from . import build as _build
+    from . import build as _build
+    if _build.have_nvcc():
         _build.build()
+    elif not os.path.exists(LIB_PATH):
+        raise KlnmfError("libklnmf.so is missing and there is no nvcc to build it: " + LIB_PATH)
     lib = ctypes.CDLL(LIB_PATH)
     for name, (res, args) in PROTOTYPES.items():
         fn = getattr(lib, name)          # AttributeError here == header/library mismatch
         fn.restype = res
         fn.argtypes = args
-    if lib.klnmf_abi_version() != 1:
-        raise KlnmfError("libklnmf ABI mismatch")
+    if lib.klnmf_abi_version() != ABI_VERSION:
+        raise KlnmfError("libklnmf ABI mismatch: the binary says %d, this binding %d -- rebuild with "
+                         "`python -m multimodal_b200.build --force`" % (lib.klnmf_abi_version(), ABI_VERSION))
     _lib = lib
     return lib
 
@@ -113,7 +126,7 @@ def _check(rc):
 
 def resolve_mode(mode):
     if mode is None:
-        mode = os.environ.get("KLNMF_MODE", "tf32x3")
+        mode = os.environ.get("KLNMF_MODE", DEFAULT_MODE)
     if isinstance(mode, str):
         if mode not in MODES:
             raise ValueError("unknown arithmetic mode %r (expected one of %s)" % (mode, sorted(MODES)))
@@ -258,6 +271,12 @@ class Engine(object):
         _check(self.lib.klnmf_get_coefficients_host(self.h, _ptr(W), self.k))
         return W
 
+    def get_coefficients_into(self, out):
+        """The coefficients written into a caller's C-contiguous float64 (n, k) array (e.g. a row block of W)."""
+        assert out.dtype == np.float64 and out.shape == (self.n, self.k) and out.flags.c_contiguous
+        _check(self.lib.klnmf_get_coefficients_host(self.h, _ptr(out), self.k))
+        return out
+
     # -- compute ----------------------------------------------------------------------------
     def run(self, max_iter, tol_abs, fit):
         """Returns (errors ndarray, n_iter) with the reference's meaning of both."""
@@ -302,6 +321,11 @@ class Engine(object):
         buf = (ctypes.c_char * 128).from_buffer_copy(bytes(uid))
         _check(self.lib.klnmf_comm_init(self.h, ctypes.cast(buf, _c_vp), int(rank), int(world)))
 
+    def comm_attach(self, comm):
+        """Lend a cached communicator (see `Comm`) to this context."""
+        _check(self.lib.klnmf_comm_attach(self.h, comm.h, comm.rank, comm.world))
+        self._keep.append(comm)
+
     # -- accounting ------------------------------------------------------------------------------
     def counters(self):
         out = (_c_i64 * 4)()
@@ -314,6 +338,25 @@ class Engine(object):
         _check(self.lib.klnmf_last_run_profile(self.h, ms, cnt))
         names = ["ratio", "coefficient", "numerator", "dictionary", "allreduce", "total"]
         return ({n: ms[i] for i, n in enumerate(names)}, {n: cnt[i] for i, n in enumerate(names[:5])})
+
+
+class Comm(object):
+    """An NCCL communicator that outlives the engines it is lent to (klnmf_comm_create): creating one is collective
+    and costs 0.2-1 s, an Engine is created per fit / transform call."""
+
+    def __init__(self, device, uid, rank, world):
+        self.lib = load()
+        nccl_load()
+        self.device, self.rank, self.world = int(device), int(rank), int(world)
+        buf = (ctypes.c_char * 128).from_buffer_copy(bytes(uid))
+        h = _c_vp()
+        _check(self.lib.klnmf_comm_create(ctypes.byref(h), self.device, ctypes.cast(buf, _c_vp), self.rank, self.world))
+        self.h = h
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.klnmf_comm_destroy(self.h)
+            self.h = None
 
 
 def nccl_unique_id(libnccl_path=None):

@@ -28,6 +28,14 @@ def _nvcc():
     raise RuntimeError("nvcc not found; libklnmf cannot be built")
 
 
+def have_nvcc():
+    try:
+        _nvcc()
+        return True
+    except RuntimeError:
+        return False
+
+
 def is_stale():
     if not os.path.exists(LIB):
         return True

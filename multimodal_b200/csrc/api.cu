@@ -595,8 +595,11 @@ int klnmf_set_dense_device(klnmf_ctx *ctx, const void *X_dev, int dtype, int64_t
   KL_TRY(kind_guard(ctx, false));
   release_data(ctx);
   const int64_t ses = dtype == KLNMF_F64 ? 8 : 4;
-  const bool borrow = ses == ctx->es && (ld * ses) % 16 == 0 && ((uintptr_t)X_dev % 16) == 0 &&
-                      ld >= round_up(ctx->f, 32);   // epilogues read whole 32-column chunks
+  // The epilogues read whole 32-column chunks of X and rely on columns f..round_up(f, 32) being ZERO (x = 0 against
+  // s = 0 gives q = 1 and an objective term of exactly 0).  A caller's buffer is therefore borrowed only when it has
+  // no such padding columns (f % 32 == 0); anything else -- a column slice of a wider matrix, an uninitialised
+  // pitch -- is copied into an owned, zero-padded buffer.
+  const bool borrow = ses == ctx->es && (ld * ses) % 16 == 0 && ((uintptr_t)X_dev % 16) == 0 && ctx->f % 32 == 0;
   if (borrow) {
     ctx->X = const_cast<void *>(X_dev);
     ctx->ldx = ld;
@@ -807,8 +810,9 @@ int klnmf_run(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, double *err
   // tol == 0 is the learner's "run exactly `iterations` updates" idiom (learner.py:12,39): the float64
   // reference then breaks only if the objective RISES.  Objective noise of the reduced-precision
   // contractions must not trigger that break, so the rise has to exceed the mode's noise floor.
-  double slack = 0.0;
-  if (tol_abs == 0.0) slack = ctx->mode == KLNMF_MODE_FP64 ? 0.0 : (ctx->mode == KLNMF_MODE_TF32X3 ? 1e-6 : (ctx->mode == KLNMF_MODE_TF32R ? 1e-5 : 1e-4));
+  // The same holds for any tol below that floor (a tiny positive tol near convergence): decide_kernel applies the
+  // slack whenever tol_abs <= slack * |previous objective|, and the plain reference test above it.
+  const double slack = ctx->mode == KLNMF_MODE_FP64 ? 0.0 : (ctx->mode == KLNMF_MODE_TF32X3 ? 1e-6 : (ctx->mode == KLNMF_MODE_TF32R ? 1e-5 : 1e-4));
   double *hp = ctx->pinned;
   hp[DS_KL] = 0.0; hp[DS_PREV] = INFINITY; hp[DS_WHSUM] = slack; hp[DS_TOL] = tol_abs;
   KL_CUDA(cudaMemcpyAsync(ctx->dscal + DS_KL, hp + DS_KL, 8, cudaMemcpyHostToDevice, ctx->stream));
@@ -1054,6 +1058,23 @@ int klnmf_comm_init(klnmf_ctx *ctx, const void *id128, int rank, int world) {
   KL_CHECK(ctx && id128, KLNMF_EINVAL, "comm_init: NULL argument");
   return nccl_comm_init(ctx, id128, rank, world);
 }
+int klnmf_comm_create(void **comm, int device, const void *id128, int rank, int world) {
+  KL_CHECK(comm && id128, KLNMF_EINVAL, "comm_create: NULL argument");
+  const int ndev = klnmf_device_count();
+  KL_CHECK(ndev > 0, KLNMF_ENODEVICE, "no CUDA device: libklnmf has no CPU path");
+  KL_CHECK(device >= 0 && device < ndev, KLNMF_EINVAL, "device %d out of range (%d devices)", device, ndev);
+  return nccl_comm_create(comm, device, id128, rank, world);
+}
+int klnmf_comm_attach(klnmf_ctx *ctx, void *comm, int rank, int world) {
+  KL_CHECK(ctx && comm && world >= 1 && rank >= 0 && rank < world, KLNMF_EINVAL, "comm_attach: bad argument");
+  nccl_comm_destroy(ctx);          // an owned communicator of an earlier klnmf_comm_init
+  ctx->comm = comm;
+  ctx->comm_owned = false;
+  ctx->rank = rank;
+  ctx->world = world;
+  return KLNMF_OK;
+}
+int klnmf_comm_destroy(void *comm) { return nccl_comm_free(comm); }
 
 // ------------------------------------------------------------------------------------------------
 int klnmf_fill_dense_synthetic(klnmf_ctx *ctx, uint64_t seed) {

@@ -61,17 +61,27 @@ struct TcParams {
 // stages: with K = 512 the ratio contraction is bound by the TMA latency of its operand ring, not by smem.
 // QIP = the ratio is written back IN PLACE into the X chunk it was computed from and leaves by TMA store from
 // there: the 32 KB of Q staging boxes become two more X chunks in flight.
-template <int BN, bool SPLIT, bool XT = false, int CG = 1, int XB = 2, bool QIP = false>
+// Wide tiles (the plain contractions of a CTA pair, one-pass modes): MS = 2 stacks two 256-row blocks on one B tile
+// (512 x 256: the numerator, M = k), BN = 512 puts two 256-column MMAs on one A block (256 x 512: the coefficient
+// contraction, N = k).  A 256 x 256 pair tile pulls 64 B/clk per SM out of L2 at the full TF32 rate -- more than the
+// fabric delivers; the wide tiles need 48 B/clk and read the ratio panel from HBM once instead of
+// once per 256 components.  Their accumulator fills the whole TMEM (512 columns), so it is single-buffered: the
+// epilogue of a tile (1-2 % of its mainloop at these contraction lengths) is not overlapped.
+template <int BN, bool SPLIT, bool XT = false, int CG = 1, int XB = 2, bool QIP = false, int MS = 1>
 struct Cfg {
-  static constexpr int A_BYTES = BM * BK * 4;
+  static constexpr int NI = BN > 256 ? 256 : BN;         // N of one tcgen05.mma
+  static constexpr int NS = BN / NI;                     // MMAs side by side on one A block
+  static constexpr int A_BYTES = MS * BM * BK * 4;
   static constexpr int B_BYTES = (BN / CG) * BK * 4;     // a CTA pair splits the B tile
   static constexpr int STAGE_BYTES = (A_BYTES + B_BYTES) * (SPLIT ? 2 : 1);
+  static constexpr int ACC_COLS = MS * BN;               // TMEM columns of one accumulator
+  static constexpr int NACC = 2 * ACC_COLS <= 512 ? 2 : 1;
   static constexpr int XBUFS = XB;
   // split-TF32 contractions (no XT form): one 32 x 32 transpose box per epilogue warp, so that X arrives and the
   // (hi, lo) ratio leaves as full 128-byte lines (epilogue_ratio_staged)
   static constexpr int XQ_BYTES = XT ? XB * XCHUNK_BYTES + (QIP ? 0 : EPI_WARPS * QWARP_BYTES) : (SPLIT ? EPI_WARPS * QWARP_BYTES : 0);
   static constexpr int STAGES = (XT ? (224 * 1024 - XQ_BYTES) : 192 * 1024) / STAGE_BYTES;
-  static constexpr int TMEM_COLS = 2 * BN;   // power of two: 256 or 512
+  static constexpr int TMEM_COLS = NACC * ACC_COLS;   // power of two: 256 or 512
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + XQ_BYTES + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -196,14 +206,23 @@ __device__ __forceinline__ void epilogue_ratio_staged(const TcParams &p, int64_t
   float q[32];
   float part = 0.f;
   if (p.accurate) {
+    f32x2_t part2 = splat2(0.f);
+    const bool store_u = p.qshift == 1.f;          // centered: u = q - 1 without the cancellation
+    const f32x2_t nshift2 = splat2(-p.qshift);
 #pragma unroll
     for (int j = 0; j < 8; j++) {
       const float4 t = *reinterpret_cast<const float4 *>(mine + ((j ^ sw) << 4));
-      part += ratio_term_cf(t.x, __uint_as_float(acc_u[4 * j]), q[4 * j]);
-      part += ratio_term_cf(t.y, __uint_as_float(acc_u[4 * j + 1]), q[4 * j + 1]);
-      part += ratio_term_cf(t.z, __uint_as_float(acc_u[4 * j + 2]), q[4 * j + 2]);
-      part += ratio_term_cf(t.w, __uint_as_float(acc_u[4 * j + 3]), q[4 * j + 3]);
+      f32x2_t qa, ua, qb, ub;
+      part2 = add2(part2, ratio_pair_cf<true>(pack2(t.x, t.y), pack2(__uint_as_float(acc_u[4 * j]), __uint_as_float(acc_u[4 * j + 1])), qa, ua));
+      part2 = add2(part2, ratio_pair_cf<true>(pack2(t.z, t.w), pack2(__uint_as_float(acc_u[4 * j + 2]), __uint_as_float(acc_u[4 * j + 3])), qb, ub));
+      qa = store_u ? ua : add2(qa, nshift2);
+      qb = store_u ? ub : add2(qb, nshift2);
+      unpack2(qa, q[4 * j], q[4 * j + 1]);
+      unpack2(qb, q[4 * j + 2], q[4 * j + 3]);
     }
+    float pa, pb;
+    unpack2(part2, pa, pb);
+    part = pa + pb;
   } else {
 #pragma unroll
     for (int j = 0; j < 8; j++) {
@@ -213,12 +232,12 @@ __device__ __forceinline__ void epilogue_ratio_staged(const TcParams &p, int64_t
       part += ratio_term<false>(t.z, __uint_as_float(acc_u[4 * j + 2]), q[4 * j + 2]);
       part += ratio_term<false>(t.w, __uint_as_float(acc_u[4 * j + 3]), q[4 * j + 3]);
     }
+#pragma unroll
+    for (int j = 0; j < 32; j++) q[j] -= p.qshift;
   }
   // rows >= M hold x = 0 against an accumulator of 0: q = 1, the term is exactly 0
   kl += (double)part;
   if (p.only_kl) return;                         // warp-uniform
-#pragma unroll
-  for (int j = 0; j < 32; j++) q[j] -= p.qshift;
   const bool two = SPLIT && p.out_lo != nullptr;
 #pragma unroll 1
   for (int part_i = 0; part_i < (two ? 2 : 1); part_i++) {
@@ -253,14 +272,17 @@ __device__ __forceinline__ void epilogue_ratio_staged(const TcParams &p, int64_t
 // XT = true: the ratio contraction (EPI_RATIO, A K-major, B MN-major) with X streamed into a
 // 128B-swizzled smem ring by TMA (warp 10) and Q leaving through smem + TMA store, so that both
 // cross HBM as full 128-byte lines instead of one 16-byte piece per thread and row.
-template <int BN, bool A_MN, bool B_MN, bool SPLIT, bool XT, int CG, int XB, bool QIP>
+template <int BN, bool A_MN, bool B_MN, bool SPLIT, bool XT, int CG, int XB, bool QIP, int MS>
 __global__ void __launch_bounds__(XT ? NUM_THREADS_XT : NUM_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmAlo,
                const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmBlo,
                const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQ, const TcParams p) {
-  using C = Cfg<BN, SPLIT, XT, CG, XB, QIP>;
+  using C = Cfg<BN, SPLIT, XT, CG, XB, QIP, MS>;
   constexpr int STAGES = C::STAGES;
   constexpr int XBUFS = C::XBUFS;
+  constexpr int NI = C::NI, NS = C::NS, NACC = C::NACC, ACC_COLS = C::ACC_COLS;
+  static_assert(!XT || (MS == 1 && NS == 1), "the TMA-staged ratio epilogue works on 256-column tiles");
+  static_assert((MS == 1 && NS == 1) || (CG == 2 && !SPLIT), "wide tiles exist for CTA pairs in the one-pass modes");
   if (p.stop != nullptr && *p.stop != 0) return;
   const uint32_t crank = CG == 2 ? cluster_ctarank() : 0u;   // position in the CTA pair; 0 issues the MMAs
 
@@ -313,7 +335,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     // that for split-TF32): every lane issues at most one box, so a stage costs one issue slot of the
     // warp instead of a dozen serial UTMALDGs on one thread.
     {
-      constexpr int NA = A_MN ? BM / 32 : 1, NB = B_MN ? BN / 32 / CG : 1;
+      // boxes per stage: MN-major operands one 32 x 32 box per 32-wide M/N group, K-major operands one box per
+      // 128-row block (MS blocks of A, NS blocks of B per CTA)
+      constexpr int NA = A_MN ? MS * BM / 32 : MS, NB = B_MN ? BN / 32 / CG : NS;
+      constexpr int GB = NI / 32 / CG;         // 32-wide groups of one MMA's B block held by this CTA
       static_assert(NA + NB <= 16, "lo operands use lanes 16..31");
       const int l = lane & 15;
       const bool is_lo = lane >= 16;
@@ -321,16 +346,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       const int grp = is_a ? l : l - NA;
       const bool active = l < NA + NB && (SPLIT || !is_lo);
       const CUtensorMap *map = is_a ? (is_lo ? &tmAlo : &tmA) : (is_lo ? &tmBlo : &tmB);
-      const uint32_t dst_off = (is_a ? 0u : (uint32_t)C::A_BYTES * (SPLIT ? 2 : 1)) +
-                               (is_lo ? (uint32_t)(is_a ? C::A_BYTES : C::B_BYTES) : 0u) + (uint32_t)grp * 4096u;
       const bool mn = is_a ? A_MN : B_MN;
+      // block (sub-tile) and 32-wide group inside it
+      const int sub = is_a ? (A_MN ? grp / (BM / 32) : grp) : (B_MN ? grp / GB : grp);
+      const int g32 = is_a ? (A_MN ? grp % (BM / 32) : 0) : (B_MN ? grp % GB : 0);
+      const uint32_t dst_off = (is_a ? 0u : (uint32_t)C::A_BYTES * (SPLIT ? 2 : 1)) +
+                               (is_lo ? (uint32_t)(is_a ? C::A_BYTES : C::B_BYTES) : 0u) +
+                               (uint32_t)sub * (uint32_t)(BM * BK * 4) + (uint32_t)g32 * 4096u;
+      static_assert((NI / CG) * BK * 4 == BM * BK * 4 || NS == 1, "a B block of a wide tile is 128 rows per CTA");
       int stage = 0; uint32_t phase = 0;
       for (int64_t u = u_first; u < total_units; u += u_step) {
         int mi, ni, si;
         decode(u, mi, ni, si);
         const int64_t kb0 = (int64_t)si * p.kb_per_split;
         const int64_t kb1 = kb0 + p.kb_per_split < p.kb_total ? kb0 + p.kb_per_split : p.kb_total;
-        const int32_t mn0 = (is_a ? (mi * CG + (int)crank) * BM : ni * BN + (int)crank * (BN / CG)) + (mn ? 32 * grp : 0);
+        const int32_t mn0 = (is_a ? ((mi * MS + sub) * CG + (int)crank) * BM : ni * BN + sub * NI + (int)crank * (NI / CG)) + 32 * g32;
         for (int64_t kb = kb0; kb < kb1; kb++) {
           mbar_wait(empty_bar(stage), phase ^ 1, p.err, 1);
           // the leader's barrier collects the bytes of both CTAs of a pair
@@ -360,7 +390,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (crank == 0) {
       // instruction descriptor: D=f32, A=B=tf32, majors, N>>3, M>>4 (M = 256 across a CTA pair)
       const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((A_MN ? 1u : 0u) << 15) | ((B_MN ? 1u : 0u) << 16) |
-                             ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
+                             ((uint32_t)(NI >> 3) << 17) | ((uint32_t)((BM * CG) >> 4) << 24);
       // K-major: +32 B inside the 128 B swizzle row; MN-major: next 8-row group (+1024 B)
       const uint32_t a_kadv = (A_MN ? p.mn_kadv : 32u) >> 4, b_kadv = (B_MN ? p.mn_kadv : 32u) >> 4;
       const uint32_t a_hi = desc_hi(A_MN ? p.mn_sbo : 1024u, A_MN ? p.mn_lt : p.k_lt);
@@ -377,7 +407,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int nkb = (int)(kb1 - kb0);
         mbar_wait(tempty_bar(acc), acc_phase ^ 1, p.err, 2);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * ACC_COLS);
         for (int kb = 0; kb < nkb; kb++) {
           mbar_wait(full_bar(stage), phase, p.err, 3);
           tc_fence_after();
@@ -396,8 +426,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 umma_tf32<CG>(d_tmem, dal, db, idesc, first);   // lo*hi
                 umma_tf32<CG>(d_tmem, da, dbl, idesc, 1u);      // hi*lo
                 umma_tf32<CG>(d_tmem, da, db, idesc, 1u);       // hi*hi
-              } else {
+              } else if (MS == 1 && NS == 1) {
                 umma_tf32<CG>(d_tmem, da, db, idesc, first);
+              } else {
+                // wide tile: MS blocks of A x NS blocks of B, each block 128 rows x 32 floats (16 KB) per CTA
+#pragma unroll
+                for (int ms = 0; ms < MS; ms++)
+#pragma unroll
+                  for (int ns = 0; ns < NS; ns++)
+                    umma_tf32<CG>(d_tmem + (uint32_t)((ms * NS + ns) * NI),
+                                  desc_pack(al + ms * ((BM * BK * 4) >> 4) + kk * a_kadv, a_hi),
+                                  desc_pack(bl + ns * ((BM * BK * 4) >> 4) + kk * b_kadv, b_hi), idesc, first);
               }
             }
             umma_commit<CG>(empty_bar(stage));            // smem slot free once these MMAs retire
@@ -406,7 +445,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
       }
     }
   } else if (XT && warp == 10) {
@@ -497,25 +536,36 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if ((!QIP || p.only_kl) && lane == 0) mbar_arrive(xempty_bar(b));
         // rows >= M and columns >= N hold x = 0, s = 0 (TMA zero fill): q = 1, the term is exactly 0
-        float part0 = 0.f, part1 = 0.f;
+        // two elements per instruction (FFMA2 / FADD2 / FMUL2, tc_ptx.cuh): the eight epilogue warps are bound by their
+        // issue rate once the objective takes its cancellation-free form
+        f32x2_t part2 = splat2(0.f);
+        const f32x2_t nshift2 = splat2(-p.qshift);
+        const bool store_u = p.accurate && p.qshift == 1.f;     // centered ratio: q - 1 = (x - s)/(s + eps), no cancellation
 #pragma unroll
         for (int j = 0; j < 32; j += 2) {
           if (p.dbg & 1) break;
-          float q0, q1;
-          if (p.accurate) {      // TF32R: the objective in its cancellation-free form (tc_ptx.cuh)
-            part0 += ratio_term_cf(x[j], __uint_as_float(v[j]), q0);
-            part1 += ratio_term_cf(x[j + 1], __uint_as_float(v[j + 1]), q1);
+          const f32x2_t x2 = pack2(x[j], x[j + 1]);
+          const f32x2_t s2 = pack2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+          f32x2_t q2, out2;
+          if (p.accurate) {      // TF32R: the objective in its cancellation-free form
+            f32x2_t u2;
+            part2 = add2(part2, ratio_pair_cf<false>(x2, s2, q2, u2));
+            out2 = store_u ? u2 : add2(q2, nshift2);
           } else {
-            part0 += ratio_term<false>(x[j], __uint_as_float(v[j]), q0);
-            part1 += ratio_term<false>(x[j + 1], __uint_as_float(v[j + 1]), q1);
+            part2 = add2(part2, ratio_pair_fast(x2, s2, q2));
+            out2 = add2(q2, nshift2);
           }
-          x[j] = q0 - p.qshift; x[j + 1] = q1 - p.qshift;
+          unpack2(out2, x[j], x[j + 1]);
         }
         if (p.round_out) {     // TF32R: the consumers multiply exactly what is stored (the tensor core would truncate)
 #pragma unroll
           for (int j = 0; j < 32; j++) x[j] = tf32_round(x[j]);
         }
-        kl_tile += part0 + part1;
+        {
+          float part0, part1;
+          unpack2(part2, part0, part1);
+          kl_tile += part0 + part1;
+        }
         if (!p.only_kl) {
           if (QIP) {
             // in place: every thread overwrites the row of X it has just read; the warp's 32 rows are one 4 KB box
@@ -576,18 +626,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
       decode(u, mi, ni, si);
       mbar_wait(tfull_bar(acc), acc_phase, p.err, 4);
       tc_fence_after();
-      const int64_t row = ((int64_t)mi * CG + crank) * BM + quarter * 32 + lane;
 #pragma unroll 1
-      for (int c = 0; c < BN / 64; c++) {
-        const int col_in_tile = half * (BN / 2) + c * 32;
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN + col_in_tile);
-        uint32_t v[32];
-        tmem_ld32(taddr, v);
-        if (SPLIT && p.epi == EPI_RATIO)
-          epilogue_ratio_staged<SPLIT>(p, row - lane, lane, (int64_t)ni * BN + col_in_tile, v, kl,
-                                       smem_gen + STAGES * C::STAGE_BYTES + e * QWARP_BYTES);
-        else
-          epilogue_chunk<SPLIT>(p, row, (int64_t)ni * BN + col_in_tile, v, kl);
+      for (int ms = 0; ms < MS; ms++) {
+        const int64_t row = (((int64_t)mi * MS + ms) * CG + crank) * BM + quarter * 32 + lane;
+#pragma unroll 1
+        for (int c = 0; c < BN / 64; c++) {
+          const int col_in_tile = half * (BN / 2) + c * 32;
+          const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * ACC_COLS + ms * BN + col_in_tile);
+          uint32_t v[32];
+          tmem_ld32(taddr, v);
+          if (SPLIT && p.epi == EPI_RATIO)
+            epilogue_ratio_staged<SPLIT>(p, row - lane, lane, (int64_t)ni * BN + col_in_tile, v, kl,
+                                         smem_gen + STAGES * C::STAGE_BYTES + e * QWARP_BYTES);
+          else
+            epilogue_chunk<SPLIT>(p, row, (int64_t)ni * BN + col_in_tile, v, kl);
+        }
       }
       tc_fence_before();
       __syncwarp();
@@ -600,7 +653,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
           else mbar_arrive_cluster(mapa(tempty_bar(acc), 0));
         }
       }
-      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      if (++acc == NACC) { acc = 0; acc_phase ^= 1; }
     }
     if (p.epi == EPI_RATIO && p.kl != nullptr) {
 #pragma unroll
@@ -624,9 +677,9 @@ struct TcState {
   int *err_dev = nullptr;
 };
 
-template <int BN, bool A_MN, bool B_MN, bool SPLIT, bool XT = false, int CG = 1, int XB = 2, bool QIP = false>
+template <int BN, bool A_MN, bool B_MN, bool SPLIT, bool XT = false, int CG = 1, int XB = 2, bool QIP = false, int MS = 1>
 int launch_cfg(klnmf_ctx *ctx, const GemmDesc &d, TcParams p) {
-  using C = Cfg<BN, SPLIT, XT, CG, XB, QIP>;
+  using C = Cfg<BN, SPLIT, XT, CG, XB, QIP, MS>;
   static_assert(C::STAGES >= 2, "pipeline too shallow");
   static_assert(C::SMEM_BYTES <= 232448, "shared memory budget exceeded");
   CUtensorMap tmA, tmAlo, tmB, tmBlo, tmX, tmQ;
@@ -638,14 +691,14 @@ int launch_cfg(klnmf_ctx *ctx, const GemmDesc &d, TcParams p) {
   p.k_lt = kswz32 ? 1u : 2u;
   if (!A_MN) KL_TRY(make_map(&tmA, d.A, d.K, d.M, d.a_sm, BM, kswz32));
   else KL_TRY(make_map(&tmA, d.A, d.M, d.K, d.a_sk, 32, true));
-  if (!B_MN) KL_TRY(make_map(&tmB, d.B, d.K, d.N, d.b_sn, BN / CG, kswz32));
+  if (!B_MN) KL_TRY(make_map(&tmB, d.B, d.K, d.N, d.b_sn, C::NI / CG, kswz32));
   else KL_TRY(make_map(&tmB, d.B, d.N, d.K, d.b_sk, 32, true));
   tmAlo = tmA;
   tmBlo = tmB;
   if (SPLIT) {
     if (!A_MN) KL_TRY(make_map(&tmAlo, d.A_lo, d.K, d.M, d.a_sm, BM, kswz32));
     else KL_TRY(make_map(&tmAlo, d.A_lo, d.M, d.K, d.a_sk, 32, true));
-    if (!B_MN) KL_TRY(make_map(&tmBlo, d.B_lo, d.K, d.N, d.b_sn, BN / CG, kswz32));
+    if (!B_MN) KL_TRY(make_map(&tmBlo, d.B_lo, d.K, d.N, d.b_sn, C::NI / CG, kswz32));
     else KL_TRY(make_map(&tmBlo, d.B_lo, d.N, d.K, d.b_sk, 32, true));
   }
   tmX = tmA;
@@ -656,7 +709,7 @@ int launch_cfg(klnmf_ctx *ctx, const GemmDesc &d, TcParams p) {
     KL_TRY(make_map(&tmX, d.aux, d.N, d.M, d.ldaux, BM, false));
     if (!p.only_kl) KL_TRY(make_map(&tmQ, d.out, d.N, d.M, d.ldo, 32, false));
   }
-  p.m_tiles = (int)ceil_div(d.M, BM * CG);      // tiles of a CTA pair span 256 rows
+  p.m_tiles = (int)ceil_div(d.M, BM * CG * MS);      // tiles of a CTA pair span 256 (MS = 2: 512) rows
   p.n_tiles = (int)ceil_div(d.N, BN);
   const int64_t slots = ctx->sm_count / CG;     // CTAs or CTA pairs resident at once
   p.kb_total = ceil_div(d.K, BK);
@@ -679,7 +732,7 @@ int launch_cfg(klnmf_ctx *ctx, const GemmDesc &d, TcParams p) {
   const int64_t units = (int64_t)p.m_tiles * p.n_tiles * p.splits;
   if (units == 0 || p.kb_total == 0) return KLNMF_OK;
   const int grid = (int)(units < slots ? units : slots) * CG;
-  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, SPLIT, XT, CG, XB, QIP>;
+  auto kern = tc_gemm_kernel<BN, A_MN, B_MN, SPLIT, XT, CG, XB, QIP, MS>;
   static bool attr_done = false;
   if (!attr_done) {
     KL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
@@ -766,6 +819,17 @@ int tc_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d) {
   const char *force = getenv("KLNMF_TC_BN");
   bool narrow = d.N <= 128;
   if (force) narrow = atoi(force) == 128;
+  // wide tiles of the one-pass modes (Cfg): 256 x 512 when the contraction has more than 256 output columns and both
+  // operands are K-major (coefficient contraction, W0 = X.H0^T: N = k), 512 x 256 for the numerator (M = k > 256, both
+  // operands MN-major).  KLNMF_TC_WIDE=0 keeps the 256 x 256 pair tiles for comparison.
+  static const bool wide = !(getenv("KLNMF_TC_WIDE") && atoi(getenv("KLNMF_TC_WIDE")) == 0) &&
+                           !(getenv("KLNMF_TC_CG") && atoi(getenv("KLNMF_TC_CG")) == 1);
+  if (wide && !split && !force) {
+    if (!a_mn && !b_mn && d.N > 256 && (epi == EPI_MULW || epi == EPI_STORE))
+      return launch_cfg<512, false, false, false, false, 2>(ctx, d, p);
+    if (a_mn && b_mn && d.M > 256 && d.N > 128 && epi == EPI_ACC)
+      return launch_cfg<256, true, true, false, false, 2, 2, false, 2>(ctx, d, p);
+  }
   if (!a_mn && !b_mn) return launch_major<false, false>(ctx, d, p, split, narrow);
   // the ratio contraction of the loop: X and Q go through shared memory by TMA
   if (!a_mn && b_mn && epi == EPI_RATIO && !split && !narrow && !getenv("KLNMF_TC_NO_XT")) {

@@ -115,8 +115,11 @@ __global__ void decide_kernel(double *dred, double *dscal, int *flags, double *e
   }
   if (flags[FL_STOP] == 0) {
     const double prev = dscal[DS_PREV];
-    // DS_WHSUM holds the relative noise slack that applies when tol == 0 (see klnmf_run)
-    const double tol = dscal[DS_TOL] - dscal[DS_WHSUM] * (isfinite(prev) ? fabs(prev) : 0.0);
+    // DS_WHSUM holds the relative objective noise of the arithmetic mode (see klnmf_run): a tolerance at or below that
+    // noise (tol == 0 above all) asks "did the objective rise", and a rise has to exceed the noise to count
+    const double noise = dscal[DS_WHSUM] * (isfinite(prev) ? fabs(prev) : 0.0);
+    double tol = dscal[DS_TOL];
+    if (tol <= noise) tol -= noise;
     if (prev - e < tol) {
       flags[FL_STOP] = 1;
     } else {

@@ -37,7 +37,12 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.
+// Bounded wait: a protocol bug must surface as an error, never as a hung GPU.  The bound only has to be far above any
+// legitimate wait (microseconds); build with -DKLNMF_WATCHDOG_NS=... to change it (e.g. on a time-sliced GPU, where a
+// preempted CTA can wait for seconds), -DKLNMF_WATCHDOG_NS=0 to wait forever.
+#ifndef KLNMF_WATCHDOG_NS
+#define KLNMF_WATCHDOG_NS 10000000000ull   // 10 s
+#endif
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *err, int code) {
   if (mbar_try_wait(bar, parity)) return;
   uint64_t t0;
@@ -47,7 +52,7 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int *er
       if (mbar_try_wait(bar, parity)) return;
     uint64_t t1;
     asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
-    if (t1 - t0 > 4000000000ull) {   // 4 s
+    if (KLNMF_WATCHDOG_NS != 0 && t1 - t0 > KLNMF_WATCHDOG_NS) {
       if (err) atomicExch(err, code);
       __threadfence_system();
       asm volatile("trap;");
@@ -257,6 +262,84 @@ __device__ __forceinline__ float ratio_term_cf(float x, float s, float &q) {
   const float p_large = fmaf(0.69314718055994531f, lg2_approx(fmaxf(q, 1e-37f)), -u);
   const float P = fabsf(u) < 0.25f ? p_small : p_large;
   return fmaf(x, P, xs * (xs - (float)KL_EPS) * r);
+}
+// ---- the same two forms on PAIRS of elements with the packed FP32 instructions of sm_100 (fma/add/mul.f32x2 ->
+// FFMA2 / FADD2 / FMUL2: two FP32 operations per issue slot).  The ratio epilogue is bound by the issue rate of its
+// eight warps, not by the tensor pipe, once the objective takes its cancellation-free form (~31 instructions per
+// element in scalar code, ~16 here); the MUFU operations stay scalar. ----
+typedef unsigned long long f32x2_t;
+__device__ __forceinline__ f32x2_t pack2(float a, float b) {
+  f32x2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2_t v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f32x2_t fma2(f32x2_t a, f32x2_t b, f32x2_t c) {
+  f32x2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f32x2_t add2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t mul2(f32x2_t a, f32x2_t b) {
+  f32x2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2_t splat2(float a) { return pack2(a, a); }
+// two elements of ratio_term<false>: q = (x+eps) * rcp(s+eps); returns the packed terms x ln2 lg2(q) + (s - x)
+__device__ __forceinline__ f32x2_t ratio_pair_fast(f32x2_t x, f32x2_t s, f32x2_t &q) {
+  const f32x2_t eps2 = splat2((float)KL_EPS);
+  const f32x2_t d = add2(s, eps2);
+  float d0, d1;
+  unpack2(d, d0, d1);
+  const f32x2_t r = pack2(rcp_approx(d0), rcp_approx(d1));
+  q = mul2(add2(x, eps2), r);
+  float q0, q1;
+  unpack2(q, q0, q1);
+  const f32x2_t l = pack2(lg2_approx(q0), lg2_approx(q1));
+  const f32x2_t smx = fma2(x, splat2(-1.f), s);
+  return fma2(mul2(x, splat2(0.69314718055994531f)), l, smx);
+}
+// two elements of ratio_term_cf; u = q - 1 is returned as well (the centered ratio, free of the cancellation of q - 1).
+// NEWTON: one Newton step on the reciprocal (FP32-grade split mode); without it the MUFU's 1 ulp is kept (TF32R, whose
+// stored ratio is rounded to TF32 anyway).
+template <bool NEWTON>
+__device__ __forceinline__ f32x2_t ratio_pair_cf(f32x2_t x, f32x2_t s, f32x2_t &q, f32x2_t &u) {
+  const f32x2_t eps2 = splat2((float)KL_EPS);
+  const f32x2_t d = add2(s, eps2);
+  float d0, d1;
+  unpack2(d, d0, d1);
+  f32x2_t r = pack2(rcp_approx(d0), rcp_approx(d1));
+  if (NEWTON) r = fma2(fma2(mul2(d, splat2(-1.f)), r, splat2(1.f)), r, r);
+  q = mul2(add2(x, eps2), r);
+  const f32x2_t xs = fma2(s, splat2(-1.f), x);
+  u = mul2(xs, r);
+  f32x2_t R = splat2(-0.1f);
+  R = fma2(R, u, splat2(1.f / 9.f));
+  R = fma2(R, u, splat2(-0.125f));
+  R = fma2(R, u, splat2(1.f / 7.f));
+  R = fma2(R, u, splat2(-1.f / 6.f));
+  R = fma2(R, u, splat2(0.2f));
+  R = fma2(R, u, splat2(-0.25f));
+  R = fma2(R, u, splat2(1.f / 3.f));
+  R = fma2(R, u, splat2(-0.5f));
+  const f32x2_t p_small = mul2(mul2(u, u), R);
+  float q0, q1, u0, u1, ps0, ps1;
+  unpack2(q, q0, q1);
+  unpack2(u, u0, u1);
+  unpack2(p_small, ps0, ps1);
+  // q > 0 in exact arithmetic; the clamp keeps lg2 finite where x = 0 and (x+eps) * r underflows
+  const f32x2_t l = pack2(lg2_approx(fmaxf(q0, 1e-37f)), lg2_approx(fmaxf(q1, 1e-37f)));
+  const f32x2_t p_large = fma2(l, splat2(0.69314718055994531f), mul2(u, splat2(-1.f)));
+  float pl0, pl1;
+  unpack2(p_large, pl0, pl1);
+  const f32x2_t P = pack2(fabsf(u0) < 0.25f ? ps0 : pl0, fabsf(u1) < 0.25f ? ps1 : pl1);
+  const f32x2_t tail = mul2(mul2(xs, add2(xs, splat2(-(float)KL_EPS))), r);
+  return fma2(x, P, tail);
 }
 __device__ __forceinline__ float tf32_round(float v) {
   uint32_t u;

@@ -1,11 +1,20 @@
 """Sample-sharded KL-NMF over the GPUs of one box.
 
-One process per GPU.  Rows of X and W are split into contiguous blocks; the k x f
-dictionary is replicated.  Per fit iteration the library all-reduces (NCCL, on the
-context's stream) the k x f numerator W'^T.Q and the objective partials; transform needs no
-communication at all.  torch.distributed is only the bootstrap that carries the
-128-byte NCCL unique id and the host-drawn H0 to every rank.
+Rows of X and W are split into contiguous blocks, one per GPU; the k x f dictionary is replicated.  Per fit iteration
+the library all-reduces (NCCL, over NVLink) the k x f numerator W'^T.Q and the objective partials; transform needs no
+communication at all.  Two ways to drive the shards:
+
+* `DeviceGroup` -- ONE process, one host thread and one engine per GPU.  This is what `KLdivNMF(device=[0, 1, ...])`
+  and `MultimodalLearner(..., device=[...])` use, so `learner.train` (learner.py:31-41) shards over the box without
+  `torchrun`; every thread uploads its own row block, so the host->device copies run in parallel over the GPUs' own
+  PCIe links.
+* `ShardedNMF` -- one process per GPU under `torchrun`; torch.distributed is only the bootstrap that carries the
+  128-byte NCCL unique id and the host-drawn H0 to every rank.
+
+NCCL communicators are cached per process (`ncclCommInitRank` costs 0.2-1 s; an engine is created per call).
 """
+import threading
+
 import numpy as np
 
 from . import _native
@@ -51,8 +60,122 @@ def draw_shared_dictionary(k, f):
     return broadcast_object(H0, 0)
 
 
+# ---- communicator caches -------------------------------------------------------------------------------------
+_RANK_COMM = {}      # torchrun: (device, rank, world) -> _native.Comm
+_GROUP_COMMS = {}    # one process: tuple(devices) -> [_native.Comm per device]
+_CACHE_LOCK = threading.Lock()
+
+
+def rank_comm(device):
+    """The communicator of this torchrun rank, created (collectively) on first use and kept for the process."""
+    dist = _dist()
+    key = (int(device), dist.get_rank(), dist.get_world_size())
+    comm = _RANK_COMM.get(key)
+    if comm is None:
+        _native.nccl_load()
+        comm = _native.Comm(device, broadcast_unique_id(), key[1], key[2])
+        _RANK_COMM[key] = comm
+    return comm
+
+
+def _in_threads(fns):
+    """Run the callables concurrently (one per device); re-raise the first exception."""
+    errs = [None] * len(fns)
+    outs = [None] * len(fns)
+
+    def wrap(i):
+        try:
+            outs[i] = fns[i]()
+        except BaseException as e:          # noqa: B902 -- re-raised below
+            errs[i] = e
+    ts = [threading.Thread(target=wrap, args=(i,)) for i in range(len(fns))]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    for e in errs:
+        if e is not None:
+            raise e
+    return outs
+
+
+def group_comms(devices):
+    """One communicator per device of this process (ncclCommInitRank from one thread per device), cached."""
+    key = tuple(int(d) for d in devices)
+    with _CACHE_LOCK:
+        comms = _GROUP_COMMS.get(key)
+        if comms is None:
+            uid = _native.nccl_unique_id()
+            comms = _in_threads([(lambda r=r, d=d: _native.Comm(d, uid, r, len(key))) for r, d in enumerate(key)])
+            _GROUP_COMMS[key] = comms
+    return comms
+
+
+def _rows(X, r0, r1):
+    """Row block of a dense array (a view), a CSR matrix (a copy of the block) or a StackedBlocks stack."""
+    from .lib.array_utils import StackedBlocks
+    if isinstance(X, StackedBlocks):
+        return StackedBlocks([b[r0:r1] for b in X.blocks], X.coefs)
+    return X[r0:r1]
+
+
+class DeviceGroup(object):
+    """fit / transform over several GPUs of one box from ONE process: rows sharded, one engine and one host thread
+    per GPU (ctypes releases the GIL inside the library), NCCL all-reduce of the numerator between the engines."""
+
+    def __init__(self, devices, mode=None):
+        self.devices = [int(d) for d in devices]
+        assert len(self.devices) >= 1 and len(set(self.devices)) == len(self.devices), devices
+        self.mode = mode
+
+    def run(self, X, k, H_init, H_loop, max_iter, tol_abs, fit, want_coefficients=True, set_data=None):
+        """The body of KLdivNMF.fit_transform (nmf.py:193-222) on row shards.  Returns
+        (W or None, H after the run, errors, n_iter, (negative, non_finite))."""
+        n = X.shape[0]
+        world = len(self.devices)
+        bounds = shard_bounds(n, world)
+        comms = group_comms(self.devices) if world > 1 else [None]
+        W = np.empty((n, k), dtype=np.float64) if want_coefficients else None
+        flags = [None] * world
+        results = [None] * world
+        gate = threading.Barrier(world)
+
+        def shard(r):
+            r0, r1 = bounds[r], bounds[r + 1]
+            eng = _native.Engine(r1 - r0, X.shape[1], k, mode=self.mode, device=self.devices[r])
+            try:
+                set_data(eng, _rows(X, r0, r1))
+                flags[r] = eng.check_input()
+                gate.wait()                                    # every shard validated before anybody iterates
+                if any(fl[0] or fl[1] for fl in flags):
+                    return
+                if comms[r] is not None:
+                    eng.comm_attach(comms[r])
+                eng.set_dictionary(H_init)
+                eng.init_coefficients()                        # W0 = X.H0^T   (nmf.py:156), rows are independent
+                if H_loop is not None:
+                    eng.set_dictionary(H_loop)
+                errors, n_iter = eng.run(max_iter, tol_abs, fit)
+                if W is not None and r1 > r0:
+                    eng.get_coefficients_into(W[r0:r1])
+                results[r] = (errors, n_iter, eng.get_dictionary() if (fit and r == 0) else None)
+            except BaseException:
+                gate.abort()
+                raise
+            finally:
+                eng.close()
+
+        _in_threads([(lambda r=r: shard(r)) for r in range(world)])
+        neg = any(fl[0] for fl in flags)
+        bad = any(fl[1] for fl in flags)
+        if neg or bad:
+            return None, None, None, None, (neg, bad)
+        errors, n_iter, H = results[0]
+        return W, H, errors, n_iter, (False, False)
+
+
 class ShardedNMF(object):
-    """fit / transform of a row shard; every rank calls the same methods in the same order."""
+    """fit / transform of a row shard under torchrun; every rank calls the same methods in the same order."""
 
     def __init__(self, n_components, max_iter=200, tol=1e-6, mode=None, device=0):
         self.n_components, self.max_iter, self.tol = n_components, max_iter, tol
@@ -69,8 +192,7 @@ class ShardedNMF(object):
         else:
             eng.set_dense(X_local)
         if dist.get_world_size() > 1:
-            _native.nccl_load()
-            eng.comm_init(broadcast_unique_id(), dist.get_rank(), dist.get_world_size())
+            eng.comm_attach(rank_comm(self.device))
         return eng
 
     def fit_transform(self, X_local, n_global, H0=None, fit=True, return_errors=False):

@@ -37,7 +37,7 @@ class MultimodalLearner(object):
         self.sp_coef = sp_coef
         self.dico = None                 # k x sum(dim) once trained (or assigned by the caller)
         self.mode = mode                 # arithmetic mode of libklnmf (not in the reference)
-        self.device = device
+        self.device = device             # CUDA ordinal, or a list of ordinals: the samples are sharded over them
 
     # ---- layout ---------------------------------------------------------------------------------------------
     def get_index(self, modality):
@@ -93,8 +93,9 @@ class MultimodalLearner(object):
 
     def _dot(self, internal, dico):
         """internal.dot(dico) on the device (learner.py:81, 84)."""
+        device = self.device[0] if isinstance(self.device, (list, tuple)) else self.device
         return _native.contract(np.asarray(internal, dtype=np.float64), np.asarray(dico, dtype=np.float64),
-                                self.mode, device=self.device)
+                                self.mode, device=device)
 
     def reconstruct_modalities(self, dest_mods, internal):
         return self._dot(internal, self.get_stacked_dicos(dest_mods))

@@ -7,8 +7,10 @@ numpy fallback, and importing this module on a machine without the CUDA library 
 B200 raises as soon as an estimator method needs the device.
 
 Extra, keyword-only constructor arguments (not in the reference): `mode` in
-{"tf32x3" (default), "tf32", "fp64"} or the KLNMF_MODE environment variable, and
-`device` (CUDA ordinal).
+{"tf32r" (default), "tf32x3", "tf32", "fp64"} or the KLNMF_MODE environment variable
+(see _native.MODES / DEFAULT_MODE and DESIGN.md section 2 for what each computes and its
+stated tolerance), and `device` (CUDA ordinal, or a list of ordinals to shard the samples
+over several GPUs of the box).
 """
 import sys
 
@@ -55,39 +57,63 @@ def _canonical_csr(X):
     return X
 
 
+def _first_device(device):
+    """`device` is a CUDA ordinal or a list of ordinals (sample sharding, distributed.DeviceGroup)."""
+    if isinstance(device, (list, tuple)):
+        return int(device[0])
+    return int(device)
+
+
+def _load(eng, X):
+    """Hand X (dense array, CSR matrix or a stack of dense modality blocks) to an engine."""
+    if isinstance(X, StackedBlocks):
+        eng.set_dense_blocks(X.blocks, X.coefs)
+    elif sp.issparse(X):
+        eng.set_csr(X)
+    else:
+        eng.set_dense(X)
+
+
 def _engine_for(X, k, mode, device):
     """Context holding X (validated on the device with the reference's messages)."""
     n, f = X.shape
-    eng = _native.Engine(n, f, k, mode=mode, device=device)
+    eng = _native.Engine(n, f, k, mode=mode, device=_first_device(device))
     try:
-        if isinstance(X, StackedBlocks):
-            eng.set_dense_blocks(X.blocks, X.coefs)
-        elif sp.issparse(X):
-            eng.set_csr(X)
-        else:
-            eng.set_dense(X)
+        _load(eng, X)
     except Exception:
         eng.close()
         raise
     return eng
 
 
-def _validated(X, whom, mode, device, k):
-    """atleast2d_or_csr + check_non_negative (nmf.py:193-194), with the O(n f) scans run
-    on the device copy.  Returns (X, engine)."""
+def _host_prepare(X):
+    """atleast2d_or_csr (nmf.py:193) and the dtype the device copy is made from; no O(n f) scan on the host."""
     if not isinstance(X, StackedBlocks):
         X = atleast2d_or_csr(X, check_finite=False)
         if sp.issparse(X):
             X = _canonical_csr(X)
         elif X.dtype not in (np.float32, np.float64):
             X = X.astype(np.float64)
+    return X
+
+
+def _raise_invalid(neg, bad, whom):
+    """The reference's messages (sklearn_utils.py:59-69, nmf.py:23-26); non-finite wins, as atleast2d_or_csr runs first."""
+    if bad:
+        raise ValueError("array contains NaN or infinity")
+    if neg:
+        raise ValueError("Negative values in data passed to %s" % whom)
+
+
+def _validated(X, whom, mode, device, k):
+    """atleast2d_or_csr + check_non_negative (nmf.py:193-194), with the O(n f) scans run
+    on the device copy.  Returns (X, engine)."""
+    X = _host_prepare(X)
     eng = _engine_for(X, k, mode, device)
     neg, bad = eng.check_input()
     if bad or neg:
         eng.close()
-        if bad:
-            raise ValueError("array contains NaN or infinity")
-        raise ValueError("Negative values in data passed to %s" % whom)
+        _raise_invalid(neg, bad, whom)
     return X, eng
 
 
@@ -160,6 +186,8 @@ class KLdivNMF(object):
         n_samples, n_features = Xv.shape
         if not self.n_components:
             self.n_components = n_features
+        if isinstance(self.device, (list, tuple)) and len(self.device) > 1:
+            return self._fit_transform_sharded(Xv, _fit, return_errors)
         Xv, eng = _validated(Xv, "NMF.fit", self.mode, self.device, self.n_components)
         try:
             H_init = self._draw_dictionary(n_features)
@@ -183,6 +211,36 @@ class KLdivNMF(object):
                 self.components_ = eng.get_dictionary()
         finally:
             eng.close()
+        if n_iter == self.max_iter and tol > 0:
+            sys.stderr.write("Warning: Iteration limit reached during fit\n")
+        if return_errors:
+            return W, [e for e in errors]
+        return W
+
+    def _fit_transform_sharded(self, Xv, _fit, return_errors):
+        """The same call with the samples sharded over `self.device` (a list of CUDA ordinals): one engine and one
+        host thread per GPU, the k x f numerator and the objective partials all-reduced over NCCL every fit
+        iteration; identical state transitions and return values as the single-device path above."""
+        from ..distributed import DeviceGroup
+        n_samples, n_features = Xv.shape
+        Xv = _host_prepare(Xv)
+        H_init = self._draw_dictionary(n_features)
+        H_loop = None
+        if _fit:
+            self.components_ = H_init
+        elif self.components_ is not H_init:
+            H_loop = np.asarray(self.components_)
+            assert H_loop.shape == (self.n_components, n_features)
+        if self.max_iter < 1:
+            raise NameError("name 'n_iter' is not defined (max_iter < 1)")
+        tol = self.tol * n_samples * n_features
+        group = DeviceGroup(self.device, mode=self.mode)
+        W, H, errors, n_iter, (neg, bad) = group.run(
+            Xv, self.n_components, H_init, H_loop, self.max_iter, tol, _fit,
+            want_coefficients=not getattr(self, "_discard_coefficients", False), set_data=_load)
+        _raise_invalid(neg, bad, "NMF.fit")
+        if _fit:
+            self.components_ = H
         if n_iter == self.max_iter and tol > 0:
             sys.stderr.write("Warning: Iteration limit reached during fit\n")
         if return_errors:

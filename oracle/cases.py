@@ -82,6 +82,20 @@ def cfg2_inputs(n=1000, f_sound=110000, density=0.01):
     return motion, sound, coefs
 
 
+def rise_case():
+    """A fit whose objective RISES between the first and the second evaluation in float64 (found by a seeded search,
+    seed 51): zero-heavy 9 x 4 data and an initial dictionary with a huge dynamic range, k = 2.  The reference's
+    update (new W with the stale ratio, nmf.py:349) is not monotone by construction; with tol = 0 it breaks here
+    (nmf.py:215) with one recorded error.  Returns (X, H0)."""
+    rs = np.random.RandomState(51)
+    n = rs.randint(3, 10)
+    f = rs.randint(3, 10)
+    k = rs.randint(1, min(n, f))
+    X = (rs.random_sample((n, f)) < 0.4) * rs.random_sample((n, f)) * 10
+    H = np.exp(rs.normal(0, 3, size=(k, f)))
+    return X, H / (1e-16 + H.sum(axis=1, keepdims=True))
+
+
 def rel_fro(a, b):
     """Norm-relative error used by every parity test (tiny entries
     differ wildly between paths, so never compare element-relative)."""

@@ -97,6 +97,13 @@ def main():
     np.savez_compressed(os.path.join(OUT, "early_stop.npz"), W=W, H=H, errors=e)
     print("early_stop n_errors", len(e))
 
+    # --- tol = 0 and an objective that rises: the reference breaks at the second evaluation (nmf.py:215) ---
+    X, H0 = cases.rise_case()
+    W, H, e = run_fit(X, H0.shape[0], 50, 0, tol=0, H0=H0)
+    assert len(e) == 1, len(e)
+    np.savez_compressed(os.path.join(OUT, "rise_tol0.npz"), W=W, H=H, errors=e)
+    print("rise_tol0 n_errors", len(e), "shape", X.shape, "k", H0.shape[0])
+
     # --- learner: two modalities (dense motion + CSR sound), cfg2 in miniature ---
     mot, snd, coefs = cases.learner_small()
     lr = MultimodalLearner(['motion', 'sound'], [mot.shape[1], snd.shape[1]], coefs, 8)

@@ -1,3 +1,4 @@
+import json
 import os
 import sys
 
@@ -12,6 +13,29 @@ GOLDEN = os.path.join(ROOT, "tests", "golden")
 
 def pytest_configure(config):
     config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+    config.addinivalue_line("markers", "multigpu: needs at least two CUDA devices")
+
+
+def _device_count():
+    try:
+        from multimodal_b200 import _native
+        return _native.device_count()
+    except Exception:
+        return 0
+
+
+def pytest_collection_modifyitems(config, items):
+    """A plain `pytest tests` on a machine without a B200 skips the GPU tests instead of failing them; an explicit
+    `-m gpu` selection still runs (and fails loudly) there, so the driver's GPU tier can never pass on skips."""
+    if not any("gpu" in it.keywords or "multigpu" in it.keywords for it in items):
+        return
+    ndev = _device_count()
+    explicit = "gpu" in (config.getoption("-m") or "")
+    for it in items:
+        if "multigpu" in it.keywords and ndev < 2:
+            it.add_marker(pytest.mark.skip(reason="needs two CUDA devices (found %d)" % ndev))
+        elif "gpu" in it.keywords and ndev == 0 and not explicit:
+            it.add_marker(pytest.mark.skip(reason="no CUDA device: libklnmf has no CPU path"))
 
 
 @pytest.fixture(scope="session")
@@ -21,3 +45,32 @@ def golden():
     def load(name):
         return np.load(os.path.join(GOLDEN, name + ".npz"))
     return load
+
+
+# ---- measured-vs-stated record of the parity tests ----------------------------------------------------------
+# Every parity assertion goes through `within(label, measured, tolerance)`: it asserts and records, and the session
+# writes gpurun_out/parity_measured.json (worst measured value per label) -- the evidence the stated tolerances in
+# DESIGN.md section 2 are derived from (stated <= ~3 x measured worst case).
+_RECORD = {}
+
+
+@pytest.fixture
+def within(request):
+    def check(label, measured, tol):
+        measured = float(measured)
+        key = "%s::%s" % (request.node.name, label)
+        _RECORD[key] = {"measured": measured, "tol": float(tol)}
+        assert measured < tol, "%s: measured %.3e, stated tolerance %.1e" % (key, measured, tol)
+    return check
+
+
+def pytest_sessionfinish(session, exitstatus):
+    if not _RECORD:
+        return
+    out = os.path.join(ROOT, "gpurun_out")
+    try:
+        os.makedirs(out, exist_ok=True)
+        with open(os.path.join(out, "parity_measured.json"), "w") as fh:
+            json.dump(_RECORD, fh, indent=1, sort_keys=True)
+    except OSError:
+        pass

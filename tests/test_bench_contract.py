@@ -1,5 +1,6 @@
-"""CPU: the JSON contract of the reference arm of bench.py (`--impl reference`), which times the float64 oracle port on
-the host cores and needs no GPU: the keys the driver reads, the tier's `cpu_baseline` and `e2e` objects."""
+"""CPU: the JSON contract of the reference arm of bench.py (`--impl reference`), which times the unmodified reference
+(baseline/_ref, installed by baseline/install_reference.sh) -- or, when that directory is absent, the float64 oracle
+port -- on the host cores and needs no GPU: the keys the driver reads, the tier's `cpu_baseline` and `e2e` objects."""
 import json
 import os
 import subprocess
@@ -21,6 +22,8 @@ def test_reference_arm_prints_one_contract_line():
     assert d["vs_baseline"] is None and d["dtype"] == "f64" and d["data"] == "synthetic"
     assert "cfg3" in d["config"]["workload"] and d["config"]["k"] == 256
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "extrapolated" in cb["sample"]
+    installed = os.path.isdir(os.path.join(ROOT, "baseline", "_ref", "multimodal"))
+    assert cb["kind"] == ("reference" if installed else "port")
+    assert cb["cores"] >= 1 and cb["value"] == d["value"] and "extrapolated" in cb["sample"]
     assert d["e2e"] == {"value": d["value"], "unit": d["unit"], "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert d["gpu_launches"] == 0

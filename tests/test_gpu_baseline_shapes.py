@@ -1,0 +1,105 @@
+"""-m gpu: SURVEY 8d's parity protocol at the FEATURE / COMPONENT shapes of BASELINE.json's large configs, against
+the float64 oracle (not against the engine's own FP64 mode): identical host X and H0, a row subsample that the
+oracle finishes in seconds, 10 iterations, norm-relative error on W and H and relative error on every recorded
+objective, in every arithmetic mode.
+
+    cfg3  transform   n = 8192, f = 4096,   k = 256   (BASELINE.json configs[2]; nmf.py:275-291)
+    cfg5  dense fit   n = 8192, f = 8192,   k = 512   (configs[4]; nmf.py:159-230)
+    cfg4  CSR fit     n = 2048, f = 50 000, k = 256, density 0.005   (configs[3]; nmf.py:52-70, 301-308, 332-349)
+
+The oracle runs once per shape (module cache) and every mode is compared with it.
+"""
+import functools
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from multimodal_b200.lib.nmf import KLdivNMF
+from oracle import cases, klnmf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+MODES = ["fp64", "tf32x3", "tf32r", "tf32"]
+# about 3 x the worst measured value (profiles/r2_parity_measured.json)
+TOL_WH = {"fp64": 1e-9, "tf32x3": 2e-5, "tf32r": 1.5e-4, "tf32": 3e-4}
+TOL_KL = {"fp64": 1e-9, "tf32x3": 1.5e-4, "tf32r": 1.5e-4, "tf32": 4e-3}
+ITERS = 10
+
+
+def maxrel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.abs(b)))
+
+
+@functools.lru_cache(maxsize=None)
+def cfg3_case():
+    rs = np.random.RandomState(303)
+    n, f, k = 8192, 4096, 256
+    X = rs.random_sample((n, f)).astype(np.float32)            # uniform(0, 1), float32 like the bench's shards
+    np.random.seed(31)
+    H = O.init_dictionary(k, f)                                # row-normalised uniform + .01
+    W, _, errs, _ = O.fit_transform(X.astype(np.float64), k=k, max_iter=ITERS, tol=0, H0=H, fit=False)
+    return X, H, W, np.asarray(errs)
+
+
+@functools.lru_cache(maxsize=None)
+def cfg5_case():
+    rs = np.random.RandomState(505)
+    n, f, k = 8192, 8192, 512
+    X = rs.random_sample((n, f)).astype(np.float32)
+    np.random.seed(51)
+    H0 = O.init_dictionary(k, f)
+    W, H, errs, _ = O.fit_transform(X.astype(np.float64), k=k, max_iter=ITERS, tol=0, H0=H0)
+    return X, H0, W, H, np.asarray(errs)
+
+
+@functools.lru_cache(maxsize=None)
+def cfg4_case():
+    rs = np.random.RandomState(404)
+    n, f, k = 2048, 50000, 256
+    X = sp.random(n, f, density=0.005, random_state=rs, format="csr", dtype=np.float64)
+    X.data = 1.0 - X.data                                      # uniform (0, 1]
+    X.sort_indices()
+    np.random.seed(41)
+    H0 = O.init_dictionary(k, f)
+    W, H, errs, _ = O.fit_transform(X.copy(), k=k, max_iter=ITERS, tol=0, H0=H0)
+    return X, H0, W, H, np.asarray(errs)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_cfg3_shape_transform_vs_oracle(within, mode):
+    X, H, W_ref, errs_ref = cfg3_case()
+    est = KLdivNMF(n_components=H.shape[0], max_iter=ITERS, tol=0, mode=mode)
+    est.components_ = H
+    est._init_dictionary = H
+    W, errs = est.fit_transform(X, _fit=False, return_errors=True)
+    assert len(errs) == ITERS and est.components_ is H
+    within("W", cases.rel_fro(W, W_ref), TOL_WH[mode])
+    within("objective", maxrel(errs, errs_ref), TOL_KL[mode])
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_cfg5_shape_fit_vs_oracle(within, mode):
+    X, H0, W_ref, H_ref, errs_ref = cfg5_case()
+    est = KLdivNMF(n_components=H0.shape[0], max_iter=ITERS, tol=0, mode=mode)
+    est._init_dictionary = H0
+    W, errs = est.fit_transform(X, return_errors=True)
+    assert len(errs) == ITERS
+    within("W", cases.rel_fro(W, W_ref), TOL_WH[mode])
+    within("H", cases.rel_fro(est.components_, H_ref), TOL_WH[mode])
+    within("objective", maxrel(errs, errs_ref), TOL_KL[mode])
+
+
+@pytest.mark.parametrize("mode", ["fp64", "tf32r"])
+def test_cfg4_shape_sparse_fit_vs_oracle(within, mode):
+    # the CSR path computes in FP32 FMA in every TF32 mode (one representative) and in FP64 FMA in fp64
+    X, H0, W_ref, H_ref, errs_ref = cfg4_case()
+    est = KLdivNMF(n_components=H0.shape[0], max_iter=ITERS, tol=0, mode=mode)
+    est._init_dictionary = H0
+    W, errs = est.fit_transform(X.copy(), return_errors=True)
+    assert len(errs) == ITERS
+    tol = 1e-9 if mode == "fp64" else 2e-5
+    within("W", cases.rel_fro(W, W_ref), tol)
+    within("H", cases.rel_fro(est.components_, H_ref), tol)
+    within("objective", maxrel(errs, errs_ref), tol)

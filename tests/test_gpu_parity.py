@@ -21,8 +21,19 @@ from oracle import klnmf_oracle as O
 pytestmark = pytest.mark.gpu
 
 MODES = ["fp64", "tf32x3", "tf32r", "tf32"]
+# stated tolerances = about 3 x the worst value measured on the B200 (profiles/r2_parity_measured.json, written by the
+# `within` fixture of conftest.py); k, f >= 6 cases.  The 6 x 2, k = 2 known-answer case has its own row: nothing
+# averages the operand rounding of the one-pass modes there.
 TOL_WH = {"fp64": 1e-9, "tf32x3": 2e-5, "tf32r": 5e-4, "tf32": 3e-3}
 TOL_KL = {"fp64": 1e-9, "tf32x3": 2e-5, "tf32r": 5e-4, "tf32": 1e-2}
+TOL_KL_LONG = {"fp64": 1e-9, "tf32x3": 2e-5, "tf32r": 1e-3, "tf32": 1e-2}      # converged fit: objective small against sum(X)
+TOL_KAT_WH = {"fp64": 1e-9, "tf32x3": 2e-5, "tf32r": 5e-4, "tf32": 3e-3}
+TOL_KAT_KL = {"fp64": 1e-8, "tf32x3": 2e-4, "tf32r": 1e-2, "tf32": 1e-1}
+
+
+def maxrel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.abs(b))) if a.size else 0.0
 
 
 def fit(X, k, iters, seed, mode, tol=0, **kw):
@@ -33,28 +44,28 @@ def fit(X, k, iters, seed, mode, tol=0, **kw):
 
 
 @pytest.mark.parametrize("mode", MODES)
-def test_kat_dense(golden, mode):
+def test_kat_dense(golden, within, mode):
     g = golden("kat_dense")
     est, W, errs = fit(cases.kat_dense(), 2, 10, 0, mode)
-    assert cases.rel_fro(W, g["W"]) < TOL_WH[mode]
-    assert cases.rel_fro(est.components_, g["H"]) < TOL_WH[mode]
+    within("W", cases.rel_fro(W, g["W"]), TOL_KAT_WH[mode])
+    within("H", cases.rel_fro(est.components_, g["H"]), TOL_KAT_WH[mode])
     # a 6 x 2 matrix with k = 2: nothing averages the 2^-12 operand rounding of the one-pass modes, and the objective
     # after 10 iterations (0.185, from 5.75) magnifies the resulting 2e-4 on W
-    kl_tol = 1e-2 if mode == "tf32r" else TOL_KL[mode] * 10
-    np.testing.assert_allclose(errs, g["errors"], rtol=kl_tol)
-    np.testing.assert_allclose(est.error(cases.kat_dense(), W), g["after"], rtol=kl_tol)
+    within("objective", maxrel(errs, g["errors"]), TOL_KAT_KL[mode])
+    within("objective_after", maxrel(est.error(cases.kat_dense(), W), g["after"]), TOL_KAT_KL[mode])
 
 
 @pytest.mark.parametrize("mode", MODES)
-def test_kat_csr(golden, mode):
+def test_kat_csr(golden, within, mode):
     g = golden("kat_csr")
     est, W, errs = fit(cases.kat_csr(), 2, 10, 0, mode)
-    tol = 1e-9 if mode == "fp64" else 2e-5        # the sparse path is FP32 FMA in both TF32 modes
-    assert cases.rel_fro(W, g["W"]) < tol and cases.rel_fro(est.components_, g["H"]) < tol
-    np.testing.assert_allclose(errs, g["errors"], rtol=tol)
+    tol = 1e-9 if mode == "fp64" else 2e-5        # the sparse path is FP32 FMA in every TF32 mode
+    within("W", cases.rel_fro(W, g["W"]), tol)
+    within("H", cases.rel_fro(est.components_, g["H"]), tol)
+    within("objective", maxrel(errs, g["errors"]), tol)
     # and the dense path on the same matrix is the reference's OTHER algorithm (eps at X == 0)
     est, W, errs = fit(cases.kat_csr().toarray(), 2, 10, 0, mode)
-    np.testing.assert_allclose(errs, g["errors_densepath"], rtol=1e-2 if mode == "tf32r" else TOL_KL[mode] * 10)   # k = 2
+    within("objective_densepath", maxrel(errs, g["errors_densepath"]), TOL_KAT_KL[mode])   # k = 2
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -63,59 +74,60 @@ def test_kat_csr(golden, mode):
     ("ragged_dense", cases.ragged_dense_X, 13, 5, 200),
     ("zeros_dense", cases.zeros_dense_X, 8, 7, 60),
 ])
-def test_dense_fit_golden(golden, mode, name, maker, k, seed, long_iters):
+def test_dense_fit_golden(golden, within, mode, name, maker, k, seed, long_iters):
     g = golden(name)
     est, W, errs = fit(maker(), k, 10, seed, mode)
     assert W.dtype == np.float64 and W.flags.c_contiguous and W.shape == g["W10"].shape
     assert len(errs) == 10
-    assert cases.rel_fro(W, g["W10"]) < TOL_WH[mode]
-    assert cases.rel_fro(est.components_, g["H10"]) < TOL_WH[mode]
-    np.testing.assert_allclose(errs, g["errors10"], rtol=TOL_KL[mode])
+    within("W10", cases.rel_fro(W, g["W10"]), TOL_WH[mode])
+    within("H10", cases.rel_fro(est.components_, g["H10"]), TOL_WH[mode])
+    within("objective10", maxrel(errs, g["errors10"]), TOL_KL[mode])
     est, W, errs = fit(maker(), k, long_iters, seed, mode)
     assert len(errs) == long_iters
-    # on a converged fit the objective is small against sum(X) and follows the 1e-5..1e-4 of W and H: tf32r states 1e-3
-    tol_long = 1e-3 if mode == "tf32r" else TOL_KL[mode]
-    assert abs(errs[-1] - g["errors_long"][-1]) <= tol_long * abs(g["errors_long"][-1])
-    final = est.error(maker(), W)
-    assert abs(final - g["final_error"]) <= tol_long * abs(g["final_error"])
+    # on a converged fit the objective is small against sum(X) and follows the 1e-5..1e-4 of W and H
+    within("objective_long", maxrel(errs[-1], g["errors_long"][-1]), TOL_KL_LONG[mode])
+    within("final_error", maxrel(est.error(maker(), W), g["final_error"]), TOL_KL_LONG[mode])
 
 
 @pytest.mark.parametrize("mode", MODES)
-def test_sparse_fit_golden(golden, mode):
+def test_sparse_fit_golden(golden, within, mode):
     g = golden("sparse_mid")
     tol = 1e-9 if mode == "fp64" else 2e-5
     est, W, errs = fit(cases.sparse_mid_X(), 16, 10, 11, mode)
-    assert cases.rel_fro(W, g["W10"]) < tol and cases.rel_fro(est.components_, g["H10"]) < tol
-    np.testing.assert_allclose(errs, g["errors10"], rtol=tol)
+    within("W10", cases.rel_fro(W, g["W10"]), tol)
+    within("H10", cases.rel_fro(est.components_, g["H10"]), tol)
+    within("objective10", maxrel(errs, g["errors10"]), tol)
     est, W, errs = fit(cases.sparse_mid_X(), 16, 200, 11, mode)
-    assert abs(errs[-1] - g["errors_long"][-1]) <= 10 * tol * abs(g["errors_long"][-1])
-    assert abs(est.error(cases.sparse_mid_X(), W) - g["final_error"]) <= 10 * tol * abs(g["final_error"])
+    within("objective_long", maxrel(errs[-1], g["errors_long"][-1]), 10 * tol)
+    within("final_error", maxrel(est.error(cases.sparse_mid_X(), W), g["final_error"]), 10 * tol)
 
 
 @pytest.mark.parametrize("mode", MODES)
-def test_transform_golden(golden, mode):
+def test_transform_golden(golden, within, mode):
     H0 = cases.sub_dictionary(10, 200)
     est = KLdivNMF(n_components=10, max_iter=30, tol=0, mode=mode)
     est.components_ = H0
     np.random.seed(0)
     W = est.transform(cases.cfg1_X()[:64])
     assert est.components_ is H0 and est._init_dictionary is H0      # untouched + sticky (nmf.py:289)
-    assert cases.rel_fro(W, golden("transform_dense")["W"]) < TOL_WH[mode]
+    within("W_dense", cases.rel_fro(W, golden("transform_dense")["W"]), TOL_WH[mode])
     Xs = cases.sparse_mid_X()[:50]
     W = fit_coefficients(Xs, cases.sub_dictionary(16, Xs.shape[1]), iter_nmf=30, mode=mode)
-    assert cases.rel_fro(W, golden("transform_sparse")["W"]) < (1e-9 if mode == "fp64" else 2e-5)
+    within("W_csr", cases.rel_fro(W, golden("transform_sparse")["W"]), 1e-9 if mode == "fp64" else 2e-5)
 
 
-@pytest.mark.parametrize("mode", ["fp64", "tf32x3"])
-def test_early_stop_golden(golden, mode, capsys):
+@pytest.mark.parametrize("mode", MODES)
+def test_early_stop_golden(golden, within, mode, capsys):
     g = golden("early_stop")
     est, W, errs = fit(cases.cfg1_X()[:120, :60], 6, 500, 2, mode, tol=1e-5)
     if mode == "fp64":
         assert len(errs) == len(g["errors"])          # stops at the same iteration as the reference
-        assert cases.rel_fro(W, g["W"]) < 1e-8 and cases.rel_fro(est.components_, g["H"]) < 1e-8
+        within("W", cases.rel_fro(W, g["W"]), 1e-8)
+        within("H", cases.rel_fro(est.components_, g["H"]), 1e-8)
     else:
-        assert abs(len(errs) - len(g["errors"])) <= 25
-        assert cases.rel_fro(W, g["W"]) < 2e-2
+        # the stop test compares an improvement of ~tol_abs with the mode's objective noise: the iteration differs
+        within("iterations_off", abs(len(errs) - len(g["errors"])) + 0.5, {"tf32x3": 26, "tf32r": 60, "tf32": 120}[mode])
+        within("W", cases.rel_fro(W, g["W"]), {"tf32x3": 2e-2, "tf32r": 5e-2, "tf32": 1e-1}[mode])
     assert "Iteration limit" not in capsys.readouterr().err
     # and the warning text when the limit IS reached with tol > 0 (nmf.py:224-225)
     fit(cases.cfg1_X()[:120, :60], 6, 5, 2, mode, tol=1e-5)
@@ -123,28 +135,48 @@ def test_early_stop_golden(golden, mode, capsys):
 
 
 @pytest.mark.parametrize("mode", MODES)
-def test_learner_golden(golden, mode):
+def test_tol0_breaks_on_a_rise_like_the_reference(golden, mode):
+    """tol = 0 (the learner's idiom, learner.py:12,39): the reference breaks iff the objective RISES (nmf.py:215).
+    With this adversarial initial dictionary it does, at the second objective evaluation, by 73 % -- far above any
+    mode's noise floor, so every mode has to stop exactly there and hand back the state after ONE update."""
+    g = golden("rise_tol0")
+    X, H0 = cases.rise_case()
+    est = KLdivNMF(n_components=H0.shape[0], max_iter=50, tol=0, mode=mode)
+    est._init_dictionary = H0
+    W, errs = est.fit_transform(X, return_errors=True)
+    assert len(g["errors"]) == 1 and len(errs) == 1
+    tol = {"fp64": 1e-9, "tf32x3": 1e-5, "tf32r": 2e-3, "tf32": 5e-3}[mode]
+    np.testing.assert_allclose(errs, g["errors"], rtol=tol)
+    assert cases.rel_fro(W, g["W"]) < tol and cases.rel_fro(est.components_, g["H"]) < tol
+    # ... and the objective of the returned state is indeed the larger one the reference saw and refused
+    assert est.error(X, W) > errs[0] * 1.5
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_learner_golden(golden, within, mode):
     g = golden("learner_small")
     tol = 1e-9 if mode == "fp64" else 5e-5
     mot, snd, coefs = cases.learner_small()
     lr = MultimodalLearner(['motion', 'sound'], [mot.shape[1], snd.shape[1]], coefs, 8, mode=mode)
     np.random.seed(3)
     lr.train([mot, snd.copy()], 20)
-    assert lr.dico.shape == g["dico"].shape and cases.rel_fro(lr.dico, g["dico"]) < tol
-    assert cases.rel_fro(lr.reconstruct_internal('sound', snd[:25].copy(), 15), g["internal_sound"]) < tol
+    assert lr.dico.shape == g["dico"].shape
+    within("dico", cases.rel_fro(lr.dico, g["dico"]), tol)
+    within("internal_sound", cases.rel_fro(lr.reconstruct_internal('sound', snd[:25].copy(), 15), g["internal_sound"]), tol)
     # a dense-only sub-problem goes through the dense engine of the mode
-    assert cases.rel_fro(lr.reconstruct_internal('motion', mot[:25], 15), g["internal_motion"]) < max(tol, TOL_WH[mode])
+    within("internal_motion", cases.rel_fro(lr.reconstruct_internal('motion', mot[:25], 15), g["internal_motion"]),
+           max(tol, TOL_WH[mode]))
     m2s = lr.modality_to_modality('motion', 'sound', mot[:25], 15)
     assert m2s.shape == g["motion_to_sound"].shape
-    assert cases.rel_fro(m2s, g["motion_to_sound"]) < max(tol, TOL_WH[mode])
+    within("motion_to_sound", cases.rel_fro(m2s, g["motion_to_sound"]), max(tol, TOL_WH[mode]))
     both = lr.reconstruct_internal_multi(['motion', 'sound'], [mot[:25], snd[:25].copy()], 15)
-    assert cases.rel_fro(both, g["internal_both"]) < tol
+    within("internal_both", cases.rel_fro(both, g["internal_both"]), tol)
     with pytest.raises(AssertionError):
         lr.reconstruct_internal('sound', mot[:25], 5)          # wrong width (learner.py:73)
 
 
-@pytest.mark.parametrize("mode", ["tf32x3", "tf32"])
-def test_mid_size_dense_vs_oracle(mode):
+@pytest.mark.parametrize("mode", MODES)
+def test_mid_size_dense_vs_oracle(within, mode):
     """cfg3/cfg5-like tile shapes (f, k multiples of the MMA tile) on a row subsample."""
     rs = np.random.RandomState(5)
     n, f, k = 1000, 1024, 256
@@ -152,23 +184,41 @@ def test_mid_size_dense_vs_oracle(mode):
     np.random.seed(9)
     Wr, Hr, er, _ = O.fit_transform(X, k=k, max_iter=10, tol=0)
     est, W, errs = fit(X, k, 10, 9, mode)
-    assert cases.rel_fro(W, Wr) < TOL_WH[mode] and cases.rel_fro(est.components_, Hr) < TOL_WH[mode]
-    np.testing.assert_allclose(errs, er, rtol=TOL_KL[mode])
+    within("W", cases.rel_fro(W, Wr), TOL_WH[mode])
+    within("H", cases.rel_fro(est.components_, Hr), TOL_WH[mode])
+    within("objective", maxrel(errs, er), TOL_KL[mode])
 
 
 @pytest.mark.parametrize("mode", MODES)
 @pytest.mark.parametrize("n,f", [(391, 1000), (1030, 333)])
-def test_k512_ragged_dense_vs_oracle(mode, n, f):
+def test_k512_ragged_dense_vs_oracle(within, mode, n, f):
     """k = 512 (cfg5's component count) on ragged rows / features: the ratio contraction takes its in-place form
-    (the ratio overwrites the X chunk in shared memory, dense_tc.cu) for k >= 512, and tf32x3 the centered ratio."""
+    (the ratio overwrites the X chunk in shared memory, dense_tc.cu) for k >= 512, the coefficient and numerator
+    contractions their wide tiles (256 x 512 / 512 x 256), and tf32x3 / tf32r the centered ratio."""
     rs = np.random.RandomState(n + f)
     X = rs.gamma(0.5, 1.0, size=(n, f))
     X[rs.random_sample((n, f)) < 0.25] = 0.0
     np.random.seed(21)
     Wr, Hr, er, _ = O.fit_transform(X, k=512, max_iter=10, tol=0)
     est, W, errs = fit(X, 512, 10, 21, mode)
-    assert cases.rel_fro(W, Wr) < TOL_WH[mode] and cases.rel_fro(est.components_, Hr) < TOL_WH[mode]
-    np.testing.assert_allclose(errs, er, rtol=max(TOL_KL[mode], 1e-4 if mode == "tf32x3" else 0))
+    within("W", cases.rel_fro(W, Wr), TOL_WH[mode])
+    within("H", cases.rel_fro(est.components_, Hr), TOL_WH[mode])
+    within("objective", maxrel(errs, er), max(TOL_KL[mode], 1e-4 if mode == "tf32x3" else 0))
+
+
+@pytest.mark.parametrize("n,f,k", [(600, 700, 300), (520, 300, 700)])
+def test_ragged_component_counts_beyond_one_tile(within, n, f, k):
+    """256 < k not a multiple of anything: the second 256-column MMA of the wide coefficient tile and the second
+    256-row block of the wide numerator tile are partly (k = 300) or more than once (k = 700: two tiles) used."""
+    rs = np.random.RandomState(n + k)
+    X = rs.gamma(0.5, 1.0, size=(n, f))
+    np.random.seed(22)
+    Wr, Hr, er, _ = O.fit_transform(X, k=k, max_iter=6, tol=0)
+    for mode in ("tf32r", "tf32"):
+        est, W, errs = fit(X, k, 6, 22, mode)
+        within(mode + "_W", cases.rel_fro(W, Wr), TOL_WH[mode])
+        within(mode + "_H", cases.rel_fro(est.components_, Hr), TOL_WH[mode])
+        within(mode + "_objective", maxrel(errs, er), TOL_KL[mode])
 
 
 def test_multi_panel_equals_single_panel():
@@ -189,31 +239,31 @@ def test_multi_panel_equals_single_panel():
     np.testing.assert_allclose(outs[1][2], outs[0][2], rtol=1e-12)
 
 
-def test_cfg2_full_shapes_learner_vs_oracle():
+def test_cfg2_full_shapes_learner_vs_oracle(within):
     """BASELINE.json configs[1] at its real shapes: 1000 samples, motion 450 dense + sound 110 000
     CSR at 1 % -> a 1000 x 110 450 CSR stack (learner.py:53-56), k = 50; a few training iterations and a
     reconstruction of the missing modality against the float64 oracle (3 iterations keep the oracle's
     nnz x k temporaries, 3 x 0.6 GB, and its runtime in seconds)."""
     motion, sound, coefs = cases.cfg2_inputs()
     mods, dims = ['motion', 'sound'], [motion.shape[1], sound.shape[1]]
-    lr = MultimodalLearner(mods, dims, coefs, 50, mode="tf32x3")
+    lr = MultimodalLearner(mods, dims, coefs, 50)
     np.random.seed(3)
     lr.train([motion, sound.copy()], 3)
     ref = O.Learner(mods, dims, coefs, 50)
     np.random.seed(3)
     ref.train([motion, sound.copy()], 3)
     assert lr.dico.shape == (50, 110450)
-    assert cases.rel_fro(lr.dico, ref.dico) < 5e-5
+    within("dico", cases.rel_fro(lr.dico, ref.dico), 5e-5)
     internal = lr.reconstruct_internal('motion', motion[:40], 5)
     internal_ref = ref.reconstruct_internal_multi(['motion'], [motion[:40]], 5)
-    assert cases.rel_fro(internal, internal_ref) < 5e-4
+    within("internal", cases.rel_fro(internal, internal_ref), 5e-4)
     snd = lr.reconstruct_modality('sound', internal)
     assert snd.shape == (40, 110000)
-    assert cases.rel_fro(snd, internal_ref.dot(ref.get_dico('sound'))) < 5e-4
+    within("reconstruction", cases.rel_fro(snd, internal_ref.dot(ref.get_dico('sound'))), 5e-4)
 
 
 @pytest.mark.parametrize("mode", MODES)
-def test_learner_dense_stack_formed_on_the_device(mode):
+def test_learner_dense_stack_formed_on_the_device(within, mode):
     """Three dense modalities (float64, float32, integer counts): learner.stack_data hands the estimator the blocks
     and klnmf_set_dense_blocks_host scales and concatenates them on the device; same dictionary as the reference
     formula safe_hstack([c * m]) (learner.py:53-56) fed to the estimator, and as the float64 oracle."""
@@ -230,11 +280,12 @@ def test_learner_dense_stack_formed_on_the_device(mode):
     est = KLdivNMF(n_components=9, max_iter=10, tol=0, mode=mode)
     np.random.seed(4)
     est.fit(V)
-    assert cases.rel_fro(lr.dico, est.components_) < (1e-12 if mode == "fp64" else (1e-5 if mode == "tf32r" else 1e-6))
+    within("blocks_vs_hstack", cases.rel_fro(lr.dico, est.components_) + 1e-300,
+           1e-12 if mode == "fp64" else (1e-5 if mode == "tf32r" else 1e-6))
     ref = O.Learner(mods, dims, coefs, 9)
     np.random.seed(4)
     ref.train(mats, 10)
-    assert cases.rel_fro(lr.dico, ref.dico) < TOL_WH[mode]
+    within("dico", cases.rel_fro(lr.dico, ref.dico), TOL_WH[mode])
     internal = lr.reconstruct_internal_multi(['sound', 'motion'], [mats[0][:50], mats[2][:50]], 10)
     internal_ref = ref.reconstruct_internal_multi(['sound', 'motion'], [mats[0][:50], mats[2][:50]], 10)
-    assert cases.rel_fro(internal, internal_ref) < TOL_WH[mode]
+    within("internal", cases.rel_fro(internal, internal_ref), TOL_WH[mode])

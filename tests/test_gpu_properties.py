@@ -23,7 +23,7 @@ from oracle import cases, klnmf_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-NOISE = {"fp64": 1e-12, "tf32x3": 1e-6, "tf32": 1e-4}      # relative rise of the objective a mode may show
+NOISE = {"fp64": 1e-12, "tf32x3": 1e-6, "tf32r": 1e-5, "tf32": 1e-4}      # relative rise of the objective a mode may show
 
 
 def transform(X, H, iters, mode):
@@ -74,7 +74,7 @@ def check_fit_state(W, H, errs, mode):
     assert (rises < NOISE[mode]).all(), rises
 
 
-@pytest.mark.parametrize("mode", ["tf32", "tf32x3"])
+@pytest.mark.parametrize("mode", ["tf32r", "tf32", "tf32x3"])
 def test_cfg5_shape_fit_properties(mode):
     """f = 8192, k = 512 (BASELINE.json configs[4]) on 32768 device-generated samples."""
     n, f, k = 32768, 8192, 512
@@ -96,7 +96,7 @@ def test_cfg5_shape_modes_agree():
     np.random.seed(11)
     H0 = O.init_dictionary(k, f)
     out = {}
-    for mode in ("tf32", "tf32x3", "fp64"):
+    for mode in ("tf32", "tf32r", "tf32x3", "fp64"):
         with _native.Engine(n, f, k, mode=mode) as e:
             e.fill_dense_synthetic(5)            # the same generator and seed in every mode
             e.set_dictionary(H0)
@@ -108,10 +108,11 @@ def test_cfg5_shape_modes_agree():
     # split mode therefore contracts the CENTERED ratio Q - 1 (api.cu, dense_iteration): measured 5.4e-6 here
     # (tools/accuracy_vs_shape.py).  The objective is a contraction over k = 512 non-negative
     # terms that cannot be centered: 4.2e-5.
-    tol_w = {"tf32x3": 2e-5, "tf32": 3e-3}
-    tol_h = {"tf32x3": 2e-5, "tf32": 3e-3}
-    tol_kl = {"tf32x3": 1e-4, "tf32": 1e-2}
-    for mode in ("tf32x3", "tf32"):
+    # stated = about 3 x measured (tools/accuracy_vs_shape.py: tf32r 1.3e-5 / 1.1e-5 / 2.8e-5, tf32 3.0e-5 / 1.4e-5 / 6.4e-4)
+    tol_w = {"tf32x3": 2e-5, "tf32r": 5e-5, "tf32": 1e-4}
+    tol_h = {"tf32x3": 2e-5, "tf32r": 5e-5, "tf32": 5e-5}
+    tol_kl = {"tf32x3": 1e-4, "tf32r": 1e-4, "tf32": 2e-3}
+    for mode in ("tf32x3", "tf32r", "tf32"):
         assert cases.rel_fro(out[mode][0], out["fp64"][0]) < tol_w[mode]
         assert cases.rel_fro(out[mode][1], out["fp64"][1]) < tol_h[mode]
         np.testing.assert_allclose(out[mode][2], out["fp64"][2], rtol=tol_kl[mode])

@@ -25,7 +25,7 @@ def is_NN(a):
     return np.all(a >= 0)
 
 
-@pytest.fixture(params=["fp64", "tf32x3"])
+@pytest.fixture(params=["fp64", "tf32x3", "tf32r"])
 def mode(request):
     return request.param
 

@@ -140,6 +140,17 @@ def test_early_stop_golden(golden):
     assert cases.rel_fro(W, g["W"]) < 1e-10 and cases.rel_fro(H, g["H"]) < 1e-10
 
 
+def test_rise_with_tol0_golden(golden):
+    # nmf.py:215 with tol = 0: the loop breaks when the objective rises; the reference does so at the second evaluation
+    g = golden("rise_tol0")
+    X, H0 = cases.rise_case()
+    W, H, errs, n_iter = O.fit_transform(X, k=H0.shape[0], max_iter=50, tol=0, H0=H0)
+    assert n_iter == 2 and len(errs) == len(g["errors"]) == 1
+    np.testing.assert_allclose(errs, g["errors"], rtol=TIGHT)
+    assert cases.rel_fro(W, g["W"]) < TIGHT and cases.rel_fro(H, g["H"]) < TIGHT
+    assert O.error(X, W, H) > 1.5 * errs[0]          # the state handed back is the one whose objective rose
+
+
 def test_learner_golden(golden):
     g = golden("learner_small")
     mot, snd, coefs = cases.learner_small()

@@ -17,7 +17,7 @@ k = 48
 np.random.seed(4)
 H0 = O.init_dictionary(k, X.shape[1])
 b = D.shard_bounds(X.shape[0], world)
-for mode, tol in (("fp64", 1e-9), ("tf32x3", 2e-5), ("tf32", 3e-3)):
+for mode, tol in (("fp64", 1e-9), ("tf32x3", 2e-5), ("tf32r", 3e-4), ("tf32", 3e-4)):
     sh = D.ShardedNMF(k, max_iter=10, tol=0, mode=mode, device=local)
     W, errs = sh.fit_transform(X[b[rank]:b[rank + 1]], X.shape[0], H0=H0, fit=True, return_errors=True)
     np.random.seed(4)
