@@ -320,19 +320,18 @@ def phase_roofline(ms, cnt, n_local, f, k, kind, steps, peaks, mode):
              "numerator": "tc_gemm_kernel<numerator: N+=W'^T.Q>"}
     if mode == "fp64":
         names = {k_: v.replace("tc_gemm_kernel", "generic_gemm_kernel<double>") for k_, v in names.items()}
-    dom = max(names, key=lambda p: ms[p])
-    launches = max(cnt[dom], 1)
-    flops_per_launch = 2.0 * n_local * k * f * steps / launches        # each contraction is 2 n k f per iteration
-    fused = kind == "dense_transform" and mode == "tf32" and os.environ.get("KLNMF_FUSED", "1") != "0" and \
+    fused = kind != "sparse_fit" and mode in ("tf32", "tf32r") and os.environ.get("KLNMF_FUSED", "1") != "0" and \
         (k <= 128 or (k <= 256 and os.environ.get("KLNMF_FUSED256", "1") != "0"))
+    per_launch = {p_: 2.0 for p_ in names}                             # each contraction is 2 n k f per iteration
     if fused:
-        # one kernel per iteration does both contractions of the transform (dense_fused.cu, k <= 128; on
-        # clusters of two CTAs for 128 < k <= 256, dense_fused256.cu): 4 n k f
+        # one kernel per row panel does both contractions of the coefficient half-step (dense_fused.cu, k <= 128; on
+        # clusters of two CTAs for 128 < k <= 256, dense_fused256.cu): 4 n k f, timed under the "ratio" phase
         names["ratio"] = ("fused_coef_kernel" if k <= 128 else "fused_coef256_kernel") + \
             "<S=W.H -> Q=(X+eps)/(S+eps), KL -> G+=Q.H^T -> W'=W(.)G>"
-        dom = "ratio"
-        launches = max(cnt[dom], 1)
-        flops_per_launch = 4.0 * n_local * k * f * steps / launches
+        per_launch["ratio"] = 4.0
+    dom = max(names, key=lambda p_: ms[p_])
+    launches = max(cnt[dom], 1)
+    flops_per_launch = per_launch[dom] * n_local * k * f * steps / launches
     avg_s = ms[dom] / launches * 1e-3
     ach = flops_per_launch / avg_s / 1e12
     peak = peaks["bf16_sustained"] / 2.0                                 # TF32 dense = half the BF16 rate
@@ -340,7 +339,7 @@ def phase_roofline(ms, cnt, n_local, f, k, kind, steps, peaks, mode):
         peak = 40.0
     rows_per_launch = int(round(n_local * steps / float(launches)))
     r = {"bound": "tensor", "achieved": ach, "peak": peak, "unit": "TFLOP/s", "frac": ach / peak,
-         "traffic": ncu_traffic(("fused" if k <= 128 else "fused256") if fused else dom, rows_per_launch, f, k, mode),
+         "traffic": ncu_traffic(("fused" if k <= 128 else "fused256") if (fused and dom == "ratio") else dom, rows_per_launch, f, k, mode),
          "rows_per_launch": rows_per_launch,
          "kernel": names[dom], "avg_launch_ms": ms[dom] / launches, "launches": launches,
          "peak_source": ("TF32 = 1/2 x sustained cuBLAS bf16, " + peaks["source"]) if mode != "fp64" else "nominal B200 FP64",

@@ -346,6 +346,8 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
     d.Wout = ctx->W[cur ^ 1]; d.ldwo = ctx->ldw;
     d.kl = ctx->dred; d.stop = stop;
     d.qshift = qshift; d.colbias = colbias;
+    d.Wlo = ctx->split ? ctx->Wlo[cur] : nullptr; d.Wout_lo = ctx->split ? ctx->Wlo[cur ^ 1] : nullptr;
+    d.accurate = ctx->single_pass ? 1 : 0;
     return fused_coef_step(ctx, d);
   }
   for (int64_t r0 = 0; r0 < ctx->n; r0 += ctx->panel_rows) {
@@ -366,6 +368,8 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
       d.Q = ctx->Q; d.ldq = ctx->ldq;
       d.kl = ctx->dred; d.stop = stop;
       d.qshift = qshift; d.colbias = colbias;
+      d.Wlo = Wclo; d.Wout_lo = Wnlo;
+      d.accurate = ctx->single_pass ? 1 : 0;
       KL_TRY(fused_coef_step(ctx, d));
     } else {  // ratio + objective: Q = (X+eps)/(W.H+eps)   (nmf.py:325-336, metrics.py:18-20)
       PhaseTimer t(ctx, prof, PH_RATIO);

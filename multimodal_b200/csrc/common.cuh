@@ -176,6 +176,11 @@ struct FusedDesc {
   int only_kl;
   float qshift;                      // the ratio tile holds q - qshift
   const float *colbias;              // W' = W (.) (G + colbias[component]) (nullptr: no bias)
+  // TF32R: W is a (hi, lo) pair, hi the round-to-nearest TF32 value the contractions multiply; the ratio tile is
+  // rounded to nearest before the second contraction reads it, the objective takes its cancellation-free form
+  const void *Wlo;                   // low parts of W (nullptr: W is plain FP32)
+  void *Wout_lo;                     // low parts of the updated coefficients (nullptr: plain FP32 output)
+  int accurate;                      // cancellation-free objective + rounded ratio tile
 };
 bool fused_supported(const klnmf_ctx *ctx, int fit);
 int fused_coef_step256(klnmf_ctx *ctx, const FusedDesc &d, int *err_dev);   // 128 < k <= 256, transform, CTA pairs

@@ -69,6 +69,9 @@ struct FusedParams {
   float qshift;            // the ratio tile holds q - qshift (centered ratio, api.cu)
   const float *colbias;    // W' = W (.) (G + colbias[component])
   int lookahead;           // steps the first contraction runs ahead of the second one (1 or 2)
+  const float *Wlo;        // TF32R: low parts of W (W itself is the TF32-exact high part); nullptr otherwise
+  float *Wout_lo;          // TF32R: low parts of W'
+  int accurate;            // TF32R: cancellation-free objective, centered ratio stored as u, tile rounded to TF32
 };
 
 __device__ __forceinline__ void tmem_ld16_issue(uint32_t taddr, uint32_t v[16]) {
@@ -334,15 +337,33 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         if (lane == 0) { mbar_arrive_relaxed(s_empty(grp)); mbar_arrive(x_empty(xb)); }
         // rows >= M and columns >= F hold x = 0, s = 0 (TMA zero fill): q = 1, the term is exactly 0 and the
         // zero-filled dictionary columns keep it out of G
-        float part0 = 0.f, part1 = 0.f;
+        {
+          f32x2_t part2 = splat2(0.f);
+          const f32x2_t nshift2 = splat2(-p.qshift);
+          const bool store_u = p.accurate && p.qshift == 1.f;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          float q0, q1;
-          part0 += ratio_term<false>(x[i], __uint_as_float(v[i]), q0);
-          part1 += ratio_term<false>(x[i + 1], __uint_as_float(v[i + 1]), q1);
-          x[i] = q0 - p.qshift; x[i + 1] = q1 - p.qshift;
+          for (int i = 0; i < 32; i += 2) {
+            const f32x2_t x2 = pack2(x[i], x[i + 1]);
+            const f32x2_t s2 = pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+            f32x2_t q2, out2;
+            if (p.accurate) {
+              f32x2_t u2;
+              part2 = add2(part2, ratio_pair_cf<false>(x2, s2, q2, u2));
+              out2 = store_u ? u2 : add2(q2, nshift2);
+            } else {
+              part2 = add2(part2, ratio_pair_fast(x2, s2, q2));
+              out2 = add2(q2, nshift2);
+            }
+            unpack2(out2, x[i], x[i + 1]);
+          }
+          if (p.accurate) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) x[i] = tf32_round(x[i]);
+          }
+          float part0, part1;
+          unpack2(part2, part0, part1);
+          kl_blk += part0 + part1;
         }
-        kl_blk += part0 + part1;
         if (!p.only_kl) {
           mbar_wait(q_empty(grp), ph2 ^ 1u, p.err, 11);
           if (WRITE_Q) {
@@ -392,11 +413,25 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
             if (TSW) w = make_float4(__uint_as_float(wt[4 * i]), __uint_as_float(wt[4 * i + 1]), __uint_as_float(wt[4 * i + 2]),
                                      __uint_as_float(wt[4 * i + 3]));
             else w = __ldg(reinterpret_cast<const float4 *>(wi + 4 * i));
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.colbias) b = __ldg(reinterpret_cast<const float4 *>(p.colbias + col0 + 4 * i));
-            *reinterpret_cast<float4 *>(wo + 4 * i) =
-                make_float4(w.x * (__uint_as_float(v[4 * i]) + b.x), w.y * (__uint_as_float(v[4 * i + 1]) + b.y),
-                            w.z * (__uint_as_float(v[4 * i + 2]) + b.z), w.w * (__uint_as_float(v[4 * i + 3]) + b.w));
+            if (p.Wlo) {
+              const float4 l = __ldg(reinterpret_cast<const float4 *>(p.Wlo + row * p.ldw + col0 + 4 * i));
+              w.x += l.x; w.y += l.y; w.z += l.z; w.w += l.w;
+            }
+            float4 g = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                   __uint_as_float(v[4 * i + 3]));
+            if (p.colbias) {
+              // centered ratio: G = (Q-1).H^T + rowsum(H), clamped at zero like the unfused epilogue (dense_tc.cu)
+              const float4 b = __ldg(reinterpret_cast<const float4 *>(p.colbias + col0 + 4 * i));
+              g.x = fmaxf(g.x + b.x, 0.f); g.y = fmaxf(g.y + b.y, 0.f); g.z = fmaxf(g.z + b.z, 0.f); g.w = fmaxf(g.w + b.w, 0.f);
+            }
+            float4 o = make_float4(w.x * g.x, w.y * g.y, w.z * g.z, w.w * g.w);
+            if (p.Wout_lo) {
+              const float4 h = make_float4(tf32_round(o.x), tf32_round(o.y), tf32_round(o.z), tf32_round(o.w));
+              *reinterpret_cast<float4 *>(p.Wout_lo + row * p.ldwo + col0 + 4 * i) =
+                  make_float4(o.x - h.x, o.y - h.y, o.z - h.z, o.w - h.w);
+              o = h;
+            }
+            *reinterpret_cast<float4 *>(wo + 4 * i) = o;
           }
         }
       }
@@ -456,10 +491,11 @@ int launch_fused(klnmf_ctx *ctx, const FusedDesc &d, FusedParams p) {
 
 bool fused_supported(const klnmf_ctx *ctx, int fit) {
   const bool off = getenv("KLNMF_FUSED") && atoi(getenv("KLNMF_FUSED")) == 0;   // read per call: tests toggle it
-  // k <= 128: fit and transform (this file); 128 < k <= 256: transform on CTA pairs (dense_fused256.cu)
+  // k <= 128 (this file) and 128 < k <= 256 on CTA pairs (dense_fused256.cu): fit and transform
   const bool off256 = getenv("KLNMF_FUSED256") && atoi(getenv("KLNMF_FUSED256")) == 0;
-  return !off && ctx->mode == KLNMF_MODE_TF32 && !ctx->sparse && !ctx->debug_simt &&
-         (ctx->k <= 128 || (!fit && !off256 && ctx->k <= 256));
+  // the one-pass modes: TF32, and TF32R (rounded operands: the (hi, lo) state's high parts; centered, rounded ratio tile)
+  return !off && (ctx->mode == KLNMF_MODE_TF32 || ctx->mode == KLNMF_MODE_TF32R) && !ctx->sparse && !ctx->debug_simt &&
+         (ctx->k <= 128 || (!off256 && ctx->k <= 256));
 }
 
 int fused_coef_step(klnmf_ctx *ctx, const FusedDesc &d) {
@@ -485,6 +521,7 @@ int fused_coef_step(klnmf_ctx *ctx, const FusedDesc &d) {
   p.w_cols = d.ldw < d.ldwo ? d.ldw : d.ldwo;
   p.kl = d.kl; p.stop = d.stop; p.err = st->err_dev; p.only_kl = d.only_kl;
   p.qshift = d.qshift; p.colbias = d.colbias;
+  p.Wlo = (const float *)d.Wlo; p.Wout_lo = (float *)d.Wout_lo; p.accurate = d.accurate;
   // default: W block in TMEM ("TS" form of tcgen05.mma); KLNMF_FUSED_TS=0 keeps it in shared memory
   const bool ts = !(getenv("KLNMF_FUSED_TS") && atoi(getenv("KLNMF_FUSED_TS")) == 0);
   const int v = getenv("KLNMF_FUSED_V") ? atoi(getenv("KLNMF_FUSED_V")) : 0;

@@ -29,8 +29,11 @@
 // 1700 clk, and halving the dictionary bytes does not change that -- it is the round trip
 // "tcgen05.commit -> producer -> TMA -> L2 -> full barrier" of a ring that shared memory limits to two stages per
 // operand (2 x 32 KB H^T + 2 x 32 KB H + 2 x 32 KB Q + 2 x 16 KB X = 224 KB).  Four half-size stages were slower.
-// Reference lines as in dense_fused.cu (nmf.py:325-343, metrics.py:18-20).  Transform only (fit keeps the
-// three-contraction form at k > 128).
+// Reference lines as in dense_fused.cu (nmf.py:325-343, metrics.py:18-20).  Fit (write_q): every warp also stores
+// its 32 x 32 box of the ratio tile by TMA, once, for the numerator contraction N += W'^T.Q (nmf.py:349), which
+// needs the finished W' of the whole panel.  TF32R (accurate): the TMEM block of W holds the round-to-nearest high
+// parts, the ratio tile is centered (u = q - 1) and rounded to nearest, the objective takes its cancellation-free form,
+// W' = (W_hi + W_lo) (.) max(G + rowsum(H), 0) leaves as a (hi, lo) pair.
 #include <cuda.h>
 
 #include "common.cuh"
@@ -75,6 +78,10 @@ struct Fused256Params {
   int *err;
   float qshift;   // the ratio tile holds q - qshift (centered ratio, api.cu)
   const float *colbias;   // W' = W (.) (G + colbias[component])
+  const float *Wlo;       // TF32R: low parts of W (W itself is the TF32-exact high part); nullptr otherwise
+  float *Wout_lo;         // TF32R: low parts of W'
+  int accurate;           // TF32R: cancellation-free objective, centered ratio stored as u, tile rounded to TF32
+  int write_q;            // fit: every CTA also stores its half of the ratio tile (TMA) for the numerator N += W'^T.Q
   int dbg;        // timing experiments only (KLNMF_F256_DBG): 1 no exchange, 2 no S MMAs, 4 no G MMAs, 8 no ratio math
 };
 
@@ -134,7 +141,8 @@ __device__ __forceinline__ void umma_tf32_tsp(uint32_t d_tmem, uint32_t a_tmem, 
 
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(P_THREADS, 1)
 fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_constant__ CUtensorMap tmH,
-                     const __grid_constant__ CUtensorMap tmX, const Fused256Params p) {
+                     const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmQ,
+                     const Fused256Params p) {
   if (p.stop != nullptr && *p.stop != 0) return;     // uniform over the grid: both CTAs of a cluster leave together
   const uint32_t crank = cluster_ctarank();
   const uint32_t peer = crank ^ 1u;
@@ -172,6 +180,7 @@ fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_cons
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmHt); tma_prefetch_desc(&tmH); tma_prefetch_desc(&tmX);
+    if (p.write_q) tma_prefetch_desc(&tmQ);
     mbar_init(w_full, P_EPI_WARPS); mbar_init(w_empty, 1); mbar_init(g_full, 1); mbar_init(g_empty, P_EPI_WARPS);
     for (int s = 0; s < PS1; s++) { mbar_init(h1_full(s), 1); mbar_init(h1_empty(s), 1); }
     for (int s = 0; s < PS2; s++) { mbar_init(h2_full(s), 1); mbar_init(h2_empty(s), 1); }
@@ -345,6 +354,17 @@ fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_cons
           if (fill_col(cc) < nkb * 32) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.W + prow * p.ldw + fill_col(cc)));
       }
     };
+    // TF32R: the low parts of this row block's coefficients are read in its final epilogue only -- pull them into L2
+    auto prefetch_wlo = [&](int rb_cur) {
+      const int64_t prow = (int64_t)rb_cur * PBM + r;
+      if (p.Wlo != nullptr && prow < p.M) {
+#pragma unroll
+        for (int cc = 0; cc < 2; cc++) {
+          const int col = (int)crank * PKH + grp * (PKH / 2) + cc * 32;
+          if (col < p.w_cols) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.Wlo + prow * p.ldw + col));
+        }
+      }
+    };
     const int j_pf = nsteps > 8 ? nsteps - 8 : 0;
     if (cl_first < p.n_blocks) fill_w(cl_first, 0u);
     uint32_t c = 0, rbc = 0;
@@ -355,7 +375,7 @@ fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_cons
       const int rb_next = rb + cl_step;
 #pragma unroll 1
       for (int j = 0; j < nsteps; j++, c++) {
-        if (j == j_pf) prefetch_w(rb_next);
+        if (j == j_pf) { prefetch_w(rb_next); prefetch_wlo(rb); }
         if ((int)(c & 1u) != grp) continue;
         const uint32_t ph2 = (c >> 1) & 1u;         // PXB == 2: X buffer grp, same phase as the Q buffers
         const uint32_t sa = c % PNS;
@@ -375,18 +395,40 @@ fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { mbar_arrive_relaxed(s_empty(sa)); mbar_arrive(x_empty(grp)); }
-        float part0 = 0.f, part1 = 0.f;
+        {
+          f32x2_t part2 = splat2(0.f);
+          const f32x2_t nshift2 = splat2(-p.qshift);
+          const bool store_u = p.accurate && p.qshift == 1.f;
 #pragma unroll
-        for (int i = 0; i < 32; i += 2) {
-          if (p.dbg & 8) break;
-          float q0, q1;
-          part0 += ratio_term<false>(x[i], __uint_as_float(v[i]), q0);
-          part1 += ratio_term<false>(x[i + 1], __uint_as_float(v[i + 1]), q1);
-          x[i] = q0 - p.qshift; x[i + 1] = q1 - p.qshift;
+          for (int i = 0; i < 32; i += 2) {
+            if (p.dbg & 8) break;
+            const f32x2_t x2 = pack2(x[i], x[i + 1]);
+            const f32x2_t s2 = pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
+            f32x2_t q2, out2;
+            if (p.accurate) {
+              f32x2_t u2;
+              part2 = add2(part2, ratio_pair_cf<false>(x2, s2, q2, u2));
+              out2 = store_u ? u2 : add2(q2, nshift2);
+            } else {
+              part2 = add2(part2, ratio_pair_fast(x2, s2, q2));
+              out2 = add2(q2, nshift2);
+            }
+            unpack2(out2, x[i], x[i + 1]);
+          }
+          if (p.accurate) {
+#pragma unroll
+            for (int i = 0; i < 32; i++) x[i] = tf32_round(x[i]);
+          }
+          float part0, part1;
+          unpack2(part2, part0, part1);
+          kl_blk += part0 + part1;
         }
-        kl_blk += part0 + part1;
         // both issuers are done with Q tile `grp` (ours and the peer's, of which we write half each)
         mbar_wait(q_empty(grp), ph2 ^ 1u, p.err, 11);
+        if (p.write_q) {      // ... and so is the TMA store of this warp's box two steps ago
+          if (lane == 0) bulk_wait_read0();
+          __syncwarp();
+        }
         uint8_t *qrow = q_gen + grp * QTILE_BYTES + crank * QHALF_BYTES + r * 128;
 #pragma unroll
         for (int i = 0; i < 8; i++)
@@ -394,6 +436,9 @@ fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_cons
         fence_proxy_async();                // generic-proxy stores before the async-proxy reads (our MMAs, the bulk copy)
         __syncwarp();
         if (lane == 0) {
+          // fit: this warp's 32 rows x 32 features of the ratio tile also leave for HBM (the numerator N += W'^T.Q,
+          // nmf.py:349, reads the panel once W' of all its rows exists); rows >= M and features >= F are clipped
+          if (p.write_q) tma_store_2d(&tmQ, q_half, j * PBN + (int)crank * PHN, rb * PBM + quarter * 32);
           if (!(p.dbg & 1)) bulk_copy_to_peer(q_half_peer, q_half, 32 * 128, q_full_peer);
           if (quarter == 0 && !(p.dbg & 1)) mbar_expect_tx(q_full(grp), QHALF_BYTES);   // arrives, and expects the peer's four copies
           else mbar_arrive(q_full(grp));
@@ -416,11 +461,26 @@ fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_cons
           float *wo = p.Wout + row * p.ldwo + col0;
 #pragma unroll
           for (int i = 0; i < 4; i++) {
-            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.colbias) b = __ldg(reinterpret_cast<const float4 *>(p.colbias + col0 + 4 * i));
-            *reinterpret_cast<float4 *>(wo + 4 * i) =
-                make_float4(__uint_as_float(w[4 * i]) * (__uint_as_float(v[4 * i]) + b.x), __uint_as_float(w[4 * i + 1]) * (__uint_as_float(v[4 * i + 1]) + b.y),
-                            __uint_as_float(w[4 * i + 2]) * (__uint_as_float(v[4 * i + 2]) + b.z), __uint_as_float(w[4 * i + 3]) * (__uint_as_float(v[4 * i + 3]) + b.w));
+            float4 wv = make_float4(__uint_as_float(w[4 * i]), __uint_as_float(w[4 * i + 1]), __uint_as_float(w[4 * i + 2]),
+                                    __uint_as_float(w[4 * i + 3]));
+            if (p.Wlo) {      // the TMEM block holds the TF32-exact high parts; the update multiplies the full FP32 state
+              const float4 l = __ldg(reinterpret_cast<const float4 *>(p.Wlo + row * p.ldw + col0 + 4 * i));
+              wv.x += l.x; wv.y += l.y; wv.z += l.z; wv.w += l.w;
+            }
+            float4 g = make_float4(__uint_as_float(v[4 * i]), __uint_as_float(v[4 * i + 1]), __uint_as_float(v[4 * i + 2]),
+                                   __uint_as_float(v[4 * i + 3]));
+            if (p.colbias) {  // centered ratio: G = (Q-1).H^T + rowsum(H), clamped at zero like the unfused epilogue
+              const float4 b = __ldg(reinterpret_cast<const float4 *>(p.colbias + col0 + 4 * i));
+              g.x = fmaxf(g.x + b.x, 0.f); g.y = fmaxf(g.y + b.y, 0.f); g.z = fmaxf(g.z + b.z, 0.f); g.w = fmaxf(g.w + b.w, 0.f);
+            }
+            float4 o = make_float4(wv.x * g.x, wv.y * g.y, wv.z * g.z, wv.w * g.w);
+            if (p.Wout_lo) {
+              const float4 h = make_float4(tf32_round(o.x), tf32_round(o.y), tf32_round(o.z), tf32_round(o.w));
+              *reinterpret_cast<float4 *>(p.Wout_lo + row * p.ldwo + col0 + 4 * i) =
+                  make_float4(o.x - h.x, o.y - h.y, o.z - h.z, o.w - h.w);
+              o = h;
+            }
+            *reinterpret_cast<float4 *>(wo + 4 * i) = o;
           }
         }
       }
@@ -429,6 +489,7 @@ fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_cons
       if (lane == 0) mbar_arrive_relaxed(g_empty);
       if (rb_next < p.n_blocks) fill_w(rb_next, (rbc + 1u) & 1u);
     }
+    if (p.write_q && lane == 0) bulk_wait_all();
     if (p.kl != nullptr) {
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) kl += __shfl_xor_sync(0xffffffffu, kl, o);
@@ -465,9 +526,9 @@ int make_map_ex(CUtensorMap *map, const void *base, int64_t inner, int64_t outer
 }  // namespace
 
 int fused_coef_step256(klnmf_ctx *ctx, const FusedDesc &d, int *err_dev) {
-  KL_CHECK(d.K <= PKP && d.ldw % 32 == 0 && d.ldht % 32 == 0 && d.Q == nullptr, KLNMF_EINVAL,
+  KL_CHECK(d.K <= PKP && d.ldw % 32 == 0 && d.ldht % 32 == 0, KLNMF_EINVAL,
            "fused_coef_step256: k=%lld not supported", (long long)d.K);
-  CUtensorMap tmHt, tmH, tmX;
+  CUtensorMap tmHt, tmH, tmX, tmQ;
   {
     // H^T (f x ldht) as a 3D tensor: 32 components (inner) x f feature rows x ldht/32 component blocks 128 B apart
     EncodeTiledFn enc = get_encode();
@@ -483,8 +544,15 @@ int fused_coef_step256(klnmf_ctx *ctx, const FusedDesc &d, int *err_dev) {
   }
   KL_TRY(make_map_ex(&tmH, d.H, d.F, d.K, d.ldh, 32, PKH, CU_TENSOR_MAP_SWIZZLE_128B));          // 32 features x 128 rows
   KL_TRY(make_map_ex(&tmX, d.X, d.F, d.M, d.ldx, PHN, PBM, CU_TENSOR_MAP_SWIZZLE_128B));         // 32 features x 128 rows
+  tmQ = tmX;
+  if (d.Q != nullptr) {      // fit: one 32-feature x 32-row box per warp and step, clipped at the edges of the panel
+    KL_CHECK(d.ldq >= round_up(d.F, 4), KLNMF_EINVAL, "fused_coef_step256: ratio panel leading dimension too small");
+    KL_TRY(make_map_ex(&tmQ, d.Q, d.F, d.M, d.ldq, PHN, 32, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
   Fused256Params p{};
   p.M = d.M; p.F = d.F;
+  p.Wlo = (const float *)d.Wlo; p.Wout_lo = (float *)d.Wout_lo; p.accurate = d.accurate;
+  p.write_q = d.Q != nullptr ? 1 : 0;
   p.n_blocks = (int)ceil_div(d.M, PBM);
   p.n_steps = (int)ceil_div(d.F, PBN);
   p.n_kb = (int)(d.ldw / 32);
@@ -501,7 +569,7 @@ int fused_coef_step256(klnmf_ctx *ctx, const FusedDesc &d, int *err_dev) {
     KL_CUDA(cudaFuncSetAttribute(fused_coef256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
     attr_done = true;
   }
-  fused_coef256_kernel<<<clusters * 2, P_THREADS, P_SMEM_BYTES, ctx->stream>>>(tmHt, tmH, tmX, p);
+  fused_coef256_kernel<<<clusters * 2, P_THREADS, P_SMEM_BYTES, ctx->stream>>>(tmHt, tmH, tmX, tmQ, p);
   ctx->n_launch++;
   KL_CUDA(cudaGetLastError());
   return KLNMF_OK;

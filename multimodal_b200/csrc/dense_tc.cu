@@ -824,10 +824,12 @@ int tc_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d) {
   // operands MN-major).  KLNMF_TC_WIDE=0 keeps the 256 x 256 pair tiles for comparison.
   static const bool wide = !(getenv("KLNMF_TC_WIDE") && atoi(getenv("KLNMF_TC_WIDE")) == 0) &&
                            !(getenv("KLNMF_TC_CG") && atoi(getenv("KLNMF_TC_CG")) == 1);
+  static const bool wide_n = !(getenv("KLNMF_TC_WIDE_N") && atoi(getenv("KLNMF_TC_WIDE_N")) == 0);
+  static const bool wide_m = !(getenv("KLNMF_TC_WIDE_M") && atoi(getenv("KLNMF_TC_WIDE_M")) == 0);
   if (wide && !split && !force) {
-    if (!a_mn && !b_mn && d.N > 256 && (epi == EPI_MULW || epi == EPI_STORE))
+    if (wide_n && !a_mn && !b_mn && d.N > 256 && (epi == EPI_MULW || epi == EPI_STORE))
       return launch_cfg<512, false, false, false, false, 2>(ctx, d, p);
-    if (a_mn && b_mn && d.M > 256 && d.N > 128 && epi == EPI_ACC)
+    if (wide_m && a_mn && b_mn && d.M > 256 && d.N > 128 && epi == EPI_ACC)
       return launch_cfg<256, true, true, false, false, 2, 2, false, 2>(ctx, d, p);
   }
   if (!a_mn && !b_mn) return launch_major<false, false>(ctx, d, p, split, narrow);

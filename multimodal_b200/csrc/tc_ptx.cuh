@@ -240,8 +240,10 @@ __device__ __forceinline__ float ratio_term(float x, float s, float &q) {
 // u = (x - s)/d = q - 1 and P(u) = log1p(u) - u:
 //     x log(q) - x + s  =  x P(u) + (x - s)(x - s - eps)/d
 // -- every product on the right is small when the fit has converged, where the left side cancels x log(q) against
-// s - x.  P(u) is a short polynomial for |u| < 1/4 (truncation 3.5e-7 u^2) and ln2 * lg2.approx(q) - u beyond, where
-// |P| >= 0.023 makes the 1e-7 of the MUFU harmless.  q = (x + eps) * rcp(d) with one Newton step on the reciprocal.
+// s - x.  Used for |u| < 1/4 with P(u) a short polynomial (truncation 3.5e-7 u^2); beyond, the left side is evaluated
+// as it stands with lg2.approx (|log q| >= 0.22 there, and for large u the right side would cancel x u against
+// (x - s) u instead: measured 1.7e-4 on the objective of tests' rise_case, whose ratios reach 1e3).
+// q = (x + eps) * rcp(d) with one Newton step on the reciprocal.
 __device__ __forceinline__ float ratio_term_cf(float x, float s, float &q) {
   const float d = s + (float)KL_EPS;
   float r = rcp_approx(d);
@@ -259,9 +261,11 @@ __device__ __forceinline__ float ratio_term_cf(float x, float s, float &q) {
   R = fmaf(R, u, 1.f / 3.f);
   R = fmaf(R, u, -0.5f);
   const float p_small = u * u * R;
-  const float p_large = fmaf(0.69314718055994531f, lg2_approx(fmaxf(q, 1e-37f)), -u);
-  const float P = fabsf(u) < 0.25f ? p_small : p_large;
-  return fmaf(x, P, xs * (xs - (float)KL_EPS) * r);
+  // |u| >= 1/4: the plain form -- there |log q| >= 0.22 makes the MUFU's 1e-7 harmless, and the products of the
+  // cancellation-free form (x u against (x - s) u) would themselves cancel once u is large
+  const float t_large = fmaf(x * 0.69314718055994531f, lg2_approx(fmaxf(q, 1e-37f)), -xs);
+  const float t_small = fmaf(x, p_small, xs * (xs - (float)KL_EPS) * r);
+  return fabsf(u) < 0.25f ? t_small : t_large;
 }
 // ---- the same two forms on PAIRS of elements with the packed FP32 instructions of sm_100 (fma/add/mul.f32x2 ->
 // FFMA2 / FADD2 / FMUL2: two FP32 operations per issue slot).  The ratio epilogue is bound by the issue rate of its
@@ -328,18 +332,18 @@ __device__ __forceinline__ f32x2_t ratio_pair_cf(f32x2_t x, f32x2_t s, f32x2_t &
   R = fma2(R, u, splat2(1.f / 3.f));
   R = fma2(R, u, splat2(-0.5f));
   const f32x2_t p_small = mul2(mul2(u, u), R);
-  float q0, q1, u0, u1, ps0, ps1;
+  const f32x2_t tail = mul2(mul2(xs, add2(xs, splat2(-(float)KL_EPS))), r);
+  const f32x2_t t_small = fma2(x, p_small, tail);
+  float q0, q1, u0, u1, ts0, ts1, tl0, tl1;
   unpack2(q, q0, q1);
   unpack2(u, u0, u1);
-  unpack2(p_small, ps0, ps1);
   // q > 0 in exact arithmetic; the clamp keeps lg2 finite where x = 0 and (x+eps) * r underflows
   const f32x2_t l = pack2(lg2_approx(fmaxf(q0, 1e-37f)), lg2_approx(fmaxf(q1, 1e-37f)));
-  const f32x2_t p_large = fma2(l, splat2(0.69314718055994531f), mul2(u, splat2(-1.f)));
-  float pl0, pl1;
-  unpack2(p_large, pl0, pl1);
-  const f32x2_t P = pack2(fabsf(u0) < 0.25f ? ps0 : pl0, fabsf(u1) < 0.25f ? ps1 : pl1);
-  const f32x2_t tail = mul2(mul2(xs, add2(xs, splat2(-(float)KL_EPS))), r);
-  return fma2(x, P, tail);
+  // |u| >= 1/4: the plain form x ln q + (s - x) (see ratio_term_cf)
+  const f32x2_t t_large = fma2(mul2(x, splat2(0.69314718055994531f)), l, fma2(x, splat2(-1.f), s));
+  unpack2(t_small, ts0, ts1);
+  unpack2(t_large, tl0, tl1);
+  return pack2(fabsf(u0) < 0.25f ? ts0 : tl0, fabsf(u1) < 0.25f ? ts1 : tl1);
 }
 __device__ __forceinline__ float tf32_round(float v) {
   uint32_t u;

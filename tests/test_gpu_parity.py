@@ -1,13 +1,8 @@
 """-m gpu: the CUDA path (through the drop-in Python API -> C ABI) against the golden vectors
 produced by the real reference and against the float64 oracle on the same seeds.
 
-Stated tolerances (norm-relative on W, H after 10 iterations; relative on the KL objective):
-    fp64    1e-9            DMMA float64, only the summation order differs
-    tf32x3  2e-5 / 2e-5     split-TF32 contractions are FP32-grade (measured ~1e-7 in emulation)
-    tf32    3e-3 / 1e-2     one-pass TF32 (measured 1.5e-4 / 3e-3 in emulation)
-    tf32r   5e-4 / 5e-4 (1e-3 on a converged fit)  one pass on round-to-nearest TF32 copies, centered ratio, cancellation-free objective
-                            (measured 1.3e-5..3.9e-5 / 3e-6..2.8e-5 against the FP64 mode at k, f >= 64,
-                            tools/accuracy_vs_shape.py; the 2^-12 operand rounding does not average out at k = 2)
+Stated tolerances: about 3 x the worst value measured on the B200 (profiles/r2_parity_measured.json, written by the
+`within` fixture of conftest.py); the table is TOL_* below, DESIGN.md section 2 explains each mode.
 """
 import numpy as np
 import pytest
@@ -24,11 +19,15 @@ MODES = ["fp64", "tf32x3", "tf32r", "tf32"]
 # stated tolerances = about 3 x the worst value measured on the B200 (profiles/r2_parity_measured.json, written by the
 # `within` fixture of conftest.py); k, f >= 6 cases.  The 6 x 2, k = 2 known-answer case has its own row: nothing
 # averages the operand rounding of the one-pass modes there.
-TOL_WH = {"fp64": 1e-9, "tf32x3": 2e-5, "tf32r": 5e-4, "tf32": 3e-3}
-TOL_KL = {"fp64": 1e-9, "tf32x3": 2e-5, "tf32r": 5e-4, "tf32": 1e-2}
-TOL_KL_LONG = {"fp64": 1e-9, "tf32x3": 2e-5, "tf32r": 1e-3, "tf32": 1e-2}      # converged fit: objective small against sum(X)
-TOL_KAT_WH = {"fp64": 1e-9, "tf32x3": 2e-5, "tf32r": 5e-4, "tf32": 3e-3}
-TOL_KAT_KL = {"fp64": 1e-8, "tf32x3": 2e-4, "tf32r": 1e-2, "tf32": 1e-1}
+TOL_WH = {"fp64": 1e-12, "tf32x3": 3e-6, "tf32r": 8e-4, "tf32": 1e-3}        # measured: 1e-15, 1.1e-6, 2.7e-4, 2.8e-4
+TOL_KL = {"fp64": 1e-12, "tf32x3": 3e-6, "tf32r": 2e-5, "tf32": 2e-3}        # measured: 4e-16, 9.1e-7, 5.1e-6, 7.3e-4
+TOL_KL_LONG = {"fp64": 1e-12, "tf32x3": 4e-6, "tf32r": 1e-3, "tf32": 1e-2}   # converged fit (objective small against sum(X)): 2e-15, 1.1e-6, 3.6e-4, 3.2e-3
+TOL_KAT_WH = {"fp64": 1e-12, "tf32x3": 5e-7, "tf32r": 8e-4, "tf32": 1.2e-3}  # measured: 2.7e-16, 1.4e-7, 2.6e-4, 3.7e-4
+TOL_KAT_KL = {"fp64": 1e-12, "tf32x3": 6e-6, "tf32r": 6e-3, "tf32": 5e-3}    # measured: 5.4e-15, 2.1e-6, 2.2e-3, 1.7e-3
+# shapes with k >= 256 (test_mid_size_dense_vs_oracle, test_k512_ragged_dense_vs_oracle): the FP32 accumulation of the
+# objective over k terms shows in tf32x3 (4.2e-5 at k = 512)
+TOL_KL_WIDE = {"fp64": 1e-12, "tf32x3": 1.5e-4, "tf32r": 1.5e-4, "tf32": 4e-3}
+TOL_WH_WIDE = {"fp64": 1e-12, "tf32x3": 2e-5, "tf32r": 1e-4, "tf32": 2e-4}
 
 
 def maxrel(a, b):
@@ -135,7 +134,7 @@ def test_early_stop_golden(golden, within, mode, capsys):
 
 
 @pytest.mark.parametrize("mode", MODES)
-def test_tol0_breaks_on_a_rise_like_the_reference(golden, mode):
+def test_tol0_breaks_on_a_rise_like_the_reference(golden, within, mode):
     """tol = 0 (the learner's idiom, learner.py:12,39): the reference breaks iff the objective RISES (nmf.py:215).
     With this adversarial initial dictionary it does, at the second objective evaluation, by 73 % -- far above any
     mode's noise floor, so every mode has to stop exactly there and hand back the state after ONE update."""
@@ -145,9 +144,11 @@ def test_tol0_breaks_on_a_rise_like_the_reference(golden, mode):
     est._init_dictionary = H0
     W, errs = est.fit_transform(X, return_errors=True)
     assert len(g["errors"]) == 1 and len(errs) == 1
-    tol = {"fp64": 1e-9, "tf32x3": 1e-5, "tf32r": 2e-3, "tf32": 5e-3}[mode]
-    np.testing.assert_allclose(errs, g["errors"], rtol=tol)
-    assert cases.rel_fro(W, g["W"]) < tol and cases.rel_fro(est.components_, g["H"]) < tol
+    # the ratios of this case reach 1e3 and the dictionary spans 8 decades: W.H itself is what limits the one-pass modes
+    tol = {"fp64": 1e-12, "tf32x3": 1e-5, "tf32r": 2e-3, "tf32": 5e-3}[mode]
+    within("objective", maxrel(errs, g["errors"]), tol)
+    within("W", cases.rel_fro(W, g["W"]), tol)
+    within("H", cases.rel_fro(est.components_, g["H"]), tol)
     # ... and the objective of the returned state is indeed the larger one the reference saw and refused
     assert est.error(X, W) > errs[0] * 1.5
 
@@ -184,9 +185,9 @@ def test_mid_size_dense_vs_oracle(within, mode):
     np.random.seed(9)
     Wr, Hr, er, _ = O.fit_transform(X, k=k, max_iter=10, tol=0)
     est, W, errs = fit(X, k, 10, 9, mode)
-    within("W", cases.rel_fro(W, Wr), TOL_WH[mode])
-    within("H", cases.rel_fro(est.components_, Hr), TOL_WH[mode])
-    within("objective", maxrel(errs, er), TOL_KL[mode])
+    within("W", cases.rel_fro(W, Wr), TOL_WH_WIDE[mode])
+    within("H", cases.rel_fro(est.components_, Hr), TOL_WH_WIDE[mode])
+    within("objective", maxrel(errs, er), TOL_KL_WIDE[mode])
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -201,9 +202,9 @@ def test_k512_ragged_dense_vs_oracle(within, mode, n, f):
     np.random.seed(21)
     Wr, Hr, er, _ = O.fit_transform(X, k=512, max_iter=10, tol=0)
     est, W, errs = fit(X, 512, 10, 21, mode)
-    within("W", cases.rel_fro(W, Wr), TOL_WH[mode])
-    within("H", cases.rel_fro(est.components_, Hr), TOL_WH[mode])
-    within("objective", maxrel(errs, er), max(TOL_KL[mode], 1e-4 if mode == "tf32x3" else 0))
+    within("W", cases.rel_fro(W, Wr), TOL_WH_WIDE[mode])
+    within("H", cases.rel_fro(est.components_, Hr), TOL_WH_WIDE[mode])
+    within("objective", maxrel(errs, er), TOL_KL_WIDE[mode])
 
 
 @pytest.mark.parametrize("n,f,k", [(600, 700, 300), (520, 300, 700)])
@@ -216,9 +217,9 @@ def test_ragged_component_counts_beyond_one_tile(within, n, f, k):
     Wr, Hr, er, _ = O.fit_transform(X, k=k, max_iter=6, tol=0)
     for mode in ("tf32r", "tf32"):
         est, W, errs = fit(X, k, 6, 22, mode)
-        within(mode + "_W", cases.rel_fro(W, Wr), TOL_WH[mode])
-        within(mode + "_H", cases.rel_fro(est.components_, Hr), TOL_WH[mode])
-        within(mode + "_objective", maxrel(errs, er), TOL_KL[mode])
+        within(mode + "_W", cases.rel_fro(W, Wr), TOL_WH_WIDE[mode])
+        within(mode + "_H", cases.rel_fro(est.components_, Hr), TOL_WH_WIDE[mode])
+        within(mode + "_objective", maxrel(errs, er), TOL_KL_WIDE[mode])
 
 
 def test_multi_panel_equals_single_panel():

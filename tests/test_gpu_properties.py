@@ -32,7 +32,7 @@ def transform(X, H, iters, mode):
     return est.transform(X)
 
 
-@pytest.mark.parametrize("mode,k", [("tf32", 256), ("tf32", 100), ("tf32x3", 256), ("fp64", 64)])
+@pytest.mark.parametrize("mode,k", [("tf32r", 256), ("tf32r", 100), ("tf32", 256), ("tf32", 100), ("tf32x3", 256), ("fp64", 64)])
 def test_transform_rows_are_independent(mode, k):
     rs = np.random.RandomState(3)
     n, f = 1500, 1024
@@ -146,7 +146,7 @@ def run_cfg3(n, fused256):
     H = O.init_dictionary(k, f)
     os.environ["KLNMF_FUSED256"] = "1" if fused256 else "0"
     try:
-        with _native.Engine(n, f, k, mode="tf32") as e:
+        with _native.Engine(n, f, k, mode=_native.DEFAULT_MODE) as e:
             e.fill_dense_synthetic(6)
             e.set_dictionary(H)
             e.init_coefficients()
@@ -168,6 +168,6 @@ def test_cfg3_full_size_transform_fused_equals_unfused():
     assert lf < lu, "the cluster kernel must be the one that ran"
     assert Wf.shape == (n, 256) and np.isfinite(Wf).all() and (Wf >= 0).all()
     assert cases.rel_fro(Hf, H) < 1e-7            # a transform leaves the dictionary as it was (float32 storage)
-    assert ((ef[1:] - ef[:-1]) / ef[:-1] < NOISE["tf32"]).all() and ef[-1] < ef[0]
+    assert ((ef[1:] - ef[:-1]) / ef[:-1] < NOISE[_native.DEFAULT_MODE]).all() and ef[-1] < ef[0]
     np.testing.assert_allclose(ef, eu, rtol=1e-4)
-    assert cases.rel_fro(Wf, Wu) < 1e-3
+    assert cases.rel_fro(Wf, Wu) < 2e-4
