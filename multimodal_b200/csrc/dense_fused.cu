@@ -337,33 +337,7 @@ fused_coef_kernel(const __grid_constant__ CUtensorMap tmW, const __grid_constant
         if (lane == 0) { mbar_arrive_relaxed(s_empty(grp)); mbar_arrive(x_empty(xb)); }
         // rows >= M and columns >= F hold x = 0, s = 0 (TMA zero fill): q = 1, the term is exactly 0 and the
         // zero-filled dictionary columns keep it out of G
-        {
-          f32x2_t part2 = splat2(0.f);
-          const f32x2_t nshift2 = splat2(-p.qshift);
-          const bool store_u = p.accurate && p.qshift == 1.f;
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            const f32x2_t x2 = pack2(x[i], x[i + 1]);
-            const f32x2_t s2 = pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-            f32x2_t q2, out2;
-            if (p.accurate) {
-              f32x2_t u2;
-              part2 = add2(part2, ratio_pair_cf<false>(x2, s2, q2, u2));
-              out2 = store_u ? u2 : add2(q2, nshift2);
-            } else {
-              part2 = add2(part2, ratio_pair_fast(x2, s2, q2));
-              out2 = add2(q2, nshift2);
-            }
-            unpack2(out2, x[i], x[i + 1]);
-          }
-          if (p.accurate) {
-#pragma unroll
-            for (int i = 0; i < 32; i++) x[i] = tf32_round(x[i]);
-          }
-          float part0, part1;
-          unpack2(part2, part0, part1);
-          kl_blk += part0 + part1;
-        }
+        kl_blk += ratio_chunk32_dispatch(x, v, p.qshift, p.accurate);
         if (!p.only_kl) {
           mbar_wait(q_empty(grp), ph2 ^ 1u, p.err, 11);
           if (WRITE_Q) {
@@ -522,19 +496,20 @@ int fused_coef_step(klnmf_ctx *ctx, const FusedDesc &d) {
   p.kl = d.kl; p.stop = d.stop; p.err = st->err_dev; p.only_kl = d.only_kl;
   p.qshift = d.qshift; p.colbias = d.colbias;
   p.Wlo = (const float *)d.Wlo; p.Wout_lo = (float *)d.Wout_lo; p.accurate = d.accurate;
-  // default: W block in TMEM ("TS" form of tcgen05.mma); KLNMF_FUSED_TS=0 keeps it in shared memory
-  const bool ts = !(getenv("KLNMF_FUSED_TS") && atoi(getenv("KLNMF_FUSED_TS")) == 0);
+  // The W block lives in TMEM ("TS" form of tcgen05.mma).  The round-1 variant that kept it in shared memory
+  // (KLNMF_FUSED_TS=0) is gone: tools/fused_determinism.py showed it racy at k > 64 (a handful of rows off by 1e-2 in
+  // one run out of two, both arithmetic modes -- within the old 3e-3 tolerance, hence unnoticed).
   const int v = getenv("KLNMF_FUSED_V") ? atoi(getenv("KLNMF_FUSED_V")) : 0;
-  p.lookahead = d.K <= 64 && ts ? 2 : 1;
+  p.lookahead = d.K <= 64 ? 2 : 1;
   if (getenv("KLNMF_FUSED_LA")) p.lookahead = atoi(getenv("KLNMF_FUSED_LA")) == 2 ? 2 : 1;
   if (d.Q != nullptr) {   // fit: the ratio panel is written for the numerator contraction
     KL_CHECK(d.ldq >= round_up(d.F, 4), KLNMF_EINVAL, "fused_coef_step: ratio panel leading dimension too small");
     if (d.K <= 64) return launch_fused<64, true, 0, true>(ctx, d, p);
     return launch_fused<128, true, 0, true>(ctx, d, p);
   }
-  if (d.K <= 64) return ts ? launch_fused<64, true>(ctx, d, p) : launch_fused<64, false>(ctx, d, p);
-  if (ts && v == 1) return launch_fused<128, true, 1>(ctx, d, p);
-  return ts ? launch_fused<128, true>(ctx, d, p) : launch_fused<128, false>(ctx, d, p);
+  if (d.K <= 64) return launch_fused<64, true>(ctx, d, p);
+  if (v == 1) return launch_fused<128, true, 1>(ctx, d, p);
+  return launch_fused<128, true>(ctx, d, p);
 }
 
 void fused_release(klnmf_ctx *ctx) {

@@ -395,34 +395,7 @@ fused_coef256_kernel(const __grid_constant__ CUtensorMap tmHt, const __grid_cons
         tc_fence_before();
         __syncwarp();
         if (lane == 0) { mbar_arrive_relaxed(s_empty(sa)); mbar_arrive(x_empty(grp)); }
-        {
-          f32x2_t part2 = splat2(0.f);
-          const f32x2_t nshift2 = splat2(-p.qshift);
-          const bool store_u = p.accurate && p.qshift == 1.f;
-#pragma unroll
-          for (int i = 0; i < 32; i += 2) {
-            if (p.dbg & 8) break;
-            const f32x2_t x2 = pack2(x[i], x[i + 1]);
-            const f32x2_t s2 = pack2(__uint_as_float(v[i]), __uint_as_float(v[i + 1]));
-            f32x2_t q2, out2;
-            if (p.accurate) {
-              f32x2_t u2;
-              part2 = add2(part2, ratio_pair_cf<false>(x2, s2, q2, u2));
-              out2 = store_u ? u2 : add2(q2, nshift2);
-            } else {
-              part2 = add2(part2, ratio_pair_fast(x2, s2, q2));
-              out2 = add2(q2, nshift2);
-            }
-            unpack2(out2, x[i], x[i + 1]);
-          }
-          if (p.accurate) {
-#pragma unroll
-            for (int i = 0; i < 32; i++) x[i] = tf32_round(x[i]);
-          }
-          float part0, part1;
-          unpack2(part2, part0, part1);
-          kl_blk += part0 + part1;
-        }
+        if (!(p.dbg & 8)) kl_blk += ratio_chunk32_dispatch(x, v, p.qshift, p.accurate);
         // both issuers are done with Q tile `grp` (ours and the peer's, of which we write half each)
         mbar_wait(q_empty(grp), ph2 ^ 1u, p.err, 11);
         if (p.write_q) {      // ... and so is the TMA store of this warp's box two steps ago

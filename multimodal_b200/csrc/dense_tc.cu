@@ -536,36 +536,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         __syncwarp();
         if ((!QIP || p.only_kl) && lane == 0) mbar_arrive(xempty_bar(b));
         // rows >= M and columns >= N hold x = 0, s = 0 (TMA zero fill): q = 1, the term is exactly 0
-        // two elements per instruction (FFMA2 / FADD2 / FMUL2, tc_ptx.cuh): the eight epilogue warps are bound by their
-        // issue rate once the objective takes its cancellation-free form
-        f32x2_t part2 = splat2(0.f);
-        const f32x2_t nshift2 = splat2(-p.qshift);
-        const bool store_u = p.accurate && p.qshift == 1.f;     // centered ratio: q - 1 = (x - s)/(s + eps), no cancellation
-#pragma unroll
-        for (int j = 0; j < 32; j += 2) {
-          if (p.dbg & 1) break;
-          const f32x2_t x2 = pack2(x[j], x[j + 1]);
-          const f32x2_t s2 = pack2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
-          f32x2_t q2, out2;
-          if (p.accurate) {      // TF32R: the objective in its cancellation-free form
-            f32x2_t u2;
-            part2 = add2(part2, ratio_pair_cf<false>(x2, s2, q2, u2));
-            out2 = store_u ? u2 : add2(q2, nshift2);
-          } else {
-            part2 = add2(part2, ratio_pair_fast(x2, s2, q2));
-            out2 = add2(q2, nshift2);
-          }
-          unpack2(out2, x[j], x[j + 1]);
-        }
-        if (p.round_out) {     // TF32R: the consumers multiply exactly what is stored (the tensor core would truncate)
-#pragma unroll
-          for (int j = 0; j < 32; j++) x[j] = tf32_round(x[j]);
-        }
-        {
-          float part0, part1;
-          unpack2(part2, part0, part1);
-          kl_tile += part0 + part1;
-        }
+        // two elements per instruction (FFMA2 / FADD2 / FMUL2) and the arithmetic mode as a template parameter
+        // (ratio_chunk32, tc_ptx.cuh): the eight epilogue warps are bound by their issue rate once the objective takes
+        // its cancellation-free form.  TF32R (accurate): the consumers multiply exactly what is stored (rounded to
+        // nearest; the tensor core would truncate)
+        if (!(p.dbg & 1)) kl_tile += ratio_chunk32_dispatch(x, v, p.qshift, p.accurate);
         if (!p.only_kl) {
           if (QIP) {
             // in place: every thread overwrites the row of X it has just read; the warp's 32 rows are one 4 KB box

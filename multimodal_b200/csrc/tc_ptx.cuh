@@ -345,6 +345,47 @@ __device__ __forceinline__ f32x2_t ratio_pair_cf(f32x2_t x, f32x2_t s, f32x2_t &
   unpack2(t_large, tl0, tl1);
   return pack2(fabsf(u0) < 0.25f ? ts0 : tl0, fabsf(u1) < 0.25f ? ts1 : tl1);
 }
+__device__ __forceinline__ float tf32_round(float v);
+// One 32-element chunk of the ratio epilogue held by its row-owning thread: x[] holds the data on entry and the stored
+// ratio values (q - qshift; ACC && STORE_U: u = q - 1 itself; ACC: rounded to nearest TF32) on exit; returns the chunk's
+// objective partial.  The arithmetic mode is a TEMPLATE parameter on purpose: a run-time branch inside the unrolled loop
+// keeps the compiler from interleaving the 16 independent pairs, and their ~130-cycle dependent chains then run one
+// after the other (measured: the fused k = 256 kernel 9.2 -> 12.2 ms).
+template <bool ACC, bool STORE_U>
+__device__ __forceinline__ float ratio_chunk32(float x[32], const uint32_t v[32], float qshift) {
+  f32x2_t part2 = splat2(0.f);
+  const f32x2_t nshift2 = splat2(-qshift);
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    const f32x2_t x2 = pack2(x[j], x[j + 1]);
+    const f32x2_t s2 = pack2(__uint_as_float(v[j]), __uint_as_float(v[j + 1]));
+    f32x2_t q2, out2;
+    if (ACC) {
+      f32x2_t u2;
+      part2 = add2(part2, ratio_pair_cf<false>(x2, s2, q2, u2));
+      out2 = STORE_U ? u2 : add2(q2, nshift2);
+    } else {
+      part2 = add2(part2, ratio_pair_fast(x2, s2, q2));
+      out2 = add2(q2, nshift2);
+    }
+    unpack2(out2, x[j], x[j + 1]);
+  }
+  if (ACC) {
+#pragma unroll
+    for (int j = 0; j < 32; j++) x[j] = tf32_round(x[j]);
+  }
+  float p0, p1;
+  unpack2(part2, p0, p1);
+  return p0 + p1;
+}
+// run-time mode -> template instance (one warp-uniform branch per chunk, outside the loop)
+__device__ __forceinline__ float ratio_chunk32_dispatch(float x[32], const uint32_t v[32], float qshift, int accurate) {
+  if (accurate) {
+    if (qshift == 1.f) return ratio_chunk32<true, true>(x, v, qshift);
+    return ratio_chunk32<true, false>(x, v, qshift);
+  }
+  return ratio_chunk32<false, false>(x, v, qshift);
+}
 __device__ __forceinline__ float tf32_round(float v) {
   uint32_t u;
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(u) : "f"(v));

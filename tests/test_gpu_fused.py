@@ -31,9 +31,9 @@ SHAPES = [
 
 
 MODES = ["tf32r", "tf32"]
-TOL_W = {"tf32r": 3e-4, "tf32": 1e-3}          # against the oracle
-TOL_KL = {"tf32r": 1e-4, "tf32": 4e-3}
-TOL_SAME = {"tf32r": 2e-4, "tf32": 1e-3}       # fused against unfused: same arithmetic up to the FP32 summation order
+TOL_W = {"tf32r": 6e-4, "tf32": 1.3e-3}        # against the oracle; measured worst 2.1e-4 / 4.3e-4 (k = 8, f = 32)
+TOL_KL = {"tf32r": 5e-5, "tf32": 6e-3}         # measured worst 1.7e-5 / 2.0e-3
+TOL_SAME = {"tf32r": 1.7e-4, "tf32": 1.1e-4}   # fused against unfused (same arithmetic up to the FP32 summation order): 5.6e-5 / 3.6e-5
 
 
 def maxrel(a, b):
@@ -41,9 +41,8 @@ def maxrel(a, b):
     return float(np.max(np.abs(a - b) / np.abs(b)))
 
 
-def run_transform(X, H, iters, fused, ts=False, mode="tf32"):
+def run_transform(X, H, iters, fused, ts=True, mode="tf32"):
     os.environ["KLNMF_FUSED"] = "1" if fused else "0"
-    os.environ["KLNMF_FUSED_TS"] = "1" if ts else "0"
     try:
         n, f = X.shape
         with _native.Engine(n, f, H.shape[0], mode=mode) as e:
@@ -56,7 +55,6 @@ def run_transform(X, H, iters, fused, ts=False, mode="tf32"):
             return e.get_coefficients(), np.asarray(errs), launches
     finally:
         os.environ.pop("KLNMF_FUSED", None)
-        os.environ.pop("KLNMF_FUSED_TS", None)
 
 
 def oracle_transform(X, H, iters):
@@ -76,9 +74,8 @@ def zero_heavy(n, f, k, frac=0.2):
 
 
 @pytest.mark.parametrize("mode", MODES)
-@pytest.mark.parametrize("ts", [False, True], ids=["w_in_smem", "w_in_tmem"])
 @pytest.mark.parametrize("n,f,k", SHAPES)
-def test_fused_transform_matches_oracle_and_unfused(within, n, f, k, ts, mode):
+def test_fused_transform_matches_oracle_and_unfused(within, n, f, k, mode, ts=True):
     X = zero_heavy(n, f, k)
     np.random.seed(5)
     H = O.init_dictionary(k, f)
@@ -91,7 +88,7 @@ def test_fused_transform_matches_oracle_and_unfused(within, n, f, k, ts, mode):
     within("W", cases.rel_fro(Wf, W_ref), TOL_W[mode])
     within("objective", maxrel(ef, errs_ref), TOL_KL[mode])
     within("W_fused_vs_unfused", cases.rel_fro(Wf, Wu), TOL_SAME[mode])
-    within("objective_fused_vs_unfused", maxrel(ef, eu), 1e-4)
+    within("objective_fused_vs_unfused", maxrel(ef, eu), 5e-6)
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -110,7 +107,7 @@ def test_fused_pair_transform_k256(within, n, f, k, mode):
     within("W", cases.rel_fro(Wf, W_ref), TOL_W[mode])
     within("objective", maxrel(ef, errs_ref), TOL_KL[mode])
     within("W_fused_vs_unfused", cases.rel_fro(Wf, Wu), TOL_SAME[mode])
-    within("objective_fused_vs_unfused", maxrel(ef, eu), 1e-4)
+    within("objective_fused_vs_unfused", maxrel(ef, eu), 5e-6)
 
 
 @pytest.mark.parametrize("mode", MODES)
@@ -127,7 +124,7 @@ def test_fused_transform_through_the_estimator(within, mode):
     W_ref = np.asarray(X.dot(H.T))
     for _ in range(25):
         W_ref, _ = O.update(X, W_ref, H, fit=False)
-    within("W", cases.rel_fro(W, W_ref), 1e-3)
+    within("W", cases.rel_fro(W, W_ref), TOL_W[mode])
 
 
 def run_fit(X, H, iters, fused, mode="tf32"):

@@ -4,7 +4,7 @@
 #   gpurun --timeout 900 -- 'tools/gpu.sh LABEL STEP [STEP ...]'
 #
 # Every STEP is one of (arguments separated by ':'), all output lands in gpurun_out/LABEL.log:
-#   tests[:PYTEST_K]                  python -m pytest tests -m gpu -x -q [-k PYTEST_K]
+#   tests[:PYTEST_K]                  python -m pytest tests -m gpu -x -q [-k PYTEST_K]   (testsall: without -x)
 #   smoke                             __graft_entry__.smoke()
 #   phases:WORKLOAD:N:MODE[:ENV=V,..] bench.py --workload WORKLOAD --n N --mode MODE, prints ms/step + phase times
 #   bench[:ARGS]                      python bench.py ARGS (comma separated), prints the JSON line
@@ -27,6 +27,7 @@ for STEP in "$@"; do
   echo "=== $STEP"
   case $KIND in
     tests)   timeout 1500 python -m pytest tests -m gpu -x -q ${A1:+-k "$A1"} 2>&1 | tail -15 ;;
+    testsall) timeout 1500 python -m pytest tests -m gpu -q ${A1:+-k "$A1"} 2>&1 | tail -40 ;;
     smoke)   timeout 600 python -c 'import __graft_entry__ as g; g.smoke()' 2>&1 | tail -12 ;;
     phases)  env KLNMF_PROFILE=1 $(echo "$A4" | tr ',' ' ') timeout 900 python bench.py --workload "$A1" ${A2:+--n "$A2"} --mode "$A3" --no-cpu --no-e2e --alt-mode= --no-extra 2>&1 | tail -1 | python -c "$P" ;;
     bench)   timeout 1800 python bench.py $(echo "$A1" | tr ',' ' ') 2>&1 | tail -3 ;;
