@@ -799,7 +799,10 @@ int tc_gemm(klnmf_ctx *ctx, int epi, const GemmDesc &d) {
   // operands MN-major).  KLNMF_TC_WIDE=0 keeps the 256 x 256 pair tiles for comparison.
   static const bool wide = !(getenv("KLNMF_TC_WIDE") && atoi(getenv("KLNMF_TC_WIDE")) == 0) &&
                            !(getenv("KLNMF_TC_CG") && atoi(getenv("KLNMF_TC_CG")) == 1);
-  static const bool wide_n = !(getenv("KLNMF_TC_WIDE_N") && atoi(getenv("KLNMF_TC_WIDE_N")) == 0);
+  // 256 x 512 for the coefficient contraction is OFF by default: its single-buffered accumulator exposes the epilogue
+  // (W hi + lo in, W' hi + lo out), and at the cfg5 shape that costs more than the narrower operand stream saves
+  // (n = 262144: 3.00 ms with 256 x 256 tiles, 3.60 ms wide; profiles/r2_run5.log).  KLNMF_TC_WIDE_N=1 selects it.
+  static const bool wide_n = getenv("KLNMF_TC_WIDE_N") && atoi(getenv("KLNMF_TC_WIDE_N")) == 1;
   static const bool wide_m = !(getenv("KLNMF_TC_WIDE_M") && atoi(getenv("KLNMF_TC_WIDE_M")) == 0);
   if (wide && !split && !force) {
     if (wide_n && !a_mn && !b_mn && d.N > 256 && (epi == EPI_MULW || epi == EPI_STORE))

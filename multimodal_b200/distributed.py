@@ -93,6 +93,9 @@ def _in_threads(fns):
         t.start()
     for t in ts:
         t.join()
+    real = [e for e in errs if e is not None and not isinstance(e, threading.BrokenBarrierError)]
+    if real:
+        raise real[0]                      # the cause, not the BrokenBarrierError it gave the other threads
     for e in errs:
         if e is not None:
             raise e

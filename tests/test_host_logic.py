@@ -162,3 +162,31 @@ def test_stack_data_of_dense_modalities_is_lazy_and_equals_the_reference_formula
     assert isinstance(lr.stack_data(['b'], [b]), np.ndarray)     # one modality: a plain scaled copy, as before
     mixed = lr.stack_data(['a', 'b'], [a, sp.csr_matrix(b)])     # any sparse block makes the stack sparse
     assert sp.issparse(mixed) and mixed.shape == (7, 8)
+
+
+def test_device_group_host_helpers():
+    # the host side of KLdivNMF(device=[...]) (distributed.DeviceGroup): row blocks of every input kind, the thread
+    # helper's error propagation (the cause wins over the BrokenBarrierError it gives the other threads)
+    import threading
+    from multimodal_b200 import distributed as D
+    from multimodal_b200.lib.array_utils import StackedBlocks
+    rs = np.random.RandomState(1)
+    a, b = rs.random_sample((9, 3)), rs.random_sample((9, 2)).astype(np.float32)
+    st = D._rows(StackedBlocks([a, b], [2., .5]), 4, 9)
+    assert isinstance(st, StackedBlocks) and st.shape == (5, 5)
+    np.testing.assert_array_equal(st.toarray(), np.hstack([2. * a[4:9], .5 * b[4:9]]))
+    assert D._rows(a, 2, 5).base is a                                   # dense: a view, no copy
+    Xs = sp.csr_matrix(a)
+    np.testing.assert_array_equal(D._rows(Xs, 3, 7).toarray(), a[3:7])
+    assert D.shard_bounds(1001, 2) == [0, 501, 1001] and D.shard_bounds(3, 8)[-1] == 3
+    assert D._in_threads([lambda: 1, lambda: 2]) == [1, 2]
+    gate = threading.Barrier(2)
+
+    def boom():
+        gate.abort()
+        raise MemoryError("cause")
+
+    def waits():
+        gate.wait()
+    with pytest.raises(MemoryError, match="cause"):
+        D._in_threads([waits, boom])
