@@ -55,6 +55,7 @@ def parse():
     ap.add_argument("--alt-mode", default=os.environ.get("KLNMF_BENCH_ALT", "tf32,tf32x3"),
                     help="further arithmetic modes reported under alt_modes, comma separated ('' to skip)")
     ap.add_argument("--no-extra", action="store_true", help="skip the cfg3 / cfg4 entries under `workloads`")
+    ap.add_argument("--no-balance", action="store_true", help="several ranks: keep the equal split of the samples")
     ap.add_argument("--e2e-iters", type=int, default=50,
                     help="second end-to-end call at the reference's iteration count (experiment.py:20-25); 0 to skip")
     args = ap.parse_args()
@@ -447,10 +448,34 @@ def measure_workload(args, name, mode, ctx, with_clocks, keep_engine=False, step
     H0 = H0 / (1.e-16 + H0.sum(axis=1, keepdims=True))
     if dist is not None:
         H0 = D.broadcast_object(H0, 0)
-    x_bytes = n_local * f * (8 if mode == "fp64" else 4)
-    # leave room for X + the W ping-pong (+ lo parts) on a 192 GB part
-    scratch = (8 << 30) if x_bytes > (100 << 30) else (16 << 30)
-    eng = make_engine(_native, n_local, f, k, kind, mode, local, rank, world, H0, scratch)
+
+    def build(rows):
+        x_bytes = rows * f * (8 if mode == "fp64" else 4)
+        # leave room for X + the W ping-pong (+ lo parts) on a 192 GB part
+        scratch = (8 << 30) if x_bytes > (100 << 30) else (16 << 30)
+        return make_engine(_native, rows, f, k, kind, mode, local, rank, world, H0, scratch)
+
+    eng = build(n_local)
+    balance = None
+    if dist is not None and fit and not args.no_balance:
+        # Every fit iteration ends in an all-reduce that waits for the slowest shard, and the GPUs of one box differ by
+        # several per cent under their power caps.  Calibrate on the equal split (untimed), then size the shards in
+        # proportion to the measured samples per second of each GPU (distributed.shard_bounds(weights=...)).
+        import torch
+        eng.run(max(warmup, 5), -float("inf"), fit)
+        ms_cal, _ = eng.last_run_profile()
+        t_local = sum(ms_cal[p_] for p_ in ("ratio", "coefficient", "numerator", "dictionary"))
+        t = torch.tensor([n_local / max(t_local, 1e-6)], dtype=torch.float64, device="cuda:%d" % local)
+        allv = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allv, t)
+        speeds = [float(v.item()) for v in allv]
+        bounds = D.shard_bounds(n_total, world, weights=speeds)
+        balance = {"rows_per_rank": [bounds[r + 1] - bounds[r] for r in range(world)],
+                   "relative_speed": [s_ / max(speeds) for s_ in speeds],
+                   "note": "shards sized by each GPU's measured samples/s on an untimed calibration run of the equal split"}
+        eng.close()
+        n_local = bounds[rank + 1] - bounds[rank]
+        eng = build(n_local)
     sampler = ClockSampler(local) if with_clocks else None
     if sampler:
         sampler.start()
@@ -458,6 +483,7 @@ def measure_workload(args, name, mode, ctx, with_clocks, keep_engine=False, step
     clocks = sampler.stop() if sampler else None
     roof = phase_roofline(ms, cnt, n_local, f, k, kind, steps, peaks, mode)
     roof["phase_ms_per_step_min_max_over_ranks"] = gather_phases(dist, local, ms, steps)
+    roof["shard_balance"] = balance
     out = {"value": steps / (total_ms * 1e-3), "ms_per_step": total_ms / steps, "steps": steps, "warmup": warmup,
            "launches": int(launches), "roofline": roof, "clocks": clocks, "desc": desc, "n_total": n_total, "f": f, "k": k,
            "kind": kind, "n_local": n_local, "H0": H0, "errs": errs}

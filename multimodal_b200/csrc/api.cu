@@ -176,12 +176,14 @@ int download_large(klnmf_ctx *ctx, const void *src, const void *src_lo, int64_t 
   constexpr int64_t kPin = (int64_t)64 << 20;
   // the two pinned buffers are process-wide (pinning / unpinning 128 MB costs ~0.3 s per context otherwise) and
   // held for the duration of one download
-  static std::mutex pin_mutex;
-  static void *g_pin[2] = {nullptr, nullptr};
-  std::lock_guard<std::mutex> pin_lock(pin_mutex);
+  // (one pair per DEVICE: the shards of a multi-GPU call download concurrently, one host thread each)
+  static std::mutex pin_mutex[64];
+  static void *g_pin[64][2] = {};
+  const int slot = ctx->device & 63;
+  std::lock_guard<std::mutex> pin_lock(pin_mutex[slot]);
   for (int b = 0; b < 2; b++) {
-    if (!g_pin[b]) KL_CUDA(cudaHostAlloc(&g_pin[b], kPin, cudaHostAllocPortable));
-    ctx->pin_stage[b] = g_pin[b];
+    if (!g_pin[slot][b]) KL_CUDA(cudaHostAlloc(&g_pin[slot][b], kPin, cudaHostAllocPortable));
+    ctx->pin_stage[b] = g_pin[slot][b];
   }
   int64_t chunk = kPin / (cols * des);
   if (chunk < 1) chunk = 1;

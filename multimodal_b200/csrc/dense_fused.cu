@@ -450,10 +450,11 @@ int launch_fused(klnmf_ctx *ctx, const FusedDesc &d, FusedParams p) {
   if (p.n_blocks == 0 || p.n_steps == 0) return KLNMF_OK;
   const int grid = p.n_blocks < ctx->sm_count ? p.n_blocks : ctx->sm_count;
   auto kern = fused_coef_kernel<KP, WRITE_Q, TSW, V>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  // per DEVICE: function attributes live in the device's context, and one process may drive several GPUs
+  static bool attr_done[64] = {};
+  if (!attr_done[ctx->device & 63]) {
     KL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_done = true;
+    attr_done[ctx->device & 63] = true;
   }
   kern<<<grid, F_THREADS, C::SMEM_BYTES, ctx->stream>>>(tmW, tmHt, tmH, tmX, tmQ, p);
   ctx->n_launch++;

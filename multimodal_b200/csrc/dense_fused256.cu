@@ -537,10 +537,11 @@ int fused_coef_step256(klnmf_ctx *ctx, const FusedDesc &d, int *err_dev) {
   p.dbg = getenv("KLNMF_F256_DBG") ? atoi(getenv("KLNMF_F256_DBG")) : 0;
   if (p.n_blocks == 0 || p.n_steps == 0) return KLNMF_OK;
   const int clusters = p.n_blocks < ctx->sm_count / 2 ? p.n_blocks : ctx->sm_count / 2;
-  static bool attr_done = false;
-  if (!attr_done) {
+  // per DEVICE: function attributes live in the device's context, and one process may drive several GPUs
+  static bool attr_done[64] = {};
+  if (!attr_done[ctx->device & 63]) {
     KL_CUDA(cudaFuncSetAttribute(fused_coef256_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, P_SMEM_BYTES));
-    attr_done = true;
+    attr_done[ctx->device & 63] = true;
   }
   fused_coef256_kernel<<<clusters * 2, P_THREADS, P_SMEM_BYTES, ctx->stream>>>(tmHt, tmH, tmX, tmQ, p);
   ctx->n_launch++;

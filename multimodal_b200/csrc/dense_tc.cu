@@ -708,10 +708,11 @@ int launch_cfg(klnmf_ctx *ctx, const GemmDesc &d, TcParams p) {
   if (units == 0 || p.kb_total == 0) return KLNMF_OK;
   const int grid = (int)(units < slots ? units : slots) * CG;
   auto kern = tc_gemm_kernel<BN, A_MN, B_MN, SPLIT, XT, CG, XB, QIP, MS>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  // per DEVICE: function attributes live in the device's context, and one process may drive several GPUs
+  static bool attr_done[64] = {};
+  if (!attr_done[ctx->device & 63]) {
     KL_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM_BYTES));
-    attr_done = true;
+    attr_done[ctx->device & 63] = true;
   }
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid, 1, 1);

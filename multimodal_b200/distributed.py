@@ -20,13 +20,22 @@ import numpy as np
 from . import _native
 
 
-def shard_bounds(n, world):
-    """Contiguous row blocks: rank r owns rows [b[r], b[r+1])."""
-    base, rem = divmod(int(n), int(world))
-    b = [0]
-    for r in range(world):
-        b.append(b[-1] + base + (1 if r < rem else 0))
-    return b
+def shard_bounds(n, world, weights=None):
+    """Contiguous row blocks: rank r owns rows [b[r], b[r+1]).  `weights` (one positive number per rank, e.g. measured
+    samples per second) sizes the blocks in proportion -- the GPUs of one box differ by several per cent under their
+    power caps, and every fit iteration ends in an all-reduce that waits for the slowest shard."""
+    n, world = int(n), int(world)
+    if weights is None:
+        base, rem = divmod(n, world)
+        b = [0]
+        for r in range(world):
+            b.append(b[-1] + base + (1 if r < rem else 0))
+        return b
+    w = np.asarray(weights, dtype=np.float64)
+    assert w.shape == (world,) and (w > 0).all(), weights
+    edges = np.floor(np.cumsum(w) / w.sum() * n + 0.5).astype(np.int64)
+    edges[-1] = n
+    return [0] + [int(e) for e in np.maximum.accumulate(edges)]
 
 
 def _dist():

@@ -179,6 +179,12 @@ def test_device_group_host_helpers():
     Xs = sp.csr_matrix(a)
     np.testing.assert_array_equal(D._rows(Xs, 3, 7).toarray(), a[3:7])
     assert D.shard_bounds(1001, 2) == [0, 501, 1001] and D.shard_bounds(3, 8)[-1] == 3
+    # speed-proportional shards: a GPU 5 % slower gets 5 % fewer samples; the blocks still tile [0, n)
+    bw = D.shard_bounds(4000000, 4, weights=[1.0, 0.95, 1.02, 0.97])
+    assert bw[0] == 0 and bw[-1] == 4000000 and all(b1 > b0 for b0, b1 in zip(bw, bw[1:]))
+    rows = np.diff(bw)
+    np.testing.assert_allclose(rows / rows[0], [1.0, 0.95, 1.02, 0.97], rtol=1e-5)
+    assert D.shard_bounds(10, 3, weights=[1, 1, 1]) == [0, 3, 7, 10]
     assert D._in_threads([lambda: 1, lambda: 2]) == [1, 2]
     gate = threading.Barrier(2)
 
