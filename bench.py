@@ -55,7 +55,10 @@ def parse():
     ap.add_argument("--alt-mode", default=os.environ.get("KLNMF_BENCH_ALT", "tf32,tf32x3"),
                     help="further arithmetic modes reported under alt_modes, comma separated ('' to skip)")
     ap.add_argument("--no-extra", action="store_true", help="skip the cfg3 / cfg4 entries under `workloads`")
-    ap.add_argument("--no-balance", action="store_true", help="several ranks: keep the equal split of the samples")
+    ap.add_argument("--balance", action="store_true",
+                    help="several ranks: size the shards by each GPU's measured samples/s instead of the equal split "
+                         "(experimental: under a power cap a GPU's speed depends on how long it idles in the all-reduce, "
+                         "and the calibration overshoots -- profiles/r2_run9.log)")
     ap.add_argument("--e2e-iters", type=int, default=50,
                     help="second end-to-end call at the reference's iteration count (experiment.py:20-25); 0 to skip")
     args = ap.parse_args()
@@ -457,25 +460,33 @@ def measure_workload(args, name, mode, ctx, with_clocks, keep_engine=False, step
 
     eng = build(n_local)
     balance = None
-    if dist is not None and fit and not args.no_balance:
+    if dist is not None and fit and args.balance:
         # Every fit iteration ends in an all-reduce that waits for the slowest shard, and the GPUs of one box differ by
         # several per cent under their power caps.  Calibrate on the equal split (untimed), then size the shards in
         # proportion to the measured samples per second of each GPU (distributed.shard_bounds(weights=...)).
         import torch
-        eng.run(max(warmup, 5), -float("inf"), fit)
-        ms_cal, _ = eng.last_run_profile()
-        t_local = sum(ms_cal[p_] for p_ in ("ratio", "coefficient", "numerator", "dictionary"))
-        t = torch.tensor([n_local / max(t_local, 1e-6)], dtype=torch.float64, device="cuda:%d" % local)
-        allv = [torch.zeros_like(t) for _ in range(world)]
-        dist.all_gather(allv, t)
-        speeds = [float(v.item()) for v in allv]
-        bounds = D.shard_bounds(n_total, world, weights=speeds)
-        balance = {"rows_per_rank": [bounds[r + 1] - bounds[r] for r in range(world)],
-                   "relative_speed": [s_ / max(speeds) for s_ in speeds],
-                   "note": "shards sized by each GPU's measured samples/s on an untimed calibration run of the equal split"}
-        eng.close()
-        n_local = bounds[rank + 1] - bounds[rank]
-        eng = build(n_local)
+        balance = {"rounds": [], "note": "shards sized by each GPU's measured samples/s on untimed calibration runs "
+                   "(4 discarded + 8 measured iterations per round, steady state under the power cap)"}
+        for rnd in range(2):
+            eng.run(4, -float("inf"), fit)
+            eng.run(8, -float("inf"), fit)
+            ms_cal, _ = eng.last_run_profile()
+            t_local = sum(ms_cal[p_] for p_ in ("ratio", "coefficient", "numerator", "dictionary"))
+            t = torch.tensor([n_local / max(t_local, 1e-6), t_local], dtype=torch.float64, device="cuda:%d" % local)
+            allv = [torch.zeros_like(t) for _ in range(world)]
+            dist.all_gather(allv, t)
+            speeds = [float(v[0].item()) for v in allv]
+            times = [float(v[1].item()) for v in allv]
+            spread = (max(times) - min(times)) / max(times)
+            balance["rounds"].append({"rows_per_rank": [bounds[r + 1] - bounds[r] for r in range(world)],
+                                      "compute_ms_per_step": [x / 8.0 for x in times], "spread": spread})
+            if spread < 0.01:
+                break
+            bounds = D.shard_bounds(n_total, world, weights=speeds)
+            eng.close()
+            n_local = bounds[rank + 1] - bounds[rank]
+            eng = build(n_local)
+        balance["rows_per_rank"] = [bounds[r + 1] - bounds[r] for r in range(world)]
     sampler = ClockSampler(local) if with_clocks else None
     if sampler:
         sampler.start()

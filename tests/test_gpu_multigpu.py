@@ -45,7 +45,7 @@ def test_sharded_fit_matches_oracle_and_single_device(within, mode, kind):
     within("H", cases.rel_fro(H, Hr), tol)
     within("objective", maxrel(errs, er), tol)
     # sharding changes the order of the numerator's sum only
-    same = 1e-12 if mode == "fp64" else 1e-5
+    same = {"fp64": 1e-12, "tf32x3": 1e-5, "tf32r": 2e-4}[mode]      # tf32r: the numerator's rounding follows its sum order (4e-5)
     within("W_vs_single", cases.rel_fro(W, out["0"][0]) + 1e-300, same)
     within("H_vs_single", cases.rel_fro(H, out["0"][1]) + 1e-300, same)
 
