@@ -89,6 +89,15 @@ int klnmf_set_csr_host(klnmf_ctx *ctx, const int64_t *indptr, const int32_t *ind
                        const void *values, int dtype, int64_t nnz);
 int klnmf_set_csr_device(klnmf_ctx *ctx, const int64_t *indptr_dev, const int32_t *indices_dev,
                          const void *values_dev, int dtype, int64_t nnz);
+/* A NEW context over a column subset of a dense parent's data: columns [starts[r], starts[r] + widths[r]) for
+ * r < n_ranges, concatenated in that order and gathered ON THE DEVICE (no host copy, no upload); same device, arithmetic
+ * mode and rows as the parent, k components.  This is what the evaluation of a multimodal dictionary needs: the
+ * coefficients of the SAME test samples observed through every subset of the modalities (experiment.py:350-369 calls
+ * learner.reconstruct_internal_multi once per subset, learner.py:71-78, each time re-stacking and re-uploading the data);
+ * here the scaled stack of all modalities is uploaded once (klnmf_set_dense_blocks_host) and every subset is a view.
+ * The view owns its copy: it stays valid after the parent is destroyed. */
+int klnmf_create_column_view(klnmf_ctx *parent, int n_ranges, const int64_t *starts, const int64_t *widths, int64_t k,
+                             klnmf_ctx **out);
 /* out[0] = 1 if any stored value is negative, out[1] = 1 if any is NaN/Inf */
 int klnmf_check_input(klnmf_ctx *ctx, int32_t out[2]);
 

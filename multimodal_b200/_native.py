@@ -41,6 +41,7 @@ PROTOTYPES = {
     "klnmf_set_dense_blocks_host": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "klnmf_set_csr_host": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_i64]),
     "klnmf_set_csr_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_i64]),
+    "klnmf_create_column_view": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_i64, ctypes.POINTER(_c_vp)]),
     "klnmf_check_input": (_c_int, [_c_vp, ctypes.POINTER(ctypes.c_int32)]),
     "klnmf_set_dictionary_host": (_c_int, [_c_vp, _c_vp, _c_i64]),
     "klnmf_get_dictionary_host": (_c_int, [_c_vp, _c_vp, _c_i64]),
@@ -230,6 +231,18 @@ class Engine(object):
             data, dt = np.ascontiguousarray(X.data, dtype=np.float64), F64
         assert X.shape == (self.n, self.f)
         _check(self.lib.klnmf_set_csr_host(self.h, _ptr(indptr), _ptr(indices), _ptr(data), dt, int(X.nnz)))
+
+    def column_view(self, ranges, k):
+        """A new Engine over the columns [start, stop) of every (start, stop) in `ranges`, concatenated in that order
+        and gathered on the device from this engine's dense data (klnmf_create_column_view)."""
+        starts = (ctypes.c_int64 * len(ranges))(*[int(a) for a, _ in ranges])
+        widths = (ctypes.c_int64 * len(ranges))(*[int(b) - int(a) for a, b in ranges])
+        h = _c_vp()
+        _check(self.lib.klnmf_create_column_view(self.h, len(ranges), starts, widths, int(k), ctypes.byref(h)))
+        child = Engine.__new__(Engine)
+        child.lib, child.n, child.f, child.k = self.lib, self.n, sum(int(b) - int(a) for a, b in ranges), int(k)
+        child.mode, child.h, child._keep = self.mode, h, []
+        return child
 
     def check_input(self):
         out = (ctypes.c_int32 * 2)()

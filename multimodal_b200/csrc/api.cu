@@ -104,7 +104,8 @@ int ensure_state(klnmf_ctx *ctx) {
   KL_CUDA(cudaMemsetAsync(ctx->rsh32, 0, (ctx->ldw + 32) * 4, ctx->stream));
   KL_CUDA(cudaMemsetAsync(ctx->rowsumH, 0, (ctx->k + 1) * 8, ctx->stream));
   if (!ctx->sparse) {
-    const int64_t per_row = round_up(ctx->f, 32) * es * (ctx->split ? 2 : 1);
+    // TF32R contracts the rounded ratio only: its low-part panel exists for the parity hooks alone (ensure_qlo)
+    const int64_t per_row = round_up(ctx->f, 32) * es * (ctx->split && !ctx->single_pass ? 2 : 1);
     int64_t rows = ctx->scratch_limit / per_row;
     rows = rows / 128 * 128;
     if (rows < 128) rows = 128;
@@ -112,9 +113,15 @@ int ensure_state(klnmf_ctx *ctx) {
     ctx->panel_rows = rows;
     ctx->ldq = round_up(ctx->f, 32);
     KL_TRY(dmalloc(&ctx->Q, rows * ctx->ldq * es));
-    if (ctx->split) KL_TRY(dmalloc(&ctx->Qlo, rows * ctx->ldq * es));
+    if (ctx->split && !ctx->single_pass) KL_TRY(dmalloc(&ctx->Qlo, rows * ctx->ldq * es));
   }
   return KLNMF_OK;
+}
+
+// low parts of the ratio panel, on demand (TF32R: only klnmf_ratio_host, the _Q parity hook, writes them)
+int ensure_qlo(klnmf_ctx *ctx) {
+  if (ctx->Qlo || !ctx->split || ctx->sparse) return KLNMF_OK;
+  return dmalloc(&ctx->Qlo, ctx->panel_rows * ctx->ldq * (int64_t)ctx->es);
 }
 
 void release_data(klnmf_ctx *ctx) {
@@ -321,6 +328,7 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
   // TF32R: one MMA per step on the round-to-nearest TF32 halves of W, H and Q - 1 (the _Q parity hook and the
   // stand-alone objective, KLdivNMF.error, keep the split form: they are not on the loop)
   const int single = ctx->single_pass && !ratio_host && !only_error ? 1 : 0;
+  if (ratio_host) KL_TRY(ensure_qlo(ctx));
   if (centered) KL_TRY(launch_rsh32(ctx));
   if (fused) {
     // k <= 128 (fit, transform) / k <= 256 (transform): the coefficient half-step is one fused kernel, the ratio
@@ -688,6 +696,48 @@ int klnmf_set_csr_device(klnmf_ctx *ctx, const int64_t *indptr_dev, const int32_
   return KLNMF_OK;
 }
 
+int klnmf_create_column_view(klnmf_ctx *parent, int n_ranges, const int64_t *starts, const int64_t *widths, int64_t k,
+                             klnmf_ctx **out) {
+  KL_CHECK(parent && out && n_ranges >= 1 && starts && widths, KLNMF_EINVAL, "create_column_view: bad argument");
+  KL_CHECK(parent->have_x && !parent->sparse, KLNMF_ESTATE, "create_column_view: the parent holds no dense data");
+  *out = nullptr;
+  int64_t f_sub = 0;
+  for (int r = 0; r < n_ranges; r++) {
+    KL_CHECK(starts[r] >= 0 && widths[r] > 0 && starts[r] + widths[r] <= parent->f, KLNMF_EINVAL,
+             "create_column_view: range %d = [%lld, +%lld) leaves the parent's %lld columns", r, (long long)starts[r],
+             (long long)widths[r], (long long)parent->f);
+    f_sub += widths[r];
+  }
+  klnmf_ctx *ctx = nullptr;
+  KL_TRY(klnmf_create(&ctx, parent->device, parent->n, f_sub, k, parent->mode));
+  ctx->scratch_limit = parent->scratch_limit;
+  auto fail = [&](int rc) { klnmf_destroy(ctx); return rc; };
+  ctx->sparse = false;
+  ctx->ldx = round_up(f_sub, 32);
+  const int64_t es = ctx->es;
+  const int64_t bytes = (ctx->n > 0 ? ctx->n : 1) * ctx->ldx * es;
+  int rc = dmalloc(&ctx->X, bytes);
+  if (rc != KLNMF_OK) return fail(rc);
+  ctx->x_owned = true;
+  // the parent's pending work (its upload, the per-modality scaling) comes first; then the gather runs on the view's stream
+  if (cudaStreamSynchronize(parent->stream) != cudaSuccess) { set_error("create_column_view: parent stream error"); return fail(KLNMF_ECUDA); }
+  if (ctx->ldx != f_sub && cudaMemsetAsync(ctx->X, 0, bytes, ctx->stream) != cudaSuccess) return fail(KLNMF_ECUDA);
+  int64_t off = 0;
+  for (int r = 0; r < n_ranges && ctx->n > 0; r++) {
+    if (cudaMemcpy2DAsync((char *)ctx->X + off * es, ctx->ldx * es, (const char *)parent->X + starts[r] * es, parent->ldx * es,
+                          widths[r] * es, ctx->n, cudaMemcpyDeviceToDevice, ctx->stream) != cudaSuccess) {
+      set_error("create_column_view: device copy of range %d failed", r);
+      return fail(KLNMF_ECUDA);
+    }
+    off += widths[r];
+  }
+  rc = ensure_state(ctx);
+  if (rc != KLNMF_OK) return fail(rc);
+  ctx->have_x = true;
+  *out = ctx;
+  return KLNMF_OK;
+}
+
 int klnmf_check_input(klnmf_ctx *ctx, int32_t out[2]) {
   KL_CHECK(ctx && out && ctx->have_x, KLNMF_ESTATE, "check_input: no data set");
   KL_CUDA(cudaSetDevice(ctx->device));
@@ -751,8 +801,10 @@ int klnmf_init_coefficients(klnmf_ctx *ctx) {
         KL_CUDA(cudaMemcpy2DAsync((char *)ctx->Q + rr * ctx->ldq * es, ctx->ldq * es, Xp + rr * ctx->ldx * es,
                                   ctx->ldx * es, ctx->f * es, r, cudaMemcpyDeviceToDevice, ctx->stream));
       }
-      KL_TRY(launch_split(ctx, (const float *)ctx->Q, (float *)ctx->Q, (float *)ctx->Qlo, rows, ctx->f, ctx->ldq));
-      d.A = ctx->Q; d.a_sm = ctx->ldq; d.A_lo = ctx->Qlo;
+      // (TF32R multiplies the rounded high parts only: no low-part panel)
+      KL_TRY(launch_split(ctx, (const float *)ctx->Q, (float *)ctx->Q, ctx->single_pass ? nullptr : (float *)ctx->Qlo, rows,
+                          ctx->f, ctx->ldq));
+      d.A = ctx->Q; d.a_sm = ctx->ldq; d.A_lo = ctx->single_pass ? nullptr : ctx->Qlo;
     } else {
       d.A = Xp; d.a_sm = ctx->ldx;
     }

@@ -112,8 +112,6 @@ struct klnmf_ctx {
   void *comm = nullptr;        // ncclComm_t
   bool comm_owned = false;     // created by klnmf_comm_init (destroyed with the context) vs attached (klnmf_comm_attach)
   int rank = 0, world = 1;
-  cudaStream_t comm_stream = nullptr;   // side stream: numerator chunks are all-reduced while later chunks are computed
-  cudaEvent_t comm_ev[2] = {nullptr, nullptr};
 
   // ---- accounting -----------------------------------------------------------------------------
   int64_t n_launch = 0, n_nccl = 0, bytes_h2d = 0, bytes_d2h = 0;
@@ -219,7 +217,6 @@ int nccl_comm_create(void **out, int device, const void *id128, int rank, int wo
 int nccl_comm_free(void *comm);
 int nccl_group_start();
 int nccl_group_end();
-int nccl_allreduce_on(klnmf_ctx *ctx, void *buf, int64_t count, int es, cudaStream_t stream);
 int nccl_allreduce_sum(klnmf_ctx *ctx, void *buf, int64_t count, int es);
 int nccl_allreduce_sum_f64(klnmf_ctx *ctx, double *buf, int64_t count);
 void nccl_comm_destroy(klnmf_ctx *ctx);

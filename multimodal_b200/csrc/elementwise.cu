@@ -200,7 +200,7 @@ __global__ void split_kernel(const float *__restrict__ src, float *__restrict__ 
     float v = src[r * ld + c];
     float h = tf32_hi(v);
     hi[r * ld + c] = h;
-    lo[r * ld + c] = v - h;
+    if (lo) lo[r * ld + c] = v - h;
   }
 }
 

@@ -104,14 +104,6 @@ int nccl_comm_init(klnmf_ctx *ctx, const void *id128, int rank, int world) {
 int nccl_group_start() { return g_nccl.group_start ? check(g_nccl.group_start(), "ncclGroupStart") : KLNMF_OK; }
 int nccl_group_end() { return g_nccl.group_end ? check(g_nccl.group_end(), "ncclGroupEnd") : KLNMF_OK; }
 
-int nccl_allreduce_on(klnmf_ctx *ctx, void *buf, int64_t count, int es, cudaStream_t stream) {
-  if (ctx->world <= 1 || count <= 0) return KLNMF_OK;
-  ctx->n_nccl++;
-  return check(g_nccl.allreduce(buf, buf, (size_t)count, es == 8 ? kNcclFloat64 : kNcclFloat32, kNcclSum,
-                                (nccl_comm_t)ctx->comm, stream),
-               "ncclAllReduce");
-}
-
 int nccl_allreduce_sum(klnmf_ctx *ctx, void *buf, int64_t count, int es) {
   if (ctx->world <= 1 || count <= 0) return KLNMF_OK;
   ctx->n_nccl++;

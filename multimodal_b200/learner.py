@@ -88,6 +88,43 @@ class MultimodalLearner(object):
         return fit_coefficients(self.stack_data(orig_mods, test_data), self.get_stacked_dicos(orig_mods),
                                 iter_nmf=iterations, mode=self.mode, device=self.device)
 
+    def reconstruct_internal_batch(self, test_data, subsets, iterations):
+        """Internal coefficients of the SAME samples observed through several subsets of the modalities -- what the
+        evaluation of a dictionary asks for (experiment.py:350-369: `_get_all_internals` calls
+        reconstruct_internal_multi once per subset, six for three modalities, each call re-stacking and re-uploading
+        its data).  `test_data` holds one matrix per modality of the learner, in the learner's order; `subsets` is a
+        list of lists of modality names.  Returns {tuple(subset): internal}, each entry equal to
+        reconstruct_internal_multi(subset, [data of the subset], iterations).
+
+        Dense modalities: the scaled stack of ALL modalities is uploaded and validated once; every subset is a column
+        view gathered on the device (klnmf_create_column_view) with its own sub-dictionary.  A sparse modality makes the
+        reference's stack sparse (array_utils.py:5-9): those calls go one by one, as before."""
+        assert len(test_data) == len(self.mod)
+        n_samples = test_data[0].shape[0]
+        for block, width in zip(test_data, self.dim):
+            assert(block.shape == (n_samples, width))
+        subsets = [list(s) for s in subsets]
+        if not all(isinstance(block, np.ndarray) and block.ndim == 2 for block in test_data):
+            return dict((tuple(s), self.reconstruct_internal_multi(
+                s, [test_data[self.get_index(name)] for name in s], iterations)) for s in subsets)
+        device = self.device[0] if isinstance(self.device, (list, tuple)) else self.device
+        out = {}
+        with _native.Engine(n_samples, int(sum(self.dim)), self.k, mode=self.mode, device=device) as parent:
+            parent.set_dense_blocks(test_data, self.coef)
+            negative, non_finite = parent.check_input()
+            if non_finite:
+                raise ValueError("array contains NaN or infinity")
+            if negative:
+                raise ValueError("Negative values in data passed to NMF.fit")
+            for s in subsets:
+                dictionary = np.ascontiguousarray(self.get_stacked_dicos(s), dtype=np.float64)
+                with parent.column_view([self.get_axis_range(name) for name in s], dictionary.shape[0]) as view:
+                    view.set_dictionary(dictionary)
+                    view.init_coefficients()                      # W0 = X.H^T (nmf.py:156)
+                    view.run(iterations, 0.0, False)              # fit_coefficients: tol = 0, transform (learner.py:11-15)
+                    out[tuple(s)] = view.get_coefficients()
+        return out
+
     def reconstruct_internal(self, orig_mod, test_data, iterations):
         return self.reconstruct_internal_multi([orig_mod], [test_data], iterations)
 

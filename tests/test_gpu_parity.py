@@ -291,3 +291,36 @@ def test_learner_dense_stack_formed_on_the_device(within, mode):
     internal = lr.reconstruct_internal_multi(['sound', 'motion'], [mats[0][:50], mats[2][:50]], 10)
     internal_ref = ref.reconstruct_internal_multi(['sound', 'motion'], [mats[0][:50], mats[2][:50]], 10)
     within("internal", cases.rel_fro(internal, internal_ref), TOL_WH[mode])
+
+
+@pytest.mark.parametrize("mode", ["fp64", "tf32r"])
+def test_batched_multi_subset_transform_vs_oracle(within, mode):
+    """the coefficients of the same test samples through every subset of three dense modalities
+    (experiment.py:350-369, `_get_all_internals`: six subsets for the twelve tested combinations) -- one upload of the
+    scaled stack, one device-side column view per subset (learner.reconstruct_internal_batch) -- against six separate
+    oracle transforms (learner.py:71-78 -> fit_coefficients, learner.py:11-15)."""
+    rs = np.random.RandomState(23)
+    n, mods, dims, k = 150, ['sound', 'image', 'motion'], [70, 45, 33], 9
+    mats = [rs.gamma(0.5, 1.0, size=(n, 70)), rs.random_sample((n, 45)).astype(np.float32), rs.poisson(1.5, size=(n, 33))]
+    coefs = [1. / np.mean(np.sum(m, axis=1)) for m in mats]
+    ref = O.Learner(mods, dims, coefs, k)
+    np.random.seed(4)
+    ref.train(mats, 10)
+    lr = MultimodalLearner(mods, dims, coefs, k, mode=mode)
+    lr.dico = ref.dico                                             # the same dictionary on both sides
+    subsets = [['sound'], ['image'], ['motion'], ['image', 'motion'], ['sound', 'motion'], ['sound', 'image']]
+    test = [m[:60] for m in mats]
+    got = lr.reconstruct_internal_batch(test, subsets, 12)
+    assert sorted(got) == sorted(tuple(s) for s in subsets)
+    for s in subsets:
+        want = ref.reconstruct_internal_multi(s, [test[mods.index(name)] for name in s], 12)
+        assert got[tuple(s)].shape == want.shape == (60, k)
+        within("+".join(s), cases.rel_fro(got[tuple(s)], want), TOL_WH[mode])
+        # and the batched path is the one-by-one path of the same mode, up to nothing but the upload route
+        one = lr.reconstruct_internal_multi(s, [test[mods.index(name)] for name in s], 12)
+        within("+".join(s) + "_vs_one_by_one", cases.rel_fro(got[tuple(s)], one) + 1e-300, 1e-12 if mode == "fp64" else 1e-6)
+    with pytest.raises(ValueError, match="Negative values"):
+        bad = [m.copy() for m in test]
+        bad[2] = bad[2].astype(np.float64)
+        bad[2][3, 4] = -1.0
+        lr.reconstruct_internal_batch(bad, subsets, 2)
