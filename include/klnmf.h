@@ -125,6 +125,12 @@ int klnmf_dictionary_device(klnmf_ctx *ctx, void **ptr, int64_t *ld, int *dtype)
  * (plus one every 32 iterations when tol_abs > 0). */
 int klnmf_run(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit,
               double *errors_out, int *n_errors, int *n_iter);
+/* The same loop continued: `prev_objective` is the last objective an earlier klnmf_run on this context recorded
+ * (+inf for a fresh start, which is what klnmf_run passes), so that a fit split into several calls -- e.g. to write a
+ * dictionary checkpoint every so many iterations -- applies the reference's stop test (nmf.py:215) across the call
+ * boundary exactly as one long call would. */
+int klnmf_run_resume(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, double prev_objective,
+                     double *errors_out, int *n_errors, int *n_iter);
 /* KL(X || W H) of the current state: KLdivNMF.error (nmf.py:297-310) */
 int klnmf_error(klnmf_ctx *ctx, double *out);
 

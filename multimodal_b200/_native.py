@@ -54,6 +54,8 @@ PROTOTYPES = {
                                          ctypes.POINTER(_c_int)]),
     "klnmf_run": (_c_int, [_c_vp, _c_int, _c_dbl, _c_int, _c_vp, ctypes.POINTER(_c_int),
                            ctypes.POINTER(_c_int)]),
+    "klnmf_run_resume": (_c_int, [_c_vp, _c_int, _c_dbl, _c_int, _c_dbl, _c_vp, ctypes.POINTER(_c_int),
+                                  ctypes.POINTER(_c_int)]),
     "klnmf_error": (_c_int, [_c_vp, ctypes.POINTER(_c_dbl)]),
     "klnmf_dictionary_step": (_c_int, [_c_vp]),
     "klnmf_ratio_host": (_c_int, [_c_vp, _c_vp, _c_int, _c_i64]),
@@ -291,12 +293,13 @@ class Engine(object):
         return out
 
     # -- compute ----------------------------------------------------------------------------
-    def run(self, max_iter, tol_abs, fit):
-        """Returns (errors ndarray, n_iter) with the reference's meaning of both."""
+    def run(self, max_iter, tol_abs, fit, prev_objective=float("inf")):
+        """Returns (errors ndarray, n_iter) with the reference's meaning of both.  `prev_objective`: the last objective
+        recorded by an earlier call on this engine when a fit is run in several pieces (klnmf_run_resume)."""
         errs = np.empty(max(int(max_iter), 1), dtype=np.float64)
         ne, ni = _c_int(0), _c_int(0)
-        _check(self.lib.klnmf_run(self.h, int(max_iter), float(tol_abs), 1 if fit else 0, _ptr(errs),
-                                  ctypes.byref(ne), ctypes.byref(ni)))
+        _check(self.lib.klnmf_run_resume(self.h, int(max_iter), float(tol_abs), 1 if fit else 0, float(prev_objective),
+                                         _ptr(errs), ctypes.byref(ne), ctypes.byref(ni)))
         return errs[:ne.value].copy(), ni.value
 
     def error(self):

@@ -710,7 +710,6 @@ int klnmf_create_column_view(klnmf_ctx *parent, int n_ranges, const int64_t *sta
   }
   klnmf_ctx *ctx = nullptr;
   KL_TRY(klnmf_create(&ctx, parent->device, parent->n, f_sub, k, parent->mode));
-  ctx->scratch_limit = parent->scratch_limit;
   auto fail = [&](int rc) { klnmf_destroy(ctx); return rc; };
   ctx->sparse = false;
   ctx->ldx = round_up(f_sub, 32);
@@ -857,7 +856,13 @@ int klnmf_dictionary_device(klnmf_ctx *ctx, void **ptr, int64_t *ld, int *dtype)
 
 // ------------------------------------------------------------------------------------------------
 int klnmf_run(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, double *errors_out, int *n_errors, int *n_iter) {
+  return klnmf_run_resume(ctx, max_iter, tol_abs, fit, INFINITY, errors_out, n_errors, n_iter);
+}
+
+int klnmf_run_resume(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, double prev_objective, double *errors_out,
+                     int *n_errors, int *n_iter) {
   KL_CHECK(ctx && max_iter >= 1, KLNMF_EINVAL, "klnmf_run: max_iter must be >= 1 (reference: range(1, max_iter+1))");
+  KL_CHECK(!(prev_objective != prev_objective), KLNMF_EINVAL, "klnmf_run_resume: previous objective is NaN");
   KL_CHECK(ctx->have_x && ctx->have_h && ctx->have_w, KLNMF_ESTATE, "klnmf_run needs data, dictionary and coefficients");
   KL_CUDA(cudaSetDevice(ctx->device));
   if (ctx->errors_cap < max_iter) {
@@ -872,7 +877,7 @@ int klnmf_run(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, double *err
   // slack whenever tol_abs <= slack * |previous objective|, and the plain reference test above it.
   const double slack = ctx->mode == KLNMF_MODE_FP64 ? 0.0 : (ctx->mode == KLNMF_MODE_TF32X3 ? 1e-6 : (ctx->mode == KLNMF_MODE_TF32R ? 1e-5 : 1e-4));
   double *hp = ctx->pinned;
-  hp[DS_KL] = 0.0; hp[DS_PREV] = INFINITY; hp[DS_WHSUM] = slack; hp[DS_TOL] = tol_abs;
+  hp[DS_KL] = 0.0; hp[DS_PREV] = prev_objective; hp[DS_WHSUM] = slack; hp[DS_TOL] = tol_abs;
   KL_CUDA(cudaMemcpyAsync(ctx->dscal + DS_KL, hp + DS_KL, 8, cudaMemcpyHostToDevice, ctx->stream));
   KL_CUDA(cudaMemcpyAsync(ctx->dscal + DS_PREV, hp + DS_PREV, 8, cudaMemcpyHostToDevice, ctx->stream));
   KL_CUDA(cudaMemcpyAsync(ctx->dscal + DS_WHSUM, hp + DS_WHSUM, 8, cudaMemcpyHostToDevice, ctx->stream));

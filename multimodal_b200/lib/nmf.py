@@ -64,6 +64,11 @@ def _first_device(device):
     return int(device)
 
 
+def _is_device_features(X):
+    from ..store import DeviceFeatures
+    return isinstance(X, DeviceFeatures)
+
+
 def _load(eng, X):
     """Hand X (dense array, CSR matrix or a stack of dense modality blocks) to an engine."""
     if isinstance(X, StackedBlocks):
@@ -77,6 +82,10 @@ def _load(eng, X):
 def _engine_for(X, k, mode, device):
     """Context holding X (validated on the device with the reference's messages)."""
     n, f = X.shape
+    if _is_device_features(X):      # resident on the GPU already (store.DeviceFeatures): a device-side copy, no upload
+        if _native.resolve_mode(mode) != X.mode:
+            raise ValueError("the device-resident features were uploaded for another arithmetic mode")
+        return X.view(k)
     eng = _native.Engine(n, f, k, mode=mode, device=_first_device(device))
     try:
         _load(eng, X)
@@ -88,7 +97,7 @@ def _engine_for(X, k, mode, device):
 
 def _host_prepare(X):
     """atleast2d_or_csr (nmf.py:193) and the dtype the device copy is made from; no O(n f) scan on the host."""
-    if not isinstance(X, StackedBlocks):
+    if not isinstance(X, StackedBlocks) and not _is_device_features(X):
         X = atleast2d_or_csr(X, check_finite=False)
         if sp.issparse(X):
             X = _canonical_csr(X)
@@ -142,7 +151,7 @@ class KLdivNMF(object):
     """
 
     def __init__(self, n_components=None, tol=1e-6, max_iter=200, eps=1.e-8,
-                 subit=10, random_state=None, *, mode=None, device=0):
+                 subit=10, random_state=None, *, mode=None, device=0, checkpoint=None):
         self.n_components = n_components
         self._init_dictionary = None
         self.random_state = random_state
@@ -152,6 +161,7 @@ class KLdivNMF(object):
         self.subit = subit
         self.mode = mode
         self.device = device
+        self.checkpoint = checkpoint     # store.DictionaryCheckpoint: write the dictionary every so many fit iterations
 
     # -- initialisation (nmf.py:147-157) ----------------------------------------------
     def _draw_dictionary(self, n_features):
@@ -182,7 +192,7 @@ class KLdivNMF(object):
         `y`, `weights` and `scale_W` are accepted and ignored exactly as in the
         reference (nmf.py:222 never forwards scale_W).
         """
-        Xv = X if isinstance(X, StackedBlocks) else atleast2d_or_csr(X, check_finite=False)
+        Xv = X if (isinstance(X, StackedBlocks) or _is_device_features(X)) else atleast2d_or_csr(X, check_finite=False)
         n_samples, n_features = Xv.shape
         if not self.n_components:
             self.n_components = n_features
@@ -204,7 +214,7 @@ class KLdivNMF(object):
                 # the reference dies here with an unbound `n_iter` (nmf.py:224)
                 raise NameError("name 'n_iter' is not defined (max_iter < 1)")
             tol = self.tol * n_samples * n_features
-            errors, n_iter = eng.run(self.max_iter, tol, _fit)
+            errors, n_iter = self._run(eng, tol, _fit)
             # fit() throws the coefficients away (nmf.py:259-273): do not bring them back from the device for that
             W = None if getattr(self, "_discard_coefficients", False) else eng.get_coefficients()
             if _fit:
@@ -217,11 +227,32 @@ class KLdivNMF(object):
             return W, [e for e in errors]
         return W
 
+    def _run(self, eng, tol, _fit):
+        """The loop (nmf.py:212-222), in one piece -- or, with a dictionary checkpoint, in pieces of `every` iterations
+        with the stop test carried across them (klnmf_run_resume)."""
+        ck = self.checkpoint if _fit else None
+        if ck is None:
+            return eng.run(self.max_iter, tol, _fit)
+        errors, done, prev = [], 0, float("inf")
+        while done < self.max_iter:
+            chunk = min(ck.every, self.max_iter - done)
+            errs, _ = eng.run(chunk, tol, _fit, prev)
+            errors.extend(errs)
+            done += len(errs)
+            if len(errs):
+                prev = errs[-1]
+                ck.write(eng.get_dictionary(), done, prev)
+            if len(errs) < chunk:                       # the stop test fired inside this piece
+                return np.asarray(errors), done + 1
+        return np.asarray(errors), self.max_iter
+
     def _fit_transform_sharded(self, Xv, _fit, return_errors):
         """The same call with the samples sharded over `self.device` (a list of CUDA ordinals): one engine and one
         host thread per GPU, the k x f numerator and the objective partials all-reduced over NCCL every fit
         iteration; identical state transitions and return values as the single-device path above."""
         from ..distributed import DeviceGroup
+        if self.checkpoint is not None or _is_device_features(Xv):
+            raise NotImplementedError("dictionary checkpoints and device-resident features are single-device features")
         n_samples, n_features = Xv.shape
         Xv = _host_prepare(Xv)
         H_init = self._draw_dictionary(n_features)

@@ -18,6 +18,8 @@ import json
 import numpy as np
 import scipy.sparse as sp
 
+from . import _native
+
 
 def _split(d, plain, arrays, prefix):
     # logger.py:147-152
@@ -120,3 +122,75 @@ def load_npz_features(path, var='Xmotion', pinned=True):
     with np.load(path) as z:
         X = np.ascontiguousarray(z[var], dtype=np.float32)
     return _pinned_like(X) if pinned else X
+
+
+class DeviceFeatures(object):
+    """A dense feature matrix that lives on the GPU (one upload, any number of fits / transforms): what
+    `load_npz_features_device` and `to_device` return and what `KLdivNMF.fit / fit_transform / transform` accept in place
+    of an array.  Every estimator call works on a device-side copy of the requested columns
+    (klnmf_create_column_view), so the resident data are never modified."""
+
+    def __init__(self, engine):
+        self.engine = engine
+        self.shape = (engine.n, engine.f)
+        self.ndim = 2
+        self.mode = engine.mode
+
+    def view(self, k, columns=None):
+        """A fresh engine over `columns` (list of (start, stop); default: all of them) with k components."""
+        return self.engine.column_view(columns or [(0, self.shape[1])], k)
+
+    def check_input(self):
+        return self.engine.check_input()
+
+    def close(self):
+        self.engine.close()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+
+def to_device(X, mode=None, device=0):
+    """Upload a dense host array (C-contiguous float32 / float64; pinned memory uploads at PCIe speed) once."""
+    X = np.asarray(X)
+    if X.dtype not in (np.float32, np.float64):
+        X = X.astype(np.float64)
+    # a holder, not a problem: one component and the smallest ratio scratch (the views bring their own state)
+    eng = _native.Engine(X.shape[0], X.shape[1], 1, mode=mode, device=device, scratch_limit=1 << 20)
+    try:
+        eng.set_dense(np.ascontiguousarray(X))
+    except Exception:
+        eng.close()
+        raise
+    return DeviceFeatures(eng)
+
+
+def load_npz_features_device(path, var='Xmotion', mode=None, device=0):
+    """`db/choreo2.py:74` straight to the device: file -> page-locked staging -> HBM, returned as DeviceFeatures."""
+    return to_device(load_npz_features(path, var, pinned=True), mode=mode, device=device)
+
+
+class DictionaryCheckpoint(object):
+    """Dictionary checkpoints of a running fit in the reference logger's layout (one experiment run per checkpoint
+    file, key 'dictionary' plus the iteration count and the objective): `KLdivNMF(..., checkpoint=DictionaryCheckpoint(
+    name, every=25))` writes `name.json` / `name.npz` every 25 iterations, and `resume()` hands back what a restarted
+    fit needs -- `est._init_dictionary = ck.resume()['dictionary']`.  The dictionary is read from the device between two
+    pieces of the loop (klnmf_run_resume keeps the stop test continuous across them); at k x f = 512 x 8192 that is a
+    17 MB copy against seconds of iterations."""
+
+    def __init__(self, filename, every=50):
+        assert every >= 1
+        self.filename, self.every = filename, int(every)
+
+    def write(self, dictionary, iterations_done, objective):
+        save_run_dictionaries(self.filename, [dictionary], glob={'iterations_done': int(iterations_done),
+                                                                 'objective': float(objective)})
+
+    def resume(self):
+        with open(self.filename + '.json', 'r') as f:
+            glob = json.load(f)['glob']
+        return {'dictionary': np.ascontiguousarray(load_run_dictionary(self.filename), dtype=np.float64),
+                'iterations_done': glob['iterations_done'], 'objective': glob['objective']}

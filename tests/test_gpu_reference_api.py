@@ -193,3 +193,60 @@ class TestInputGuards:
         X.data[0] = 0.0
         nmf.KLdivNMF(n_components=2, max_iter=2, tol=0, mode=mode).fit(X)
         assert X.nnz == 2                      # nmf.py:66 side effect
+
+
+class TestStoreOnDevice:
+    """SURVEY 8f-4 on the GPU: device-resident features (one upload, several estimator calls) and dictionary
+    checkpoints written while a fit runs, in the reference logger's layout (logger.py:79-136)."""
+
+    def test_device_resident_features_equal_host_arrays(self, tmp_path):
+        from multimodal_b200 import store
+        rs = np.random.RandomState(5)
+        motion = rs.dirichlet(0.1 * np.ones(45), 130)
+        np.savez(str(tmp_path / "motion.npz"), Xmotion=motion)
+        host = store.load_npz_features(str(tmp_path / "motion.npz"), pinned=False)
+        with store.load_npz_features_device(str(tmp_path / "motion.npz")) as dev:
+            assert dev.shape == (130, 45)
+            outs = []
+            for X in (host, dev, dev):                     # the resident copy serves any number of calls
+                est = nmf.KLdivNMF(n_components=6, max_iter=15, tol=0)
+                np.random.seed(8)
+                W = est.fit_transform(X)
+                outs.append((W, est.components_))
+            for W, H in outs[1:]:
+                assert np.array_equal(W, outs[0][0]) and np.array_equal(H, outs[0][1])
+            est = nmf.KLdivNMF(n_components=6, max_iter=10, tol=0)
+            est.components_ = outs[0][1]
+            assert np.array_equal(est.transform(dev), est.transform(host))
+            with pytest.raises(ValueError):
+                nmf.KLdivNMF(n_components=6, max_iter=2, mode="fp64").fit(dev)      # uploaded for another mode
+        bad = motion.copy()
+        bad[3, 3] = -1.0
+        with store.to_device(bad) as dev:
+            with pytest.raises(ValueError, match="Negative values"):
+                nmf.KLdivNMF(n_components=2, max_iter=2).fit(dev)
+
+    @pytest.mark.parametrize("tol", [0, 1e-4])
+    def test_checkpointed_fit_is_the_same_fit(self, tmp_path, tol, mode):
+        from multimodal_b200 import store
+        rs = np.random.RandomState(6)
+        X = rs.gamma(0.5, 1.0, size=(150, 80))
+        plain = nmf.KLdivNMF(n_components=5, max_iter=60, tol=tol, mode=mode)
+        np.random.seed(9)
+        W0, e0 = plain.fit_transform(X, return_errors=True)
+        ck = store.DictionaryCheckpoint(str(tmp_path / "ck"), every=7)
+        est = nmf.KLdivNMF(n_components=5, max_iter=60, tol=tol, mode=mode, checkpoint=ck)
+        np.random.seed(9)
+        W1, e1 = est.fit_transform(X, return_errors=True)
+        # the pieces are the same iterations: identical arithmetic, identical stop decision
+        assert len(e1) == len(e0) and np.array_equal(np.asarray(e1), np.asarray(e0))
+        assert np.array_equal(W1, W0) and np.array_equal(est.components_, plain.components_)
+        back = ck.resume()
+        assert back['iterations_done'] == len(e1) and back['objective'] == e1[-1]
+        assert np.array_equal(back['dictionary'], est.components_)
+        assert np.array_equal(store.load_run_dictionary(str(tmp_path / "ck")), est.components_)   # the reference's reader
+        # a restarted fit picks the dictionary up
+        again = nmf.KLdivNMF(n_components=5, max_iter=3, tol=0, mode=mode)
+        again._init_dictionary = back['dictionary']
+        again.fit(X)
+        assert again.error(X, again.transform(X)) <= e1[-1] * (1 + 1e-3)
