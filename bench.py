@@ -312,7 +312,18 @@ def phase_roofline(ms, cnt, n_local, f, k, kind, steps, peaks, mode):
         alg = 8.0 * nnz + 4.0 * (n_local + 1) + 8.0 * n_local * k + 8.0 * k * f
         t = (ms["ratio"] + ms["numerator"]) / max(steps, 1) * 1e-3
         ach = alg / t / 1e9
+        # what really bounds the path: every stored entry gathers one dictionary column (rows pass) and one coefficient
+        # row (numerator pass) of 4 k bytes from the L2 -- against the L2 -> SM read bandwidth measured on this GPU
+        gather = 2.0 * 4.0 * k * nnz
+        l2 = None
+        if peaks.get("l2_gbs"):
+            l2 = {"bound": "l2", "achieved": gather / t / 1e9, "peak": peaks["l2_gbs"], "unit": "GB/s",
+                  "frac": gather / t / 1e9 / peaks["l2_gbs"], "gather_bytes": gather,
+                  "peak_source": "klnmf_l2_read_bench on this GPU: 48 MB buffer read 200 times by every SM (ld.global.cg.v4)",
+                  "rows_pass_gbs": 0.5 * gather / (ms["ratio"] / max(steps, 1) * 1e-3) / 1e9,
+                  "numerator_pass_gbs": 0.5 * gather / (ms["numerator"] / max(steps, 1) * 1e-3) / 1e9}
         return {"bound": "hbm", "achieved": ach, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": ach / peaks["hbm_gbs"],
+                "l2_roofline": l2,
                 "traffic": ncu_traffic("sparse", n_local, f, k, "tf32" if mode != "fp64" else "fp64"),
                 "algorithmic_bytes": alg, "kernel": "sparse_rows_kernel + sparse_numerator_bcsc_kernel",
                 "peak_source": peaks["source"],
@@ -511,6 +522,10 @@ def run_ours(args):
     from multimodal_b200 import _native
     from multimodal_b200 import distributed as D
     peaks = measured_peaks()
+    try:
+        peaks["l2_gbs"] = _native.l2_read_bandwidth(device=local)
+    except Exception:
+        peaks["l2_gbs"] = None
     ctx = (_native, D, rank, world, local, dist, peaks)
 
     main = measure_workload(args, args.workload, args.mode, ctx, True, keep_engine=True)

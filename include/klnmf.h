@@ -195,6 +195,10 @@ int klnmf_contract_host(int device, int mode, int64_t M, int64_t N, int64_t K, c
 /* diagnostic: average device milliseconds of one such contraction on synthetic device-resident operands */
 int klnmf_contract_bench(int device, int mode, int64_t M, int64_t N, int64_t K, int a_trans, int b_trans, int iters,
                          double *ms_out);
+/* diagnostic: sustained L2 -> SM read bandwidth (GB/s) on a `bytes`-sized buffer (choose it below the L2 capacity) read
+ * `iters` times by every SM: the measured denominator of the sparse path's L2 roofline, whose dictionary-column and
+ * coefficient-row gathers are served by the L2, not by HBM */
+int klnmf_l2_read_bench(int device, int64_t bytes, int iters, double *gbps_out);
 /* name of the kernel family that serves the dense contractions in this context
  * ("tcgen05_tf32", "tcgen05_tf32x3", "dmma_f64") -- lets tests assert the native path. */
 const char *klnmf_engine_name(klnmf_ctx *ctx);

@@ -75,6 +75,7 @@ PROTOTYPES = {
     "klnmf_contract_host": (_c_int, [_c_int, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_int, _c_vp, _c_int, _c_vp]),
     "klnmf_contract_bench": (_c_int, [_c_int, _c_int, _c_i64, _c_i64, _c_i64, _c_int, _c_int, _c_int,
                                       ctypes.POINTER(_c_dbl)]),
+    "klnmf_l2_read_bench": (_c_int, [_c_int, _c_i64, _c_int, ctypes.POINTER(_c_dbl)]),
     "klnmf_engine_name": (ctypes.c_char_p, [_c_vp]),
     "klnmf_pairwise_host": (_c_int, [_c_int, _c_int, _c_i64, _c_i64, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64, _c_vp, _c_i64,
                                      _c_vp, _c_vp]),
@@ -425,6 +426,14 @@ def contract_bench(M, N, K, mode, a_trans=False, b_trans=False, iters=10, device
     _check(lib.klnmf_contract_bench(int(device), resolve_mode(mode), int(M), int(N), int(K), 1 if a_trans else 0,
                                     1 if b_trans else 0, int(iters), ctypes.byref(ms)))
     return ms.value
+
+
+def l2_read_bandwidth(bytes=48 << 20, iters=200, device=0):
+    """Diagnostic: sustained L2 -> SM read bandwidth in GB/s (klnmf_l2_read_bench)."""
+    lib = load()
+    out = _c_dbl(0.0)
+    _check(lib.klnmf_l2_read_bench(int(device), int(bytes), int(iters), ctypes.byref(out)))
+    return out.value
 
 
 MEASURES = {"kl_div": 0, "rev_kl_div": 1, "sym_kl_div": 2, "frobenius": 3, "cosine_diff": 4}

@@ -1309,6 +1309,12 @@ int klnmf_contract_bench(int device, int mode, int64_t M, int64_t N, int64_t K, 
   return rc;
 }
 
+int klnmf_l2_read_bench(int device, int64_t bytes, int iters, double *gbps_out) {
+  KL_CHECK(gbps_out && bytes >= (1 << 20) && iters >= 1, KLNMF_EINVAL, "l2_read_bench: bad argument");
+  KL_CHECK(klnmf_device_count() > 0, KLNMF_ENODEVICE, "no CUDA device: libklnmf has no CPU path");
+  return l2_read_bench(device, bytes, iters, gbps_out);
+}
+
 const char *klnmf_engine_name(klnmf_ctx *ctx) {
   if (!ctx) return "none";
   if (ctx->es == 8) return "dmma_f64";

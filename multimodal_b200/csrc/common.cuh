@@ -201,6 +201,7 @@ int launch_fill_uniform(klnmf_ctx *ctx, void *p, int es, int64_t rows, int64_t c
 int launch_check(klnmf_ctx *ctx, const void *p, int es, int64_t rows, int64_t cols, int64_t ld);
 int launch_rowsum_h(klnmf_ctx *ctx);        // rowsumH from the current dictionary
 int launch_sum_vals(klnmf_ctx *ctx);        // DS_SUMX = sum of CSR values
+int l2_read_bench(int device, int64_t bytes, int iters, double *gbps);   // measurement support
 
 // ---- sparse path: sparse.cu ------------------------------------------------------------------------
 int sparse_rows(klnmf_ctx *ctx, int mode);    // 0 full pass, 1 objective only, 3 SDDMM only

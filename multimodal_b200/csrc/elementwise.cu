@@ -373,6 +373,57 @@ int launch_colsum_w(klnmf_ctx *ctx, const void *W, const void *Wlo, double *out)
   return KLNMF_OK;
 }
 
+// measurement support: sustained L2 -> SM read bandwidth (a buffer that fits the L2, read many times by every SM with
+// 16-byte loads) -- the denominator of the sparse path's L2 roofline (bench.py), whose gathers never leave the L2
+__global__ void l2_read_kernel(const float4 *__restrict__ p, int64_t n4, int iters, float *__restrict__ sink) {
+  float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  for (int it = 0; it < iters; it++) {
+    // a different starting offset per pass keeps the L1 out of it (every SM walks the whole buffer)
+    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x + (int64_t)it * 4099 * blockDim.x) % n4;
+    for (int64_t c = 0; c < n4; c += stride, i = (i + stride >= n4 ? i + stride - n4 : i + stride)) {
+      float4 v;
+      asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p + i));
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
+  }
+  if (acc.x + acc.y + acc.z + acc.w == 123.456f) sink[0] = acc.x;      // never true: keeps the loads alive
+}
+
+int l2_read_bench(int device, int64_t bytes, int iters, double *gbps) {
+  KL_CUDA(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  KL_CUDA(cudaGetDeviceProperties(&prop, device));
+  float4 *buf = nullptr;
+  float *sink = nullptr;
+  const int64_t n4 = bytes / 16;
+  KL_CHECK(n4 > (int64_t)prop.multiProcessorCount * 8 * 256, KLNMF_EINVAL, "l2_read_bench: buffer smaller than one grid stride");
+  KL_CUDA(cudaMalloc((void **)&buf, (size_t)n4 * 16));
+  KL_CUDA(cudaMalloc((void **)&sink, 16));
+  cudaMemset(buf, 0, (size_t)n4 * 16);
+  const int grid = prop.multiProcessorCount * 8, block = 256;
+  l2_read_kernel<<<grid, block>>>(buf, n4, 2, sink);                     // warm the L2
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventRecord(e0);
+  l2_read_kernel<<<grid, block>>>(buf, n4, iters, sink);
+  cudaEventRecord(e1);
+  cudaError_t se = cudaDeviceSynchronize();
+  float ms = 0.f;
+  cudaEventElapsedTime(&ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(buf);
+  cudaFree(sink);
+  if (se != cudaSuccess) { set_error("l2_read_bench: %s", cudaGetErrorString(se)); return KLNMF_ECUDA; }
+  // every pass reads ceil(n4 / stride) * stride elements
+  const int64_t stride = (int64_t)grid * block;
+  const double read = (double)((n4 + stride - 1) / stride * stride) * 16.0 * iters;
+  *gbps = read / (ms * 1e-3) / 1e9;
+  return KLNMF_OK;
+}
+
 int launch_split(klnmf_ctx *ctx, const float *src, float *hi, float *lo, int64_t rows, int64_t cols, int64_t ld) {
   if (rows * cols == 0) return KLNMF_OK;
   split_kernel<<<grid_for(ctx, rows * cols, 256), 256, 0, ctx->stream>>>(src, hi, lo, rows, cols, ld);

@@ -9,7 +9,8 @@
 #   phases:WORKLOAD:N:MODE[:ENV=V,..] bench.py --workload WORKLOAD --n N --mode MODE, prints ms/step + phase times
 #   bench[:ARGS]                      python bench.py ARGS (comma separated), prints the JSON line
 #   launches:NAME[:ARGS]              ncu launch list (gpu__time_duration) of bench.py ARGS -> gpurun_out/NAME.csv
-#   ncu:KERNEL_REGEX:NAME[:ARGS]      ncu --set full of the 2nd launch matching KERNEL_REGEX -> gpurun_out/NAME.ncu-rep
+#   ncu:KERNEL_REGEX:NAME:ARGS[:S,C]  ncu --set full of C launches matching KERNEL_REGEX after skipping S (default 1,1)
+#                                     -> gpurun_out/NAME.ncu-rep
 #   py:SCRIPT[:ARGS]                  python SCRIPT ARGS
 #   dist:N[:ARGS[:ENV=V,..]]          bench.py ARGS under torchrun on N GPUs (+ NCCL transport summary)
 #   distpy:N:SCRIPT[:ARGS]            any script under torchrun on N GPUs
@@ -46,7 +47,8 @@ for STEP in "$@"; do
     phases)  env KLNMF_PROFILE=1 $(echo "$A4" | tr ',' ' ') timeout 900 python bench.py --workload "$A1" ${A2:+--n "$A2"} --mode "$A3" --no-cpu --no-e2e --alt-mode= --no-extra 2>&1 | tail -1 | python -c "$P" ;;
     bench)   timeout 1800 python bench.py $(echo "$A1" | tr ',' ' ') 2>&1 | tail -3 ;;
     launches) timeout 1500 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/$A1.csv python bench.py $(echo "$A2" | tr ',' ' ') 2>&1 | tail -1 | cut -c1-200 ;;
-    ncu)     timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:$A1" -s 1 -c 1 -f -o gpurun_out/$A2 python bench.py $(echo "$A3" | tr ',' ' ') 2>&1 | tail -2 | cut -c1-200 ;;
+    ncu)     # ncu:KERNEL_REGEX:NAME:ARGS[:SKIP,COUNT]   (default: skip 1 matching launch, capture 1)
+             SC=${A4:-1,1}; timeout 1500 ncu --set full --clock-control none --import-source on -k "regex:$A1" -s ${SC%,*} -c ${SC#*,} -f -o gpurun_out/$A2 python bench.py $(echo "$A3" | tr ',' ' ') 2>&1 | tail -2 | cut -c1-200 ;;
     py)      timeout 1500 python $A1 $(echo "$A2" | tr ',' ' ') 2>&1 | tail -40 ;;
     dist)    # dist:N[:ARGS[:ENV=V,..]]  bench.py under torchrun on N GPUs; NCCL's transport choice is summarised from NCCL_DEBUG=INFO
              env NCCL_DEBUG=INFO NCCL_DEBUG_FILE=gpurun_out/$LABEL.nccl.%h.%p $(echo "$A3" | tr ',' ' ') timeout 1500 python -m torch.distributed.run --nnodes=1 --nproc-per-node "$A1" --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus "$A1" $(echo "$A2" | tr ',' ' ') > gpurun_out/$LABEL.dist$A1.out 2>&1
