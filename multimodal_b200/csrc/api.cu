@@ -903,7 +903,7 @@ int klnmf_run_resume(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, doub
     int r = KLNMF_OK;
     if (fit) r = launch_zero(ctx, ctx->num, hbytes);
     if (r == KLNMF_OK && ctx->sparse && ctx->n > 0) {
-      { PhaseTimer t(ctx, prof, PH_RATIO); r = sparse_rows(ctx, 0); }
+      { PhaseTimer t(ctx, prof, PH_RATIO); r = sparse_rows(ctx, 0, fit ? 2 : 0); }
       if (r == KLNMF_OK && fit) { PhaseTimer t(ctx, prof, PH_NUM); r = sparse_scatter(ctx, false); }
     } else if (r == KLNMF_OK) {
       r = dense_iteration(ctx, fit, false, prof);
@@ -1017,7 +1017,7 @@ int klnmf_dictionary_step(klnmf_ctx *ctx) {
   KL_TRY(launch_zero(ctx, ctx->num, hbytes));
   if (ctx->sparse) {
     if (ctx->n > 0) {
-      KL_TRY(sparse_rows(ctx, 0));
+      KL_TRY(sparse_rows(ctx, 0, 2));
       KL_TRY(sparse_scatter(ctx, true));
     }
   } else {
@@ -1041,7 +1041,7 @@ int klnmf_ratio_host(klnmf_ctx *ctx, void *out, int dtype, int64_t ld) {
   KL_TRY(reset_reduction(ctx));
   if (ctx->sparse) {
     if (ctx->nnz > 0) {
-      KL_TRY(sparse_rows(ctx, 0));
+      KL_TRY(sparse_rows(ctx, 0, 1));
       KL_TRY(download_matrix(ctx, ctx->qnz, nullptr, ctx->nnz, out, dtype, ctx->nnz, 1, ctx->nnz, false));
     }
   } else {

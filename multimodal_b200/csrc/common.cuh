@@ -204,7 +204,9 @@ int launch_sum_vals(klnmf_ctx *ctx);        // DS_SUMX = sum of CSR values
 int l2_read_bench(int device, int64_t bytes, int iters, double *gbps);   // measurement support
 
 // ---- sparse path: sparse.cu ------------------------------------------------------------------------
-int sparse_rows(klnmf_ctx *ctx, int mode);    // 0 full pass, 1 objective only, 3 SDDMM only
+// mode: 0 full pass, 1 objective only, 3 SDDMM only.  q_order (mode 0): 0 the ratio is not kept (transform), 1 kept in
+// CSR order (the _Q hook), 2 kept in blocked-CSC order for the numerator pass (fit)
+int sparse_rows(klnmf_ctx *ctx, int mode, int q_order = 0);
 int sparse_scatter(klnmf_ctx *ctx, bool use_current_w);
 int sparse_init_w(klnmf_ctx *ctx);
 int sparse_fill_synthetic(klnmf_ctx *ctx, int64_t nnz_per_row, uint64_t seed);

@@ -186,7 +186,11 @@ sparse_rows_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict
         if (have && leader) {
           if (sizeof(T) == 4) klf += (float)xm * logf((float)q);
           else kl += (double)xm * log((double)q);
-          if (MODE == 0) qnz[p + mine] = q;
+          // (Writing q where the numerator pass reads it -- blocked-CSC order through a CSR -> blocked-CSC map, so that
+          // pass streams it instead of gathering 4 bytes per 32-byte sector -- was measured: the scattered 4-byte stores
+          // cost far more than the gathers they replace, rows pass 8.8 -> 20.0 ms at n = 500 000, numerator 13.3 -> 11.0;
+          // profiles/r2_run13_sparse_q_order.log.)
+          if (MODE == 0 && qnz != nullptr) qnz[p + mine] = q;
           if (MODE == 3) qnz[p + mine] = sm;
         }
       }
@@ -343,11 +347,27 @@ sparse_numerator_bcsc_kernel(const int64_t *__restrict__ indptr, const int32_t *
 #pragma unroll
   for (int c = 0; c < VPL; c++) act[c] = (128 * c + 4 * lane) < ldh && (128 * c + 4 * lane) < ldw;
   const int64_t units = n_blocks * f;
-  for (int64_t u = warp_global; u < units; u += n_warps) {   // block-major: the whole grid sweeps one row block at a time
+  // Software pipeline over the dependent loads (column range -> row index / ratio position -> ratio -> coefficient
+  // rows): the column range of the NEXT unit and the (row, ratio) pairs of the NEXT batch of eight entries are fetched
+  // before the eight row gathers of the current batch are issued, so the four L2 round trips of the chain overlap the
+  // gathers instead of preceding them (ncu: long_scoreboard was 75 % of all stall samples).
+  int64_t u = warp_global;
+  int32_t c0 = 0, c1 = 0;
+  if (u < units) {
+    const int32_t *cp = colptr + (u / f) * (f + 1) + (u % f);
+    c0 = __ldg(cp); c1 = __ldg(cp + 1);
+  }
+  for (; u < units; u += n_warps) {   // block-major: the whole grid sweeps one row block at a time
     const int64_t b = u / f, j = u - b * f;
-    const int32_t *cp = colptr + b * (f + 1) + j;
-    const int32_t c0 = __ldg(cp), c1 = __ldg(cp + 1);
-    if (c0 == c1) continue;
+    const int32_t t0 = c0, t1 = c1;
+    {
+      const int64_t un = u + n_warps;
+      if (un < units) {
+        const int32_t *cp = colptr + (un / f) * (f + 1) + (un % f);
+        c0 = __ldg(cp); c1 = __ldg(cp + 1);
+      }
+    }
+    if (t0 == t1) continue;
     const int64_t base = indptr[b * R];
     const T *Wb = Wn + b * R * ldw;
     T acc[VPL][4];
@@ -355,27 +375,34 @@ sparse_numerator_bcsc_kernel(const int64_t *__restrict__ indptr, const int32_t *
     for (int c = 0; c < VPL; c++)
 #pragma unroll
       for (int e = 0; e < 4; e++) acc[c][e] = (T)0;
-    for (int32_t t = c0; t < c1; t += 8) {
-      const int nb = c1 - t < 8 ? c1 - t : 8;
-      int32_t ri = 0;
-      T q = (T)0;
-      if (lane < nb) {
-        ri = __ldg(rowidx + base + t + lane);
-        q = qnz[base + __ldg(src + base + t + lane)];
+    int32_t ri = 0;
+    T q = (T)0;
+    if (lane < 8 && t0 + lane < t1) {
+      ri = __ldg(rowidx + base + t0 + lane);
+      q = qnz[base + __ldg(src + base + t0 + lane)];
+    }
+    for (int32_t t = t0; t < t1; t += 8) {
+      int32_t ri_n = 0;
+      T q_n = (T)0;
+      if (lane < 8 && t + 8 + lane < t1) {
+        ri_n = __ldg(rowidx + base + t + 8 + lane);
+        q_n = qnz[base + __ldg(src + base + t + 8 + lane)];
       }
 #pragma unroll
       for (int e8 = 0; e8 < 8; e8++) {
-        const int32_t i = __shfl_sync(0xffffffffu, ri, e8);    // lanes >= nb hold row 0 with q = 0
+        const int32_t i = __shfl_sync(0xffffffffu, ri, e8);    // lanes past the end hold row 0 with q = 0
         const T qq = __shfl_sync(0xffffffffu, q, e8);
 #pragma unroll
         for (int c = 0; c < VPL; c++)
           if (act[c]) {
             T w[4];
-            ld4(Wb + (int64_t)i * ldw + 128 * c + 4 * lane, w);
+            ldg4(Wb + (int64_t)i * ldw + 128 * c + 4 * lane, w);
 #pragma unroll
             for (int e = 0; e < 4; e++) acc[c][e] += qq * w[e];
           }
       }
+      ri = ri_n;
+      q = q_n;
     }
 #pragma unroll
     for (int c = 0; c < VPL; c++)
@@ -403,15 +430,26 @@ __global__ void fill_csr_kernel(int64_t *__restrict__ indptr, int32_t *__restric
   }
 }
 
+int bcsc_build(klnmf_ctx *ctx);
+// the blocked-CSC numerator (default) indexes a block's entries with int32 offsets: fine while nnz < 2^31 (cfg4: 5e8);
+// KLNMF_SPARSE_ATOMICS=1 selects the first version (one red.add per stored entry, CSR order)
+inline bool use_bcsc(const klnmf_ctx *ctx) {
+  static const bool atomics = getenv("KLNMF_SPARSE_ATOMICS") && atoi(getenv("KLNMF_SPARSE_ATOMICS")) == 1;
+  return !atomics && ctx->nnz > 0 && ctx->nnz < (((int64_t)1 << 31) - 1);
+}
+
+// q_order (mode 0 only): 0 = the ratio is not kept (transform: 4 bytes per stored entry less to write), 1 / 2 = kept in
+// CSR order, for the _Q hook / for the numerator pass
 template <typename T, int VPL>
-int run_rows(klnmf_ctx *ctx, int mode, const T *W, T *Wn) {
+int run_rows(klnmf_ctx *ctx, int mode, const T *W, T *Wn, int q_order) {
   const int grid = (int)(ceil_div(ctx->n, WARPS) < (int64_t)ctx->sm_count * 8 ? ceil_div(ctx->n, WARPS)
                                                                                : (int64_t)ctx->sm_count * 8);
   const int *stop = ctx->flags + FL_STOP;
   const T *Ht = (const T *)ctx->H[ctx->hcur];
   if (mode == 0)
     sparse_rows_kernel<T, VPL, 0><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->indptr, ctx->indices, (const T *)ctx->vals, W,
-                                                                        ctx->ldw, Ht, ctx->ldh, Wn, (T *)ctx->qnz, ctx->n,
+                                                                        ctx->ldw, Ht, ctx->ldh, Wn,
+                                                                        q_order == 0 ? nullptr : (T *)ctx->qnz, ctx->n,
                                                                         ctx->dred, stop);
   else if (mode == 1)
     sparse_rows_kernel<T, VPL, 1><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->indptr, ctx->indices, (const T *)ctx->vals, W,
@@ -433,7 +471,9 @@ int run_rows(klnmf_ctx *ctx, int mode, const T *W, T *Wn) {
 int bcsc_build(klnmf_ctx *ctx) {
   BlockedCsc *bc = new BlockedCsc();
   const int64_t row_bytes = ctx->ldw * (int64_t)ctx->es;
-  int64_t R = ((int64_t)24 << 20) / row_bytes / 1024 * 1024;      // W' block of about 24 MB: L2-resident
+  // W' block of about 24 MB: it stays L2-resident next to the k x f numerator the units add into (KLNMF_SPARSE_BLOCK_MB)
+  static const int64_t block_mb = getenv("KLNMF_SPARSE_BLOCK_MB") ? atoi(getenv("KLNMF_SPARSE_BLOCK_MB")) : 24;
+  int64_t R = ((block_mb > 0 ? block_mb : 24) << 20) / row_bytes / 1024 * 1024;
   if (R < 1024) R = 1024;
   if (R > ctx->n) R = ctx->n;
   bc->R = R;
@@ -471,9 +511,7 @@ template <typename T, int VPL>
 int run_scatter(klnmf_ctx *ctx, const T *Wn) {
   const int grid = (int)(ceil_div(ctx->n, WARPS) < (int64_t)ctx->sm_count * 8 ? ceil_div(ctx->n, WARPS)
                                                                                : (int64_t)ctx->sm_count * 8);
-  static const bool atomics = getenv("KLNMF_SPARSE_ATOMICS") && atoi(getenv("KLNMF_SPARSE_ATOMICS")) == 1;
-  // the blocked copy indexes a block's entries with int32 offsets: fine while nnz < 2^31 (cfg4: 5e8)
-  if (!atomics && ctx->nnz > 0 && ctx->nnz < (((int64_t)1 << 31) - 1)) {
+  if (use_bcsc(ctx)) {
     if (!ctx->bcsc) KL_TRY(bcsc_build(ctx));
     const BlockedCsc *bc = (const BlockedCsc *)ctx->bcsc;
     sparse_numerator_bcsc_kernel<T, VPL><<<ctx->sm_count * 8, WARPS * 32, 0, ctx->stream>>>(
@@ -492,12 +530,12 @@ int run_scatter(klnmf_ctx *ctx, const T *Wn) {
 }
 
 template <typename T>
-int dispatch_rows(klnmf_ctx *ctx, int mode, const T *W, T *Wn) {
+int dispatch_rows(klnmf_ctx *ctx, int mode, const T *W, T *Wn, int q_order) {
   const int64_t kp = ctx->ldw;
-  if (kp <= 128) return run_rows<T, 1>(ctx, mode, W, Wn);
-  if (kp <= 256) return run_rows<T, 2>(ctx, mode, W, Wn);
-  if (kp <= 512) return run_rows<T, 4>(ctx, mode, W, Wn);
-  if (kp <= 1024) return run_rows<T, 8>(ctx, mode, W, Wn);
+  if (kp <= 128) return run_rows<T, 1>(ctx, mode, W, Wn, q_order);
+  if (kp <= 256) return run_rows<T, 2>(ctx, mode, W, Wn, q_order);
+  if (kp <= 512) return run_rows<T, 4>(ctx, mode, W, Wn, q_order);
+  if (kp <= 1024) return run_rows<T, 8>(ctx, mode, W, Wn, q_order);
   set_error("sparse path supports n_components <= 1024 (got %lld)", (long long)ctx->k);
   return KLNMF_EINVAL;
 }
@@ -516,10 +554,10 @@ int dispatch_scatter(klnmf_ctx *ctx, const T *Wn) {
 
 // Pass 1 of the sparse iteration (SDDMM -> ratio -> objective -> SpMM -> W update), or with
 // only_error just the objective terms.
-int sparse_rows(klnmf_ctx *ctx, int mode) {
+int sparse_rows(klnmf_ctx *ctx, int mode, int q_order) {
   const int cur = ctx->cur;
-  return ctx->es == 8 ? dispatch_rows<double>(ctx, mode, (const double *)ctx->W[cur], (double *)ctx->W[cur ^ 1])
-                      : dispatch_rows<float>(ctx, mode, (const float *)ctx->W[cur], (float *)ctx->W[cur ^ 1]);
+  return ctx->es == 8 ? dispatch_rows<double>(ctx, mode, (const double *)ctx->W[cur], (double *)ctx->W[cur ^ 1], q_order)
+                      : dispatch_rows<float>(ctx, mode, (const float *)ctx->W[cur], (float *)ctx->W[cur ^ 1], q_order);
 }
 
 // Pass 2: dictionary numerator N^T[j,:] += q W'[i,:] over the stored non-zeros.
@@ -530,8 +568,8 @@ int sparse_scatter(klnmf_ctx *ctx, bool use_current_w) {
 }
 
 int sparse_init_w(klnmf_ctx *ctx) {
-  return ctx->es == 8 ? dispatch_rows<double>(ctx, 2, nullptr, (double *)ctx->W[ctx->cur])
-                      : dispatch_rows<float>(ctx, 2, nullptr, (float *)ctx->W[ctx->cur]);
+  return ctx->es == 8 ? dispatch_rows<double>(ctx, 2, nullptr, (double *)ctx->W[ctx->cur], 0)
+                      : dispatch_rows<float>(ctx, 2, nullptr, (float *)ctx->W[ctx->cur], 0);
 }
 
 void sparse_release_pattern(klnmf_ctx *ctx) {

@@ -17,7 +17,7 @@ import subprocess
 import sys
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum", "lts__t_bytes.sum",
         "lts__t_sectors_srcunit_tex_op_read.sum", "lts__t_sectors_srcunit_tex_op_write.sum",
         "sm__pipe_tc_cycles_active.avg.pct_of_peak_sustained_active",
         "sm__inst_executed_pipe_xu.avg.pct_of_peak_sustained_active",
@@ -26,6 +26,8 @@ KEYS = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "smsp__inst_executed.sum"]
 MATCH = {"ratio": "tc_gemm_kernel<256, 0, 1, 0, 1", "coefficient": "tc_gemm_kernel<256, 0, 0, 0, 0",
          "numerator": "tc_gemm_kernel<256, 1, 1, 0, 0", "fused": "fused_coef_kernel", "fused256": "fused_coef256_kernel",
+         "fp64_ratio": "generic_gemm_kernel<double, 1>", "fp64_coefficient": "generic_gemm_kernel<double, 2>",
+         "fp64_numerator": "generic_gemm_kernel<double, 3>",
          "sparse_rows": "sparse_rows_kernel", "sparse_scatter": "sparse_numerator_bcsc_kernel"}
 UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0}
 
