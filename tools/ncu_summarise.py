@@ -81,6 +81,7 @@ def main():
                 if MATCH[key] in r[hdr.index("Kernel Name")]:
                     rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
                     tot = float(r[rd]) * UNIT[units[rd]] + float(r[wr]) * UNIT[units[wr]]
+                    key = key[5:] if key.startswith("fp64_") else key      # bench.py looks the phase name up, the mode tells them apart
                     e = {"kernel": key, "rows": int(rows_), "f": int(f), "k": int(k), "mode": mode, "dram_bytes": tot,
                          "dram_bytes_read": float(r[rd]) * UNIT[units[rd]], "dram_bytes_write": float(r[wr]) * UNIT[units[wr]],
                          "report": os.path.basename(rep), "kernel_name": r[hdr.index("Kernel Name")][:120]}
