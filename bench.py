@@ -399,6 +399,10 @@ def run_e2e(args, n_local, f, k, kind, mode, local, rank, world, dist, X_host, H
         from multimodal_b200 import distributed as D
         sh = D.ShardedNMF(k, max_iter=iters, tol=0, mode=mode, device=local)
         sh.components_ = H0
+        if kind == "dense_fit":
+            # the same contract as the one-GPU leg (MultimodalLearner.train -> KLdivNMF.fit): the dictionary comes back,
+            # the coefficients of the shard stay on the device (nmf.py:259-273 throws them away)
+            return sh.fit(X, X.shape[0] * world, H0=H0).components_
         return sh.fit_transform(X, X.shape[0] * world, H0=H0, fit=(kind != "dense_transform"))
 
     # one untimed warm-up call on a small slice: the process-wide pinned staging buffers, kernel attributes, the
@@ -419,8 +423,8 @@ def run_e2e(args, n_local, f, k, kind, mode, local, rank, world, dist, X_host, H
     dt = time.perf_counter() - t0
     dt = allreduce_max(dist, local, dt)
     h2d = X_host.nbytes if not hasattr(X_host, "nnz") else (X_host.data.nbytes + X_host.indices.nbytes + X_host.indptr.nbytes)
-    if learner_path:
-        d2h = out.nbytes                      # the trained dictionary; train() keeps the coefficients on the device
+    if learner_path or (world > 1 and kind == "dense_fit"):
+        d2h = out.nbytes                      # the trained dictionary; the fit keeps the coefficients on the device
     else:
         d2h = out.nbytes + (H0.nbytes if kind != "dense_transform" else 0)
     return dt, h2d, d2h, learner_path
@@ -601,7 +605,7 @@ def run_ours(args):
         e2e = legs[0]
         e2e["note"] = ("one %s call of %d iterations (after an untimed warm-up call on a 65536-row slice); X crosses PCIe "
                        "once per call, so per-step bytes are the call's bytes / steps" % (what, args.steps)) + \
-            ("; %d ranks, each through distributed.ShardedNMF on its own pinned shard" % world if world > 1 else "") + \
+            ("; %d ranks, each through distributed.ShardedNMF%s on its own pinned shard" % (world, ".fit (the dictionary is read back)" if kind == "dense_fit" else "") if world > 1 else "") + \
             ("" if rows == n_local else "; host RAM too small for the full shard: measured on %d rows and scaled "
              "linearly in n" % rows)
         if len(legs) > 1:

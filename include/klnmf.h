@@ -83,6 +83,25 @@ int klnmf_set_dense_device(klnmf_ctx *ctx, const void *X_dev, int dtype, int64_t
  * No stacked copy is ever made on the host. */
 int klnmf_set_dense_blocks_host(klnmf_ctx *ctx, int n_blocks, const void *const *X, const int *dtypes,
                                 const int64_t *lds, const int64_t *cols, const double *scales, const int *product_f32);
+/* The same stack when at least one modality is sparse: the reference then makes the WHOLE stack sparse
+ * (scipy.sparse.hstack, array_utils.py:5-9), sparsifying, scaling and concatenating on the host.  Here every block is
+ * uploaded as it is and the scaled, stacked CSR matrix is built on the device (count -> scan -> fill); zeros -- explicit
+ * ones of a CSR block, any of a dense block -- are dropped, as the reference's eliminate_zeros() drops them from the
+ * stack before its first use (nmf.py:66).  CSR blocks: canonical (sorted indices, no duplicates), int64 indptr. */
+typedef struct klnmf_block {
+  int kind;                 /* 0: dense row-major host array, 1: CSR host arrays                               */
+  int dtype;                /* KLNMF_F32 / KLNMF_F64 of the dense array or of the CSR values                    */
+  int64_t cols;             /* width of the modality                                                            */
+  double scale;             /* its coefficient                                                                  */
+  int product_f32;          /* form scale * x in float (numpy: float32 data with a float32 / Python-float coef) */
+  const void *dense;        /* kind 0: n x cols, row pitch ld elements                                          */
+  int64_t ld;
+  const int64_t *indptr;    /* kind 1: n + 1                                                                    */
+  const int32_t *indices;   /*         nnz                                                                      */
+  const void *values;       /*         nnz                                                                      */
+  int64_t nnz;
+} klnmf_block;
+int klnmf_set_stacked_blocks_host(klnmf_ctx *ctx, int n_blocks, const klnmf_block *blocks);
 /* CSR with sorted-or-not column indices, no duplicate entries, explicit zeros already
  * removed (the reference calls eliminate_zeros() on the caller's matrix, nmf.py:66). */
 int klnmf_set_csr_host(klnmf_ctx *ctx, const int64_t *indptr, const int32_t *indices,

@@ -27,6 +27,12 @@ _c_int = ctypes.c_int
 _c_vp = ctypes.c_void_p
 _c_dbl = ctypes.c_double
 
+class Block(ctypes.Structure):
+    """klnmf_block (include/klnmf.h): one modality of a stack, dense or CSR, with its coefficient."""
+    _fields_ = [("kind", _c_int), ("dtype", _c_int), ("cols", _c_i64), ("scale", _c_dbl), ("product_f32", _c_int),
+                ("dense", _c_vp), ("ld", _c_i64), ("indptr", _c_vp), ("indices", _c_vp), ("values", _c_vp), ("nnz", _c_i64)]
+
+
 # name -> (restype, argtypes); must list every symbol include/klnmf.h declares
 PROTOTYPES = {
     "klnmf_abi_version": (_c_int, []),
@@ -39,6 +45,7 @@ PROTOTYPES = {
     "klnmf_set_dense_host": (_c_int, [_c_vp, _c_vp, _c_int, _c_i64]),
     "klnmf_set_dense_device": (_c_int, [_c_vp, _c_vp, _c_int, _c_i64]),
     "klnmf_set_dense_blocks_host": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
+    "klnmf_set_stacked_blocks_host": (_c_int, [_c_vp, _c_int, ctypes.POINTER(Block)]),
     "klnmf_set_csr_host": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_i64]),
     "klnmf_set_csr_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_i64]),
     "klnmf_create_column_view": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_i64, ctypes.POINTER(_c_vp)]),
@@ -219,6 +226,43 @@ class Engine(object):
         scl = (ctypes.c_double * nb)(*[float(s) for s in scales])
         pf = (ctypes.c_int * nb)(*f32)
         _check(self.lib.klnmf_set_dense_blocks_host(self.h, nb, ptrs, dts, lds, cols, scl, pf))
+
+    def set_stacked_blocks(self, blocks, scales):
+        """safe_hstack([c * m]) of learner.stack_data (learner.py:53-56) when a modality is sparse -- the reference then
+        makes the whole stack sparse on the host (array_utils.py:5-9).  `blocks` are host ndarrays and canonical scipy CSR
+        matrices (n, f_b); they are uploaded as they are and the scaled, stacked CSR matrix is built on the device
+        (klnmf_set_stacked_blocks_host)."""
+        import scipy.sparse as sp
+        arr = (Block * len(blocks))()
+        keep = []
+        for i, (m, c) in enumerate(zip(blocks, scales)):
+            b = arr[i]
+            b.scale = float(c)
+            b.cols = int(m.shape[1])
+            assert m.shape[0] == self.n, (m.shape, self.n)
+            if sp.issparse(m):
+                m = m.tocsr()
+                # numpy's promotion of `c * m` decides in which precision the reference forms the product
+                b.product_f32 = 1 if (c * m.data[:0]).dtype == np.float32 else 0
+                indptr = np.ascontiguousarray(m.indptr, dtype=np.int64)
+                indices = np.ascontiguousarray(m.indices, dtype=np.int32)
+                data = np.ascontiguousarray(m.data) if m.data.dtype == np.float32 else np.ascontiguousarray(m.data, dtype=np.float64)
+                keep += [indptr, indices, data]
+                b.kind, b.dtype, b.nnz = 1, (F32 if data.dtype == np.float32 else F64), int(m.nnz)
+                b.indptr, b.indices, b.values = indptr.ctypes.data, indices.ctypes.data, data.ctypes.data
+            else:
+                m = np.asarray(m)
+                b.product_f32 = 1 if (c * m[:0, :0]).dtype == np.float32 else 0
+                if m.dtype not in (np.float32, np.float64):
+                    m = m.astype(np.float64)
+                if m.strides[1] != m.itemsize or m.strides[0] < m.shape[1] * m.itemsize:
+                    m = np.ascontiguousarray(m)
+                keep.append(m)
+                b.kind, b.dtype = 0, (F32 if m.dtype == np.float32 else F64)
+                b.dense, b.ld = m.ctypes.data, ((m.strides[0] // m.itemsize) if self.n > 1 else m.shape[1])
+        assert sum(int(b.cols) for b in arr) == self.f
+        _check(self.lib.klnmf_set_stacked_blocks_host(self.h, len(blocks), arr))
+        del keep
 
     def set_dense_device(self, ptr, dtype, ld, keepalive=None):
         self._keep.append(keepalive)

@@ -15,7 +15,7 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(CSRC, "libklnmf.so")
-SOURCES = ["api.cu", "dense_generic.cu", "dense_tc.cu", "dense_fused.cu", "dense_fused256.cu", "elementwise.cu", "sparse.cu", "evaluation.cu", "nccl_dyn.cu"]
+SOURCES = ["api.cu", "dense_generic.cu", "dense_tc.cu", "dense_fused.cu", "dense_fused256.cu", "elementwise.cu", "sparse.cu", "evaluation.cu", "nccl_dyn.cu", "stack.cu"]
 HEADERS = ["common.cuh", "tc_ptx.cuh", os.path.join("..", "..", "include", "klnmf.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC", "-diag-suppress", "128,177"]

@@ -669,6 +669,20 @@ int klnmf_set_csr_host(klnmf_ctx *ctx, const int64_t *indptr, const int32_t *ind
   return KLNMF_OK;
 }
 
+int klnmf_set_stacked_blocks_host(klnmf_ctx *ctx, int n_blocks, const klnmf_block *blocks) {
+  KL_CHECK(ctx && blocks, KLNMF_EINVAL, "set_stacked_blocks_host: NULL argument");
+  KL_CUDA(cudaSetDevice(ctx->device));
+  KL_TRY(kind_guard(ctx, true));
+  release_data(ctx);
+  KL_TRY(stack_blocks_to_csr(ctx, n_blocks, blocks));
+  KL_TRY(dmalloc(&ctx->qnz, ctx->nnz * ctx->es));
+  KL_TRY(ensure_state(ctx));
+  KL_TRY(launch_sum_vals(ctx));
+  KL_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->have_x = true;
+  return KLNMF_OK;
+}
+
 int klnmf_set_csr_device(klnmf_ctx *ctx, const int64_t *indptr_dev, const int32_t *indices_dev, const void *values_dev,
                          int dtype, int64_t nnz) {
   KL_CHECK(ctx && indptr_dev && nnz >= 0, KLNMF_EINVAL, "set_csr_device: bad argument");

@@ -212,6 +212,9 @@ int sparse_init_w(klnmf_ctx *ctx);
 int sparse_fill_synthetic(klnmf_ctx *ctx, int64_t nnz_per_row, uint64_t seed);
 void sparse_release_pattern(klnmf_ctx *ctx);   // drop the blocked-CSC copy (the data changed)
 
+// ---- device-side stacking of mixed dense / CSR modality blocks: stack.cu ------------------------------
+int stack_blocks_to_csr(klnmf_ctx *ctx, int n_blocks, const klnmf_block *blocks);   // fills ctx->indptr / indices / vals / nnz
+
 // ---- NCCL through dlopen: nccl_dyn.cu ----------------------------------------------------------------
 int nccl_load(const char *path);
 int nccl_unique_id(void *id128);

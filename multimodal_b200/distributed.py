@@ -125,9 +125,11 @@ def group_comms(devices):
 
 def _rows(X, r0, r1):
     """Row block of a dense array (a view), a CSR matrix (a copy of the block) or a StackedBlocks stack."""
-    from .lib.array_utils import StackedBlocks
+    from .lib.array_utils import StackedBlocks, MixedBlocks
     if isinstance(X, StackedBlocks):
         return StackedBlocks([b[r0:r1] for b in X.blocks], X.coefs)
+    if isinstance(X, MixedBlocks):
+        return MixedBlocks([b[r0:r1] for b in X.blocks], X.coefs)
     return X[r0:r1]
 
 
@@ -207,7 +209,7 @@ class ShardedNMF(object):
             eng.comm_attach(rank_comm(self.device))
         return eng
 
-    def fit_transform(self, X_local, n_global, H0=None, fit=True, return_errors=False):
+    def fit_transform(self, X_local, n_global, H0=None, fit=True, return_errors=False, want_coefficients=True):
         f = X_local.shape[1]
         if H0 is None:
             H0 = self.components_ if not fit else draw_shared_dictionary(self.n_components, f)
@@ -216,9 +218,15 @@ class ShardedNMF(object):
             eng.set_dictionary(H0)
             eng.init_coefficients()
             errors, n_iter = eng.run(self.max_iter, self.tol * n_global * f, fit)
-            W = eng.get_coefficients()
+            W = eng.get_coefficients() if want_coefficients else None
             if fit:
                 self.components_ = eng.get_dictionary()
         finally:
             eng.close()
         return (W, list(errors)) if return_errors else W
+
+    def fit(self, X_local, n_global, H0=None):
+        """Like KLdivNMF.fit (nmf.py:259-273): the dictionary is learnt and kept (`components_`, identical on every
+        rank), the coefficients of the shard are thrown away -- and therefore never leave the device."""
+        self.fit_transform(X_local, n_global, H0=H0, fit=True, want_coefficients=False)
+        return self

@@ -12,7 +12,9 @@ Column layout of the dictionary (learner.py:43-65): modality i owns columns [sum
 import numpy as np
 
 from . import _native
-from .lib.array_utils import StackedBlocks, safe_hstack
+import scipy.sparse as sp
+
+from .lib.array_utils import MixedBlocks, StackedBlocks, safe_hstack
 from .lib.nmf import KLdivNMF as NMF
 
 
@@ -60,11 +62,15 @@ class MultimodalLearner(object):
 
     def stack_data(self, modalities, data_matrices):
         """coef-weighted concatenation in the order of `modalities` (learner.py:53-56).  A sparse block makes the
-        whole stack sparse (array_utils.py:5-9); several dense blocks stay apart until the device has them."""
+        whole stack sparse (array_utils.py:5-9).  Several blocks stay apart until the device has them: dense ones are
+        scaled and concatenated there (StackedBlocks), a mix of dense and sparse ones is turned into the scaled, stacked
+        CSR matrix there (MixedBlocks) -- no sparsification, scaling or stacking pass on the host."""
         weights = [self.coef[self.get_index(name)] for name in modalities]
-        all_dense = all(isinstance(block, np.ndarray) and block.ndim == 2 for block in data_matrices)
-        if all_dense and len(data_matrices) > 1:
+        dense = [isinstance(block, np.ndarray) and block.ndim == 2 for block in data_matrices]
+        if all(dense) and len(data_matrices) > 1:
             return StackedBlocks(data_matrices, weights)
+        if len(data_matrices) > 1 and all(d or sp.issparse(block) for d, block in zip(dense, data_matrices)):
+            return MixedBlocks(data_matrices, weights)
         return safe_hstack([w * block for block, w in zip(data_matrices, weights)])
 
     # ---- training (learner.py:31-41) --------------------------------------------------------------------------

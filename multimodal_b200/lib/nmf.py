@@ -18,7 +18,7 @@ import numpy as np
 import scipy.sparse as sp
 
 from .. import _native
-from .array_utils import normalize_sum, StackedBlocks
+from .array_utils import normalize_sum, StackedBlocks, MixedBlocks
 from .sklearn_utils import atleast2d_or_csr
 
 _EPS = 1.e-8      # the loop's literal eps (nmf.py:232, 297, 325); the kernels hard-wire it
@@ -73,6 +73,8 @@ def _load(eng, X):
     """Hand X (dense array, CSR matrix or a stack of dense modality blocks) to an engine."""
     if isinstance(X, StackedBlocks):
         eng.set_dense_blocks(X.blocks, X.coefs)
+    elif isinstance(X, MixedBlocks):
+        eng.set_stacked_blocks(X.blocks, X.coefs)
     elif sp.issparse(X):
         eng.set_csr(X)
     else:
@@ -97,6 +99,8 @@ def _engine_for(X, k, mode, device):
 
 def _host_prepare(X):
     """atleast2d_or_csr (nmf.py:193) and the dtype the device copy is made from; no O(n f) scan on the host."""
+    if isinstance(X, MixedBlocks):
+        return X.canonical()
     if not isinstance(X, StackedBlocks) and not _is_device_features(X):
         X = atleast2d_or_csr(X, check_finite=False)
         if sp.issparse(X):
@@ -192,7 +196,8 @@ class KLdivNMF(object):
         `y`, `weights` and `scale_W` are accepted and ignored exactly as in the
         reference (nmf.py:222 never forwards scale_W).
         """
-        Xv = X if (isinstance(X, StackedBlocks) or _is_device_features(X)) else atleast2d_or_csr(X, check_finite=False)
+        Xv = X if (isinstance(X, (StackedBlocks, MixedBlocks)) or _is_device_features(X)) \
+            else atleast2d_or_csr(X, check_finite=False)
         n_samples, n_features = Xv.shape
         if not self.n_components:
             self.n_components = n_features

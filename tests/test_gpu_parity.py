@@ -328,3 +328,47 @@ def test_batched_multi_subset_transform_vs_oracle(within, mode):
         bad[2] = bad[2].astype(np.float64)
         bad[2][3, 4] = -1.0
         lr.reconstruct_internal_batch(bad, subsets, 2)
+
+
+@pytest.mark.parametrize("mode", ["fp64", "tf32r"])
+def test_mixed_dense_and_csr_stack_built_on_the_device(within, mode):
+    """a dense modality next to a sparse one.  The reference sparsifies, scales and stacks on the host
+    (learner.py:53-56 -> scipy.sparse.hstack, array_utils.py:5-9); here the blocks are uploaded as they are and the
+    scaled CSR stack is built on the device (klnmf_set_stacked_blocks_host).  Same dictionary and coefficients as the
+    reference formula fed to the estimator, and as the float64 oracle; zeros of the dense block and explicit zeros of
+    the CSR block are dropped like eliminate_zeros() drops them (nmf.py:66)."""
+    rs = np.random.RandomState(31)
+    n = 260
+    motion = rs.dirichlet(0.1 * np.ones(40), n)
+    motion[motion < 1e-3] = 0.0                                   # real zeros in the dense modality
+    motion[7, :] = 0.0                                            # and an all-zero row of it
+    sound = sp.random(n, 300, density=0.05, random_state=rs, format='csr')
+    sound.data = np.ceil(5 * sound.data)
+    sound.data[::17] = 0.0                                        # explicit zeros in the CSR modality
+    image = rs.random_sample((n, 33)).astype(np.float32)
+    mods, dims = ['motion', 'sound', 'image'], [40, 300, 33]
+    coefs = [1. / np.mean(np.sum(motion, axis=1)), 1. / np.mean(np.asarray(sound.sum(axis=1))), np.float32(0.5)]
+    lr = MultimodalLearner(mods, dims, coefs, 7, mode=mode)
+    stack = lr.stack_data(mods, [motion, sound, image])
+    from multimodal_b200.lib.array_utils import MixedBlocks
+    assert isinstance(stack, MixedBlocks)
+    n_explicit = sound.nnz
+    np.random.seed(5)
+    lr.train([motion, sound, image], 10)
+    assert sound.nnz == n_explicit                               # the caller's modality matrix is left alone
+    V = sp.hstack([c * m for m, c in zip([motion, sound, image], coefs)]).tocsr()     # the reference's stack
+    est = KLdivNMF(n_components=7, max_iter=10, tol=0, mode=mode)
+    np.random.seed(5)
+    est.fit(V)
+    within("device_stack_vs_host_stack", cases.rel_fro(lr.dico, est.components_) + 1e-300, 1e-12 if mode == "fp64" else 2e-6)
+    ref = O.Learner(mods, dims, coefs, 7)
+    np.random.seed(5)
+    ref.train([motion, sound.copy(), image], 10)
+    within("dico", cases.rel_fro(lr.dico, ref.dico), 1e-12 if mode == "fp64" else 2e-5)
+    internal = lr.reconstruct_internal_multi(['motion', 'sound'], [motion[:50], sound[:50]], 10)
+    internal_ref = ref.reconstruct_internal_multi(['motion', 'sound'], [motion[:50], sound[:50]], 10)
+    within("internal", cases.rel_fro(internal, internal_ref), 1e-12 if mode == "fp64" else 2e-5)
+    with pytest.raises(ValueError, match="Negative values"):
+        bad = motion.copy()
+        bad[3, 3] = -0.5
+        lr.train([bad, sound, image], 2)

@@ -160,8 +160,14 @@ def test_stack_data_of_dense_modalities_is_lazy_and_equals_the_reference_formula
     sub = lr.stack_data(['c', 'a'], [c, a])                      # modality order of the call, coefficients by name
     np.testing.assert_array_equal(sub.toarray(), np.hstack([3. * c, 2. * a]))
     assert isinstance(lr.stack_data(['b'], [b]), np.ndarray)     # one modality: a plain scaled copy, as before
-    mixed = lr.stack_data(['a', 'b'], [a, sp.csr_matrix(b)])     # any sparse block makes the stack sparse
-    assert sp.issparse(mixed) and mixed.shape == (7, 8)
+    # any sparse block makes the reference's stack sparse (array_utils.py:5-9); here the blocks stay apart until the
+    # device builds that CSR matrix, and `tocsr()` is the reference's formula
+    from multimodal_b200.lib.array_utils import MixedBlocks
+    mixed = lr.stack_data(['a', 'b'], [a, sp.csr_matrix(b)])
+    assert isinstance(mixed, MixedBlocks) and mixed.shape == (7, 8)
+    ref = sp.hstack([2. * a, .5 * sp.csr_matrix(b)]).tocsr()
+    assert sp.issparse(mixed.tocsr()) and np.array_equal(mixed.toarray(), ref.toarray())
+    assert sp.issparse(lr.stack_data(['b'], [sp.csr_matrix(b)]))   # one sparse modality: a plain scaled matrix
 
 
 def test_device_group_host_helpers():
