@@ -924,9 +924,13 @@ int klnmf_run_resume(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, doub
     }
     if (r == KLNMF_OK && ctx->world > 1) {
       PhaseTimer t(ctx, prof, PH_COMM);
-      r = nccl_allreduce_sum_f64(ctx, ctx->dred, 2 + ctx->k);
+      // one NCCL group: the k x f numerator and the handful of FP64 partials travel in one launch
+      r = nccl_group_start();
+      if (r == KLNMF_OK) r = nccl_allreduce_sum_f64(ctx, ctx->dred, 2 + ctx->k);
       if (r == KLNMF_OK && fit)
         r = nccl_allreduce_sum(ctx, ctx->num, (ctx->sparse ? ctx->f : ctx->k) * ctx->ldh, ctx->es);
+      const int r_end = nccl_group_end();
+      if (r == KLNMF_OK) r = r_end;
     }
     if (r == KLNMF_OK) r = launch_decide(ctx, it);
     if (r == KLNMF_OK && fit) {
