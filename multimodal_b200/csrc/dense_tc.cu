@@ -124,14 +124,25 @@ __device__ __forceinline__ void epilogue_chunk(const TcParams &p, int64_t row, i
     float x[32], q[32];
     ld_row32(p.aux + row * p.ldaux + col0, x);
     float part = 0.f;
-    // split-TF32 contractions are FP32-grade, so their epilogue uses IEEE division and logf
+    if (p.accurate) {
+      // TF32R on a tile shape the TMA-staged form does not serve (f <= 128, single CTAs): the same arithmetic as there --
+      // cancellation-free objective, centered ratio rounded to nearest before the consumers multiply it
 #pragma unroll
-    for (int j = 0; j < 32; j++) part += ratio_term<SPLIT>(x[j], acc[j], q[j]);
+      for (int j = 0; j < 32; j++) part += ratio_term_cf(x[j], acc[j], q[j]);
+    } else {
+      // (split-TF32 contractions take epilogue_ratio_staged; SPLIT here only in bring-up configurations)
+#pragma unroll
+      for (int j = 0; j < 32; j++) part += ratio_term<SPLIT>(x[j], acc[j], q[j]);
+    }
     // columns >= N hold x = 0, s = 0: q = 1, the term is exactly 0
     kl += (double)part;
     if (!p.only_kl) {
 #pragma unroll
       for (int j = 0; j < 32; j++) q[j] -= p.qshift;
+      if (p.round_out && !p.out_lo) {
+#pragma unroll
+        for (int j = 0; j < 32; j++) q[j] = tf32_round(q[j]);
+      }
       if (p.out_lo) {
         float lo[32];
 #pragma unroll
