@@ -91,8 +91,9 @@ int ensure_state(klnmf_ctx *ctx) {
       KL_CUDA(cudaMemsetAsync(ctx->Hlo[i], 0, hbytes, ctx->stream));
     }
   }
-  KL_TRY(dmalloc(&ctx->num, hbytes));
-  KL_CUDA(cudaMemsetAsync(ctx->num, 0, hbytes, ctx->stream));
+  ctx->num_bytes = hbytes + (ctx->sparse ? 0 : h_rows * 8 * 32 * es);     // room for the chunked layout's padding (<= 8 chunks)
+  KL_TRY(dmalloc(&ctx->num, ctx->num_bytes));
+  KL_CUDA(cudaMemsetAsync(ctx->num, 0, ctx->num_bytes, ctx->stream));
   ctx->dred_len = 2 + ctx->ldw + 128;
   KL_TRY(dmalloc((void **)&ctx->dred, ctx->dred_len * 8));
   KL_CUDA(cudaMemsetAsync(ctx->dred, 0, ctx->dred_len * 8, ctx->stream));
@@ -306,6 +307,41 @@ struct PhaseTimer {
   }
 };
 
+// elements of the numerator buffer that hold data (what a whole-buffer all-reduce covers)
+int64_t num_elems(const klnmf_ctx *ctx) {
+  if (ctx->sparse) return ctx->f * ctx->ldh;
+  return ctx->num_chunks > 1 ? (int64_t)ctx->num_chunks * ctx->k * ctx->num_cc : ctx->k * ctx->ldh;
+}
+
+// Dense fit on several ranks: keep the numerator in contiguous f-chunks so that finished chunks can be all-reduced while
+// later ones are contracted (dense_iteration).  KLNMF_AR_CHUNKS (1..8, default 4; 1 = one all-reduce after the
+// numerator) and KLNMF_AR_CHUNK_MIN_F (default 2048: narrower dictionaries reduce in one piece) tune it.
+int setup_num_chunks(klnmf_ctx *ctx, int fit) {
+  int nch = 1;
+  if (fit && !ctx->sparse && ctx->world > 1) {
+    const char *e = getenv("KLNMF_AR_CHUNKS");
+    nch = e ? atoi(e) : 4;
+    if (nch < 1) nch = 1;
+    if (nch > 8) nch = 8;
+    const char *m = getenv("KLNMF_AR_CHUNK_MIN_F");
+    const int64_t min_f = m ? atoll(m) : 2048;
+    if (ctx->f < min_f || ctx->f < 32 * nch) nch = 1;
+  }
+  int64_t cc = 0;
+  if (nch > 1) {
+    cc = round_up(ceil_div(ctx->ldh, nch), 32);
+    if ((int64_t)nch * ctx->k * cc * ctx->es > ctx->num_bytes) { nch = 1; cc = 0; }
+  }
+  if (nch > 1 && !ctx->comm_stream) {
+    KL_CUDA(cudaStreamCreateWithFlags(&ctx->comm_stream, cudaStreamNonBlocking));
+    for (int c = 0; c < 8; c++) KL_CUDA(cudaEventCreateWithFlags(&ctx->comm_ev[c], cudaEventDisableTiming));
+    KL_CUDA(cudaEventCreateWithFlags(&ctx->comm_done, cudaEventDisableTiming));
+  }
+  ctx->num_chunks = nch;
+  ctx->num_cc = cc;
+  return KLNMF_OK;
+}
+
 // Local (per-rank) work of one iteration on the dense path: three contractions per row panel.
 int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bool dict_only = false,
                     void *ratio_host = nullptr, int ratio_dtype = KLNMF_F64, int64_t ratio_ld = 0) {
@@ -416,16 +452,50 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
     }
     if (fit) {  // dictionary numerator: N += W'^T.Q  (stale Q, new W: nmf.py:345-349)
       PhaseTimer t(ctx, prof, PH_NUM);
-      GemmDesc d{};
-      d.M = ctx->k; d.N = ctx->f; d.K = rows;
-      d.A = dict_only ? (const void *)Wc : (const void *)Wn; d.a_sm = 1; d.a_sk = ctx->ldw;
-      d.A_lo = dict_only ? (const void *)Wclo : (const void *)Wnlo;
-      d.B = ctx->Q; d.b_sk = ctx->ldq; d.b_sn = 1; d.B_lo = ctx->Qlo;
-      d.out = ctx->num; d.ldo = ctx->ldh;
-      d.stop = stop;
-      d.single_pass = single;
-      KL_TRY(dense_gemm(ctx, EPI_ACC, d));
+      // Several ranks: the numerator is contracted f-chunk by f-chunk (contiguous chunk buffers), and on the LAST row
+      // panel every finished chunk is all-reduced on a side stream while the next one is still being contracted
+      // (SURVEY 8e "overlap"): only the last chunk's reduction is exposed.
+      const bool last_panel = r0 + ctx->panel_rows >= ctx->n;
+      const int nch = ctx->num_chunks;
+      const int64_t cc = nch > 1 ? ctx->num_cc : ctx->ldh;
+      for (int c = 0; c < nch; c++) {
+        const int64_t j0 = (int64_t)c * cc;
+        const int64_t ncols = nch > 1 ? (ctx->f - j0 < cc ? ctx->f - j0 : cc) : ctx->f;
+        char *out_c = (char *)ctx->num + (nch > 1 ? (int64_t)c * ctx->k * cc * es : 0);
+        if (ncols > 0) {
+          GemmDesc d{};
+          d.M = ctx->k; d.N = ncols; d.K = rows;
+          d.A = dict_only ? (const void *)Wc : (const void *)Wn; d.a_sm = 1; d.a_sk = ctx->ldw;
+          d.A_lo = dict_only ? (const void *)Wclo : (const void *)Wnlo;
+          d.B = (const char *)ctx->Q + j0 * es; d.b_sk = ctx->ldq; d.b_sn = 1;
+          d.B_lo = ctx->Qlo ? (const char *)ctx->Qlo + j0 * es : nullptr;
+          d.out = out_c; d.ldo = cc;
+          d.stop = stop;
+          d.single_pass = single;
+          KL_TRY(dense_gemm(ctx, EPI_ACC, d));
+        }
+        if (nch > 1 && last_panel && ctx->world > 1) {
+          KL_CUDA(cudaEventRecord(ctx->comm_ev[c], ctx->stream));
+          KL_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->comm_ev[c], 0));
+          KL_TRY(nccl_allreduce_sum_on(ctx, out_c, ctx->k * cc, (int)es, ctx->comm_stream));
+          if (c == nch - 1) {
+            KL_CUDA(cudaEventRecord(ctx->comm_done, ctx->comm_stream));
+            ctx->num_reduced = true;
+          }
+        }
+      }
     }
+  }
+  if (fit && ctx->n == 0 && ctx->num_chunks > 1 && ctx->world > 1) {
+    // a shard without rows still takes part in every chunk's all-reduce (the same NCCL call sequence on every rank)
+    const int64_t cc = ctx->num_cc;
+    for (int c = 0; c < ctx->num_chunks; c++) {
+      KL_CUDA(cudaEventRecord(ctx->comm_ev[c], ctx->stream));
+      KL_CUDA(cudaStreamWaitEvent(ctx->comm_stream, ctx->comm_ev[c], 0));
+      KL_TRY(nccl_allreduce_sum_on(ctx, (char *)ctx->num + (int64_t)c * ctx->k * cc * es, ctx->k * cc, (int)es, ctx->comm_stream));
+    }
+    KL_CUDA(cudaEventRecord(ctx->comm_done, ctx->comm_stream));
+    ctx->num_reduced = true;
   }
   // colsum(W') of this rank joins the all-reduced doubles (slots the sparse objective uses for colsum(W))
   if (fit && centered) KL_TRY(launch_colsum_w(ctx, ctx->W[cur ^ 1], ctx->split ? ctx->Wlo[cur ^ 1] : nullptr, ctx->dred + 2));
@@ -521,6 +591,10 @@ int klnmf_destroy(klnmf_ctx *ctx) {
                   ctx->dscal, ctx->flags, ctx->errors_dev};
   for (void *p : ptrs)
     if (p) cudaFree(p);
+  if (ctx->comm_stream) { cudaStreamSynchronize(ctx->comm_stream); cudaStreamDestroy(ctx->comm_stream); }
+  for (int c = 0; c < 8; c++)
+    if (ctx->comm_ev[c]) cudaEventDestroy(ctx->comm_ev[c]);
+  if (ctx->comm_done) cudaEventDestroy(ctx->comm_done);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->own_stream && ctx->stream) cudaStreamDestroy(ctx->stream);
   cudaGetLastError();
@@ -900,6 +974,7 @@ int klnmf_run_resume(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, doub
   KL_TRY(reset_reduction(ctx));
   KL_CUDA(cudaStreamSynchronize(ctx->stream));   // pinned scratch is reused below
 
+  KL_TRY(setup_num_chunks(ctx, fit));
   Profiler prof_store;
   Profiler *prof = ctx->profile ? &prof_store : nullptr;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -915,7 +990,8 @@ int klnmf_run_resume(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, doub
   // one reference iteration (nmf.py:212-222), enqueued on the context's stream; nothing in it synchronises
   auto enqueue_iteration = [&](int it) -> int {
     int r = KLNMF_OK;
-    if (fit) r = launch_zero(ctx, ctx->num, hbytes);
+    ctx->num_reduced = false;
+    if (fit) r = launch_zero(ctx, ctx->num, ctx->num_bytes);
     if (r == KLNMF_OK && ctx->sparse && ctx->n > 0) {
       { PhaseTimer t(ctx, prof, PH_RATIO); r = sparse_rows(ctx, 0, fit ? 2 : 0); }
       if (r == KLNMF_OK && fit) { PhaseTimer t(ctx, prof, PH_NUM); r = sparse_scatter(ctx, false); }
@@ -927,10 +1003,14 @@ int klnmf_run_resume(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, doub
       // one NCCL group: the k x f numerator and the handful of FP64 partials travel in one launch
       r = nccl_group_start();
       if (r == KLNMF_OK) r = nccl_allreduce_sum_f64(ctx, ctx->dred, 2 + ctx->k);
-      if (r == KLNMF_OK && fit)
-        r = nccl_allreduce_sum(ctx, ctx->num, (ctx->sparse ? ctx->f : ctx->k) * ctx->ldh, ctx->es);
+      if (r == KLNMF_OK && fit && !ctx->num_reduced)     // (a shard without rows, the sparse path: the whole buffer at once)
+        r = nccl_allreduce_sum(ctx, ctx->num, num_elems(ctx), ctx->es);
       const int r_end = nccl_group_end();
       if (r == KLNMF_OK) r = r_end;
+      if (r == KLNMF_OK && ctx->num_reduced && cudaStreamWaitEvent(ctx->stream, ctx->comm_done, 0) != cudaSuccess) {
+        set_error("klnmf_run: cudaStreamWaitEvent failed");
+        r = KLNMF_ECUDA;
+      }
     }
     if (r == KLNMF_OK) r = launch_decide(ctx, it);
     if (r == KLNMF_OK && fit) {
@@ -1031,8 +1111,10 @@ int klnmf_dictionary_step(klnmf_ctx *ctx) {
   KL_CHECK(ctx && ctx->have_x && ctx->have_h && ctx->have_w, KLNMF_ESTATE, "dictionary_step needs data, dictionary, coefficients");
   KL_CUDA(cudaSetDevice(ctx->device));
   const int64_t hbytes = (ctx->sparse ? ctx->f : ctx->k) * ctx->ldh * (int64_t)ctx->es;
+  KL_TRY(setup_num_chunks(ctx, 1));
   KL_TRY(reset_reduction(ctx));
-  KL_TRY(launch_zero(ctx, ctx->num, hbytes));
+  ctx->num_reduced = false;
+  KL_TRY(launch_zero(ctx, ctx->num, ctx->num_bytes));
   if (ctx->sparse) {
     if (ctx->n > 0) {
       KL_TRY(sparse_rows(ctx, 0, 2));
@@ -1041,7 +1123,10 @@ int klnmf_dictionary_step(klnmf_ctx *ctx) {
   } else {
     KL_TRY(dense_iteration(ctx, 1, false, nullptr, true));
   }
-  if (ctx->world > 1) KL_TRY(nccl_allreduce_sum(ctx, ctx->num, (ctx->sparse ? ctx->f : ctx->k) * ctx->ldh, ctx->es));
+  if (ctx->world > 1) {
+    if (!ctx->num_reduced) KL_TRY(nccl_allreduce_sum(ctx, ctx->num, num_elems(ctx), ctx->es));
+    else KL_CUDA(cudaStreamWaitEvent(ctx->stream, ctx->comm_done, 0));
+  }
   const int hc = ctx->hcur;
   KL_TRY(ctx->sparse ? launch_dict_update_t(ctx, ctx->H[hc], ctx->H[hc ^ 1])
                      : launch_dict_update(ctx, ctx->H[hc], ctx->H[hc ^ 1], ctx->split ? ctx->Hlo[hc ^ 1] : nullptr));

@@ -83,7 +83,14 @@ struct klnmf_ctx {
   int64_t ldh = 0;             // dense: k x f (ld >= f);  sparse: f x k transposed (ld >= k)
   void *Wlo[2] = {nullptr, nullptr};   // TF32X3 low parts (same layout)
   void *Hlo[2] = {nullptr, nullptr};
-  void *num = nullptr;         // numerator accumulator, same layout as H
+  void *num = nullptr;         // numerator accumulator, same layout as H -- or, dense path on several ranks, in f-chunks:
+  int64_t num_bytes = 0;       //   [chunk][k][num_cc], every chunk contiguous, so that a finished chunk is all-reduced
+  int num_chunks = 1;          //   on a side stream while the next one is still being contracted (api.cu)
+  int64_t num_cc = 0;          //   columns per chunk (multiple of 32); 0 = plain k x ldh layout
+  bool num_reduced = false;    // this iteration's chunks were all-reduced as they finished
+  cudaStream_t comm_stream = nullptr;
+  cudaEvent_t comm_ev[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t comm_done = nullptr;
   double *rowsumH = nullptr;   // k   (sum over f of H, used by the sparse objective)
   double *colsumW = nullptr;   // k   (dense, centered ratio: column sums of the new coefficients, all ranks)
   float *rsh32 = nullptr;      // ldw + 32 floats: rowsumH as FP32, zero beyond k (bias of the centered coefficient update)
@@ -225,6 +232,7 @@ int nccl_group_start();
 int nccl_group_end();
 int nccl_allreduce_sum(klnmf_ctx *ctx, void *buf, int64_t count, int es);
 int nccl_allreduce_sum_f64(klnmf_ctx *ctx, double *buf, int64_t count);
+int nccl_allreduce_sum_on(klnmf_ctx *ctx, void *buf, int64_t count, int es, cudaStream_t stream);
 void nccl_comm_destroy(klnmf_ctx *ctx);
 
 }  // namespace klnmf

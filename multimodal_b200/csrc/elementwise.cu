@@ -39,11 +39,13 @@ __global__ void __launch_bounds__(512) dict_update_kernel(const T *__restrict__ 
                                                           const T *__restrict__ num, T *__restrict__ Hn,
                                                           T *__restrict__ Hnlo, int64_t f, int64_t ld,
                                                           double *__restrict__ rowsum, const double *__restrict__ rowadd,
-                                                          const int *stop) {
+                                                          const int *stop, int64_t cc, int64_t krows) {
   if (*stop != 0) return;
   __shared__ double red[32];
   const int64_t a = blockIdx.x;
-  const T *h = H + a * ld, *nm = num + a * ld;
+  const T *h = H + a * ld;
+  // numerator layout: plain k x ld (cc == 0) or f-chunks [chunk][krows][cc] (klnmf_ctx::num_cc)
+  auto nmv = [&](int64_t j) -> T { return cc ? num[(j / cc) * (krows * cc) + a * cc + (j % cc)] : num[a * ld + j]; };
   const T *hl = Hlo ? Hlo + a * ld : nullptr;
   // centered ratio (api.cu, dense_iteration): num holds W'^T.(Q - 1); the missing W'^T.1 = colsum(W') is the same
   // for every feature of a dictionary row
@@ -52,14 +54,16 @@ __global__ void __launch_bounds__(512) dict_update_kernel(const T *__restrict__ 
   for (int64_t j = threadIdx.x; j < f; j += blockDim.x) {
     T v = h[j];
     if (hl) v += hl[j];
-    s += (double)(v * (rowadd ? fmax(nm[j] + add, (T)0) : nm[j]));
+    const T nj = nmv(j);
+    s += (double)(v * (rowadd ? fmax(nj + add, (T)0) : nj));
   }
   s = block_sum(s, red);
   const double inv = 1.0 / (KL_NORM_EPS + s);
   for (int64_t j = threadIdx.x; j < f; j += blockDim.x) {
     T v = h[j];
     if (hl) v += hl[j];
-    T r = (T)((double)(v * (rowadd ? fmax(nm[j] + add, (T)0) : nm[j])) * inv);   // the centered numerator, clamped like G
+    const T nj = nmv(j);
+    T r = (T)((double)(v * (rowadd ? fmax(nj + add, (T)0) : nj)) * inv);   // the centered numerator, clamped like G
     if (Hnlo) {
       float hi = tf32_hi((float)r);
       Hn[a * ld + j] = (T)hi;
@@ -296,11 +300,11 @@ int launch_dict_update(klnmf_ctx *ctx, const void *H_old, void *H_new, void *Hlo
   if (ctx->es == 8) {
     dict_update_kernel<double><<<(unsigned)ctx->k, 512, 0, ctx->stream>>>(
         (const double *)H_old, nullptr, (const double *)ctx->num, (double *)H_new, nullptr, ctx->f, ctx->ldh,
-        ctx->rowsumH, rowadd, ctx->flags + FL_STOP);
+        ctx->rowsumH, rowadd, ctx->flags + FL_STOP, ctx->num_cc, ctx->k);
   } else {
     dict_update_kernel<float><<<(unsigned)ctx->k, 512, 0, ctx->stream>>>(
         (const float *)H_old, (const float *)ctx->Hlo[cur], (const float *)ctx->num, (float *)H_new,
-        (float *)Hlo_new, ctx->f, ctx->ldh, ctx->rowsumH, rowadd, ctx->flags + FL_STOP);
+        (float *)Hlo_new, ctx->f, ctx->ldh, ctx->rowsumH, rowadd, ctx->flags + FL_STOP, ctx->num_cc, ctx->k);
   }
   ctx->n_launch++;
   KL_CUDA(cudaGetLastError());

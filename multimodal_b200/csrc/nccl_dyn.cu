@@ -112,6 +112,14 @@ int nccl_allreduce_sum(klnmf_ctx *ctx, void *buf, int64_t count, int es) {
                "ncclAllReduce");
 }
 
+int nccl_allreduce_sum_on(klnmf_ctx *ctx, void *buf, int64_t count, int es, cudaStream_t stream) {
+  if (ctx->world <= 1 || count <= 0) return KLNMF_OK;
+  ctx->n_nccl++;
+  return check(g_nccl.allreduce(buf, buf, (size_t)count, es == 8 ? kNcclFloat64 : kNcclFloat32, kNcclSum,
+                                (nccl_comm_t)ctx->comm, stream),
+               "ncclAllReduce");
+}
+
 int nccl_allreduce_sum_f64(klnmf_ctx *ctx, double *buf, int64_t count) {
   return nccl_allreduce_sum(ctx, buf, count, 8);
 }

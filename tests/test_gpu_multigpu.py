@@ -50,6 +50,38 @@ def test_sharded_fit_matches_oracle_and_single_device(within, mode, kind):
     within("H_vs_single", cases.rel_fro(H, out["0"][1]) + 1e-300, same)
 
 
+@pytest.mark.parametrize("chunks", ["1", "4", "8"])
+def test_chunked_numerator_all_reduce(within, monkeypatch, chunks):
+    """Several ranks keep the dense numerator in contiguous f-chunks and all-reduce every finished chunk on a side
+    stream while the next one is contracted (api.cu: setup_num_chunks, dense_iteration).  Ragged f (chunks of unequal
+    width), several row panels per shard, a shard count that leaves one shard a row short -- against the oracle and the
+    one-all-reduce form."""
+    from multimodal_b200 import _native
+    monkeypatch.setenv("KLNMF_AR_CHUNKS", chunks)
+    monkeypatch.setenv("KLNMF_AR_CHUNK_MIN_F", "64")
+    rs = np.random.RandomState(14)
+    n, f, k = 901, 333, 40
+    X = rs.gamma(0.5, 1.0, size=(n, f))
+    np.random.seed(7)
+    Wr, Hr, er, _ = O.fit_transform(X, k=k, max_iter=8, tol=0)
+    for mode in ("fp64", "tf32r"):
+        est = KLdivNMF(n_components=k, max_iter=8, tol=0, mode=mode, device=DEVICES)
+        np.random.seed(7)
+        W, errs = est.fit_transform(X, return_errors=True)
+        within(mode + "_W", cases.rel_fro(W, Wr), TOL[mode])
+        within(mode + "_H", cases.rel_fro(est.components_, Hr), TOL[mode])
+        within(mode + "_objective", maxrel(errs, er), 1e-12 if mode == "fp64" else 2e-5)
+    # fewer samples than shards would leave one engine without rows: it still joins every chunk's all-reduce
+    est = KLdivNMF(n_components=3, max_iter=4, tol=0, mode="fp64", device=DEVICES)
+    np.random.seed(7)
+    W1 = est.fit_transform(X[:1, :])
+    ref = KLdivNMF(n_components=3, max_iter=4, tol=0, mode="fp64", device=0)
+    np.random.seed(7)
+    W0 = ref.fit_transform(X[:1, :])
+    within("one_sample_W", cases.rel_fro(W1, W0) + 1e-300, 1e-12)
+    within("one_sample_H", cases.rel_fro(est.components_, ref.components_) + 1e-300, 1e-12)
+
+
 def test_sharded_transform_needs_no_exchange_and_matches(within):
     rs = np.random.RandomState(13)
     X = rs.random_sample((700, 400))
