@@ -36,21 +36,52 @@ def have_nvcc():
         return False
 
 
+STAMP = LIB + ".srchash"
+
+
+def source_hash():
+    """sha256 over the compiler flags and every source / header: what the library was built from.  (Modification times
+    do not survive a copy of the tree to another machine; the contents do.)"""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS).encode())
+    for rel in SOURCES + HEADERS:
+        with open(os.path.join(CSRC, rel), "rb") as fh:
+            h.update(rel.encode() + b"\0" + fh.read())
+    return h.hexdigest()
+
+
 def is_stale():
-    if not os.path.exists(LIB):
+    if not os.path.exists(LIB) or not os.path.exists(STAMP):
         return True
-    t = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES + HEADERS]
-    return any(os.path.getmtime(d) > t for d in deps)
+    try:
+        with open(STAMP) as fh:
+            return fh.read().strip() != source_hash()
+    except OSError:
+        return True
 
 
 def build(force=False, verbose=False):
-    """Compile every CUDA source for sm_100a and link libklnmf.so. Returns its path."""
+    """Compile every CUDA source for sm_100a and link libklnmf.so. Returns its path.  Safe to call from several
+    processes at once (the ranks of a torchrun job): one builds under a file lock, the others find the result."""
     if not force and not is_stale():
         return LIB
+    import fcntl
+    os.makedirs(os.path.join(CSRC, "build"), exist_ok=True)
+    with open(os.path.join(CSRC, "build", ".lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            if not force and not is_stale():          # somebody else built it while we waited
+                return LIB
+            return _build_locked(verbose)
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
+def _build_locked(verbose):
     nvcc = _nvcc()
     objdir = os.path.join(CSRC, "build")
     os.makedirs(objdir, exist_ok=True)
+    digest = source_hash()
 
     def compile_one(src):
         obj = os.path.join(objdir, src.replace(".cu", ".o"))
@@ -64,11 +95,15 @@ def build(force=False, verbose=False):
 
     with ThreadPoolExecutor(max_workers=len(SOURCES)) as ex:
         objs = list(ex.map(compile_one, SOURCES))
-    cmd = [nvcc, "-shared", "-o", LIB + ".tmp"] + objs + ["-ldl", "-Wno-deprecated-gpu-targets"]
+    tmp = "%s.tmp.%d" % (LIB, os.getpid())
+    cmd = [nvcc, "-shared", "-o", tmp] + objs + ["-ldl", "-Wno-deprecated-gpu-targets"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         raise RuntimeError("link failed:\n%s" % r.stderr[-4000:])
-    os.replace(LIB + ".tmp", LIB)
+    os.replace(tmp, LIB)
+    with open(STAMP + ".tmp", "w") as fh:
+        fh.write(digest + "\n")
+    os.replace(STAMP + ".tmp", STAMP)
     return LIB
 
 
