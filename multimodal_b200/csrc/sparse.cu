@@ -285,6 +285,7 @@ struct BlockedCsc {
   int32_t *colptr = nullptr;   // n_blocks x (f + 1): offsets of the columns inside the block's entry range
   int32_t *rowidx = nullptr;   // nnz: row inside the block
   int32_t *src = nullptr;      // nnz: CSR position inside the block's entry range (where q_ij lives)
+  unsigned long long *ticket = nullptr;   // next unit to hand out (zeroed before every launch)
 };
 
 __global__ void bcsc_count_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices, int64_t n,
@@ -338,30 +339,40 @@ __global__ void __launch_bounds__(WARPS * 32)
 sparse_numerator_bcsc_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ colptr,
                              const int32_t *__restrict__ rowidx, const int32_t *__restrict__ src,
                              const T *__restrict__ qnz, const T *__restrict__ Wn, int64_t ldw, T *__restrict__ Nt,
-                             int64_t ldh, int64_t n, int64_t f, int64_t R, int64_t n_blocks, const int *stop) {
+                             int64_t ldh, int64_t n, int64_t f, int64_t R, int64_t n_blocks, const int *stop,
+                             unsigned long long *__restrict__ ticket) {
   if (*stop != 0) return;
-  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t warp_global = (int64_t)blockIdx.x * WARPS + warp;
-  const int64_t n_warps = (int64_t)gridDim.x * WARPS;
+  const int lane = threadIdx.x & 31;
   bool act[VPL];
 #pragma unroll
   for (int c = 0; c < VPL; c++) act[c] = (128 * c + 4 * lane) < ldh && (128 * c + 4 * lane) < ldw;
   const int64_t units = n_blocks * f;
-  // Software pipeline over the dependent loads (column range -> row index / ratio position -> ratio -> coefficient
-  // rows): the column range of the NEXT unit and the (row, ratio) pairs of the NEXT batch of eight entries are fetched
-  // before the eight row gathers of the current batch are issued, so the four L2 round trips of the chain overlap the
-  // gathers instead of preceding them (ncu: long_scoreboard was 75 % of all stall samples).
-  int64_t u = warp_global;
+  // Units are handed out IN ORDER by a ticket counter, one per warp and grab: every resident warp then works within a
+  // few thousand units of the frontier, i.e. inside ONE row block, whose W' rows stay in the L2.  (A static grid-stride
+  // assignment lets the warps of faster SMs run ahead by whole blocks over a long launch: at n = 10^6 the pass read
+  // 88.7 GB from DRAM for 4 GB of compulsory traffic, L2 hit rate 54 %, and its time per row grew with n -- 19.5 ns at
+  // n = 131 072, 31.9 ns at 2 * 10^6; profiles/r2_run24_sparse_scaling.log.)
+  // Software pipeline over the dependent loads (ticket -> column range -> row index / ratio position -> ratio ->
+  // coefficient rows): the ticket and the column range of the NEXT unit and the (row, ratio) pairs of the NEXT batch of
+  // eight entries are fetched before the eight row gathers of the current batch are issued, so the L2 round trips of
+  // the chain overlap the gathers instead of preceding them (ncu: long_scoreboard was 75 % of all stall samples).
+  auto grab = [&]() -> int64_t {
+    unsigned long long t = 0;
+    if (lane == 0) t = atomicAdd(ticket, 1ull);
+    return (int64_t)__shfl_sync(0xffffffffu, t, 0);
+  };
+  int64_t u = grab();
   int32_t c0 = 0, c1 = 0;
   if (u < units) {
     const int32_t *cp = colptr + (u / f) * (f + 1) + (u % f);
     c0 = __ldg(cp); c1 = __ldg(cp + 1);
   }
-  for (; u < units; u += n_warps) {   // block-major: the whole grid sweeps one row block at a time
+  int64_t un = u;
+  for (; u < units; u = un) {   // block-major: the whole grid sweeps one row block at a time
     const int64_t b = u / f, j = u - b * f;
     const int32_t t0 = c0, t1 = c1;
     {
-      const int64_t un = u + n_warps;
+      un = grab();
       if (un < units) {
         const int32_t *cp = colptr + (un / f) * (f + 1) + (un % f);
         c0 = __ldg(cp); c1 = __ldg(cp + 1);
@@ -485,6 +496,7 @@ int bcsc_build(klnmf_ctx *ctx) {
     if (bc->colptr) cudaFree(bc->colptr);
     if (bc->rowidx) cudaFree(bc->rowidx);
     if (bc->src) cudaFree(bc->src);
+    if (bc->ticket) cudaFree(bc->ticket);
     if (cursor) cudaFree(cursor);
     delete bc;
     return KLNMF_ENOMEM;
@@ -494,6 +506,7 @@ int bcsc_build(klnmf_ctx *ctx) {
   if (cudaMalloc((void **)&cursor, cells * 4) != cudaSuccess) return fail("cudaMalloc cursor");
   if (cudaMalloc((void **)&bc->rowidx, nz * 4) != cudaSuccess) return fail("cudaMalloc rowidx");
   if (cudaMalloc((void **)&bc->src, nz * 4) != cudaSuccess) return fail("cudaMalloc src");
+  if (cudaMalloc((void **)&bc->ticket, 8) != cudaSuccess) return fail("cudaMalloc ticket");
   cudaMemsetAsync(bc->colptr, 0, cells * 4, ctx->stream);
   const int grid = ctx->sm_count * 8;
   bcsc_count_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->indptr, ctx->indices, ctx->n, ctx->f, R, bc->colptr);
@@ -514,9 +527,17 @@ int run_scatter(klnmf_ctx *ctx, const T *Wn) {
   if (use_bcsc(ctx)) {
     if (!ctx->bcsc) KL_TRY(bcsc_build(ctx));
     const BlockedCsc *bc = (const BlockedCsc *)ctx->bcsc;
-    sparse_numerator_bcsc_kernel<T, VPL><<<ctx->sm_count * 8, WARPS * 32, 0, ctx->stream>>>(
+    // exactly the CTAs that are resident at once: with tickets a second wave would only find the counter exhausted
+    static int per_sm[64] = {};
+    if (!per_sm[ctx->device & 63]) {
+      int b = 0;
+      KL_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, sparse_numerator_bcsc_kernel<T, VPL>, WARPS * 32, 0));
+      per_sm[ctx->device & 63] = b > 0 ? b : 1;
+    }
+    KL_CUDA(cudaMemsetAsync(bc->ticket, 0, 8, ctx->stream));
+    sparse_numerator_bcsc_kernel<T, VPL><<<ctx->sm_count * per_sm[ctx->device & 63], WARPS * 32, 0, ctx->stream>>>(
         ctx->indptr, bc->colptr, bc->rowidx, bc->src, (const T *)ctx->qnz, Wn, ctx->ldw, (T *)ctx->num, ctx->ldh, ctx->n,
-        ctx->f, bc->R, bc->n_blocks, ctx->flags + FL_STOP);
+        ctx->f, bc->R, bc->n_blocks, ctx->flags + FL_STOP, bc->ticket);
     ctx->n_launch++;
     KL_CUDA(cudaGetLastError());
     return KLNMF_OK;
@@ -578,6 +599,7 @@ void sparse_release_pattern(klnmf_ctx *ctx) {
   if (bc->colptr) cudaFree(bc->colptr);
   if (bc->rowidx) cudaFree(bc->rowidx);
   if (bc->src) cudaFree(bc->src);
+  if (bc->ticket) cudaFree(bc->ticket);
   delete bc;
   ctx->bcsc = nullptr;
 }
