@@ -235,6 +235,169 @@ sparse_rows_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------
+// The rows pass for FP32 state whose padded width is exactly 128 * VPL (k = 128, 256, 512, 1024: cfg4 and the
+// reference's k = 200 fall here after padding only when k itself is a multiple of 128; everything else takes the
+// generic kernel above).  Same arithmetic, fewer instructions: the generic kernel issued 52 per stored entry at
+// k = 256 and kept the schedulers 69 % busy (ncu, n = 10^6: `not_selected` + `selected` = 35 % of the stall samples) --
+// it was bound by its issue rate, not by the 1 KB it gathers per entry.  Here
+//   * no predicates and no zero-initialisation of the gather registers (32 CS2R per batch of 8 entries),
+//   * the column indices of a batch are fetched by lanes 0..B-1 and handed out by shuffles, offsets inside the
+//     dictionary are 32-bit (f * ld < 2^32): one IMAD.WIDE per gather instead of a 64-bit multiply-add chain,
+//   * the dot products and the G update work on pairs (fma.rn.f32x2 -> FFMA2): 64 instead of 128 FMAs per batch.
+// ---------------------------------------------------------------------------------------------------------
+typedef unsigned long long f2_t;   // two packed FP32 values
+__device__ __forceinline__ f2_t pk2(float a, float b) {
+  f2_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(a), "f"(b));
+  return r;
+}
+__device__ __forceinline__ void upk2(f2_t v, float &a, float &b) { asm("mov.b64 {%0, %1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); }
+__device__ __forceinline__ f2_t fma2(f2_t a, f2_t b, f2_t c) {
+  f2_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ f2_t mul2(f2_t a, f2_t b) {
+  f2_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+template <int VPL, int MODE>   // MODE 0: full pass, 1: objective only
+__global__ void __launch_bounds__(WARPS * 32, VPL <= 2 ? 2 : 1)
+sparse_rows_full_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
+                        const float *__restrict__ vals, const float *__restrict__ W, const float *__restrict__ Ht,
+                        uint32_t ld, float *__restrict__ Wn, float *__restrict__ qnz, int64_t n,
+                        double *__restrict__ dred, const int *stop) {
+  constexpr int B = Batch<float, VPL>::B, SH = Batch<float, VPL>::SH;
+  if (stop != nullptr && *stop != 0) return;
+  __shared__ double red[WARPS];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t warp_global = (int64_t)blockIdx.x * WARPS + warp;
+  const int64_t n_warps = (int64_t)gridDim.x * WARPS;
+  const int mine = lane >> SH;
+  const bool leader = (lane & ((1 << SH) - 1)) == 0;
+
+  double kl = 0.0;
+  double cs[VPL][4];
+#pragma unroll
+  for (int c = 0; c < VPL; c++)
+#pragma unroll
+    for (int e = 0; e < 4; e++) cs[c][e] = 0.0;
+
+  // column indices of the batch starting at p, on lanes 0..B-1 (entries past the end of the row re-read the batch's
+  // first column; their coefficient is forced to 0)
+  auto batch_indices = [&](uint32_t p, uint32_t pend) -> int32_t {
+    const int nb = (int)(pend - p < B ? pend - p : B);
+    return lane < B ? __ldg(indices + (lane < nb ? p + lane : p)) : 0;
+  };
+  // What bounds the pass is the rate at which the L2 answers 1 KB gathers spread over the whole 51 MB dictionary
+  // (cfg4): 512 GB in 33.5 ms = 15.3 TB/s, 0.94 of what klnmf_l2_read_bench gets out of a 48 MB buffer.  Measured and
+  // dropped (profiles/r2_run26..29_*.log): FP16 gather copies (half the bytes: -5 %, at 100x the error), register
+  // double-buffering of half batches (+34 %), L1 prefetches of the next batch (+19 %; +40 % with no-allocate loads).
+  // (row and entry positions fit 32 bits: the host checks n, nnz < 2^32)
+  uint32_t i = (uint32_t)warp_global;
+  const uint32_t nn = (uint32_t)n, step = (uint32_t)n_warps;
+  uint32_t p0 = 0, p1 = 0;
+  int32_t jl = 0;
+  if (warp_global < n) {
+    p0 = (uint32_t)indptr[i]; p1 = (uint32_t)indptr[i + 1];
+    if (p0 < p1) jl = batch_indices(p0, p1);
+  }
+  for (; warp_global < n && i < nn;) {
+    const uint32_t in = i + step;
+    uint32_t pn0 = 0, pn1 = 0;
+    if (in < nn) { pn0 = (uint32_t)indptr[in]; pn1 = (uint32_t)indptr[in + 1]; }
+    f2_t w[VPL][2], g[VPL][2];
+    const ulonglong2 *wp = reinterpret_cast<const ulonglong2 *>(W + (uint64_t)i * ld) + lane;
+#pragma unroll
+    for (int c = 0; c < VPL; c++) {
+      const ulonglong2 t = wp[32 * c];
+      w[c][0] = t.x; w[c][1] = t.y;
+      float a0, a1, a2, a3;
+      upk2(t.x, a0, a1); upk2(t.y, a2, a3);
+      cs[c][0] += (double)a0; cs[c][1] += (double)a1; cs[c][2] += (double)a2; cs[c][3] += (double)a3;
+      g[c][0] = pk2(0.f, 0.f); g[c][1] = pk2(0.f, 0.f);
+    }
+    float klf = 0.f;
+    int32_t jl_next = 0;
+    if (p0 == p1 && pn0 < pn1) jl_next = batch_indices(pn0, pn1);      // an empty row hands over to the next one
+    for (uint32_t p = p0; p < p1; p += B) {
+      const int nb = (int)(p1 - p < B ? p1 - p : B);
+      const bool have = mine < nb;
+      const float xm = have ? __ldg(vals + p + mine) : 0.f;
+      // the batch after this one: the next of this row, or the first of the warp's next row
+      const bool more = p + B < p1;
+      if (more) jl_next = batch_indices(p + B, p1);
+      else if (pn0 < pn1) jl_next = batch_indices(pn0, pn1);
+      f2_t h[B][VPL][2];
+      float s[B];
+#pragma unroll
+      for (int b = 0; b < B; b++) {
+        const uint32_t j = (uint32_t)__shfl_sync(0xffffffffu, jl, b);
+        const ulonglong2 *col = reinterpret_cast<const ulonglong2 *>(Ht + (uint64_t)(j * ld)) + lane;
+#pragma unroll
+        for (int c = 0; c < VPL; c++) {
+          const ulonglong2 t = __ldg(col + 32 * c);
+          h[b][c][0] = t.x; h[b][c][1] = t.y;
+        }
+      }
+#pragma unroll
+      for (int b = 0; b < B; b++) {
+        f2_t a2 = mul2(w[0][0], h[b][0][0]);
+        a2 = fma2(w[0][1], h[b][0][1], a2);
+#pragma unroll
+        for (int c = 1; c < VPL; c++) { a2 = fma2(w[c][0], h[b][c][0], a2); a2 = fma2(w[c][1], h[b][c][1], a2); }
+        float lo, hi;
+        upk2(a2, lo, hi);
+        s[b] = lo + hi;
+      }
+      const float sm = batch_reduce<float, B>(s, lane);
+      const float q = have ? (xm + (float)KL_EPS) / (sm + (float)KL_EPS) : 0.f;
+      if (have && leader) {
+        klf += xm * logf(q);
+        if (MODE == 0 && qnz != nullptr) qnz[p + mine] = q;
+      }
+      if (MODE == 0) {
+#pragma unroll
+        for (int b = 0; b < B; b++) {
+          const float cb = __shfl_sync(0xffffffffu, q, b << SH);
+          const f2_t cb2 = pk2(cb, cb);
+#pragma unroll
+          for (int c = 0; c < VPL; c++) { g[c][0] = fma2(cb2, h[b][c][0], g[c][0]); g[c][1] = fma2(cb2, h[b][c][1], g[c][1]); }
+        }
+      }
+      jl = jl_next;
+    }
+    if (p0 == p1) jl = jl_next;
+    kl += (double)klf;
+    if (MODE == 0) {
+      ulonglong2 *op = reinterpret_cast<ulonglong2 *>(Wn + (uint64_t)i * ld) + lane;
+#pragma unroll
+      for (int c = 0; c < VPL; c++) {
+        ulonglong2 o;
+        o.x = mul2(w[c][0], g[c][0]); o.y = mul2(w[c][1], g[c][1]);
+        op[32 * c] = o;
+      }
+    }
+    i = in; p0 = pn0; p1 = pn1;
+  }
+#pragma unroll
+  for (int c = 0; c < VPL; c++)
+#pragma unroll
+    for (int e = 0; e < 4; e++) atomicAdd(&dred[2 + 128 * c + 4 * lane + e], cs[c][e]);
+  kl = warp_sum(kl);
+  if (lane == 0) red[warp] = kl;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double t = 0.0;
+    for (int w = 0; w < WARPS; w++) t += red[w];
+    atomicAdd(&dred[0], t);
+  }
+}
+
 template <typename T, int VPL>
 __global__ void __launch_bounds__(WARPS * 32)
 sparse_scatter_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
@@ -457,6 +620,22 @@ int run_rows(klnmf_ctx *ctx, int mode, const T *W, T *Wn, int q_order) {
                                                                                : (int64_t)ctx->sm_count * 8);
   const int *stop = ctx->flags + FL_STOP;
   const T *Ht = (const T *)ctx->H[ctx->hcur];
+  static const bool generic_only = getenv("KLNMF_SPARSE_GENERIC") && atoi(getenv("KLNMF_SPARSE_GENERIC")) == 1;
+  if (sizeof(T) == 4 && (mode == 0 || mode == 1) && !generic_only && ctx->ldw == 128 * VPL && ctx->ldh == ctx->ldw &&
+      ctx->f * ctx->ldh < ((int64_t)1 << 32) && ctx->nnz < ((int64_t)1 << 32) - 64 &&
+      ctx->n + (int64_t)grid * WARPS < ((int64_t)1 << 32)) {
+    if (mode == 0)
+      sparse_rows_full_kernel<VPL, 0><<<grid, WARPS * 32, 0, ctx->stream>>>(
+          ctx->indptr, ctx->indices, (const float *)ctx->vals, (const float *)W, (const float *)Ht, (uint32_t)ctx->ldh,
+          (float *)Wn, q_order == 0 ? nullptr : (float *)ctx->qnz, ctx->n, ctx->dred, stop);
+    else
+      sparse_rows_full_kernel<VPL, 1><<<grid, WARPS * 32, 0, ctx->stream>>>(
+          ctx->indptr, ctx->indices, (const float *)ctx->vals, (const float *)W, (const float *)Ht, (uint32_t)ctx->ldh,
+          nullptr, nullptr, ctx->n, ctx->dred, nullptr);
+    ctx->n_launch++;
+    KL_CUDA(cudaGetLastError());
+    return KLNMF_OK;
+  }
   if (mode == 0)
     sparse_rows_kernel<T, VPL, 0><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->indptr, ctx->indices, (const T *)ctx->vals, W,
                                                                         ctx->ldw, Ht, ctx->ldh, Wn,

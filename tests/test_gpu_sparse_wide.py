@@ -1,0 +1,70 @@
+"""-m gpu: the CSR path at k >= 128 against the float64 oracle (reference lines: nmf.py:52-70, 301-308, 325-351).
+
+k = 128, 256, 512 take `sparse_rows_full_kernel` (padded width exactly 128, 256, 512: packed FP32 FMAs, no predicates);
+the ragged values take the generic `sparse_rows_kernel` with two, three and five 128-component chunks per lane.  Both
+compute in FP32 FMA in every TF32 mode and in FP64 in `fp64`.
+"""
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from multimodal_b200.lib.nmf import KLdivNMF
+from oracle import cases
+from oracle import klnmf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+ITERS = 10
+# stated = about 3 x the worst value measured on the B200 (profiles/r2_parity_measured.json): W, H 2.9e-6, objective 2.4e-7
+TOL_WH = {"fp64": 1e-12, "tf32x3": 9e-6, "tf32r": 9e-6, "tf32": 9e-6}
+TOL_KL = {"fp64": 1e-12, "tf32x3": 1.2e-6, "tf32r": 1.2e-6, "tf32": 1.2e-6}
+
+
+def maxrel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return float(np.max(np.abs(a - b) / np.abs(b)))
+
+
+def case(n, f, k, density, seed):
+    rs = np.random.RandomState(seed)
+    X = sp.random(n, f, density=density, random_state=rs, format="csr", dtype=np.float64)
+    X.data = 1.0 - X.data                                          # uniform (0, 1]
+    X.sort_indices()
+    np.random.seed(seed + 1)
+    H0 = O.init_dictionary(k, f)
+    return X, H0
+
+
+@pytest.mark.parametrize("mode", ["fp64", "tf32x3", "tf32r", "tf32"])
+@pytest.mark.parametrize("k", [128, 160, 256, 300, 512, 520])
+def test_sparse_fit_wide_k_vs_oracle(within, mode, k):
+    X, H0 = case(384, 1500, k, 0.03, 70 + k)
+    X[5] = 0                                                       # an empty sample (no stored entries)
+    X.eliminate_zeros()
+    W_ref, H_ref, errs_ref, _ = O.fit_transform(X.copy(), k=k, max_iter=ITERS, tol=0, H0=H0)
+    est = KLdivNMF(n_components=k, max_iter=ITERS, tol=0, mode=mode)
+    est._init_dictionary = H0
+    W, errs = est.fit_transform(X.copy(), return_errors=True)
+    assert len(errs) == ITERS
+    assert (W >= 0).all() and (est.components_ >= 0).all()
+    within("W", cases.rel_fro(W, W_ref), TOL_WH[mode])
+    within("H", cases.rel_fro(est.components_, H_ref), TOL_WH[mode])
+    within("objective", maxrel(errs, errs_ref), TOL_KL[mode])
+    within("objective_after", maxrel(est.error(X.copy(), W), O.error(X, W_ref, H_ref)), TOL_KL[mode])
+
+
+@pytest.mark.parametrize("mode", ["tf32x3", "tf32r"])
+@pytest.mark.parametrize("k", [256, 200])
+def test_sparse_transform_wide_k_vs_oracle(within, mode, k):
+    """Transform with a sub-dictionary that is NOT normalised (learner.py:71-78): only the rows pass runs."""
+    X, _ = case(300, 1200, k, 0.04, 91)
+    rs = np.random.RandomState(5)
+    H = np.abs(rs.random_sample((k, 1200))) + 0.01
+    H *= rs.uniform(0.2, 3.0, size=(k, 1))
+    W_ref, _, errs_ref, _ = O.fit_transform(X.copy(), k=k, max_iter=ITERS, tol=0, H0=H, fit=False)
+    est = KLdivNMF(n_components=k, max_iter=ITERS, tol=0, mode=mode)
+    est.components_ = H
+    est._init_dictionary = H
+    W, errs = est.fit_transform(X.copy(), _fit=False, return_errors=True)
+    within("W", cases.rel_fro(W, W_ref), TOL_WH[mode])
+    within("objective", maxrel(errs, errs_ref), TOL_KL[mode])

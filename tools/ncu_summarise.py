@@ -64,7 +64,7 @@ def main():
             if key == "sparse":      # one sparse iteration = rows pass + scatter pass: sum the first launch of each
                 rd, wr = hdr.index("dram__bytes_read.sum"), hdr.index("dram__bytes_write.sum")
                 tr = tw = 0.0
-                for sub in ("sparse_rows_kernel", "sparse_numerator_bcsc_kernel"):
+                for sub in ("sparse_rows_", "sparse_numerator_bcsc_kernel"):   # sparse_rows_kernel or sparse_rows_full_kernel
                     for r in body:
                         if sub in r[hdr.index("Kernel Name")]:
                             tr += float(r[rd]) * UNIT[units[rd]]
@@ -72,7 +72,7 @@ def main():
                             break
                 e = {"kernel": key, "rows": int(rows_), "f": int(f), "k": int(k), "mode": mode, "dram_bytes": tr + tw,
                      "dram_bytes_read": tr, "dram_bytes_write": tw, "report": os.path.basename(rep),
-                     "kernel_name": "sparse_rows_kernel + sparse_numerator_bcsc_kernel"}
+                     "kernel_name": "sparse_rows_(full_)kernel + sparse_numerator_bcsc_kernel"}
                 entries = [x for x in entries if not (x["kernel"] == key and x["rows"] == e["rows"] and x["f"] == e["f"]
                                                       and x["k"] == e["k"] and x["mode"] == mode)]
                 entries.append(e)
