@@ -319,7 +319,7 @@ def phase_roofline(ms, cnt, n_local, f, k, kind, steps, peaks, mode):
         if peaks.get("l2_gbs"):
             l2 = {"bound": "l2", "achieved": gather / t / 1e9, "peak": peaks["l2_gbs"], "unit": "GB/s",
                   "frac": gather / t / 1e9 / peaks["l2_gbs"], "gather_bytes": gather,
-                  "peak_source": "klnmf_l2_read_bench on this GPU: best of a 24 MB and a 48 MB buffer read 200 times by every SM (ld.global.cg.v4)",
+                  "peak_source": "klnmf_l2_read_bench on this GPU: best of a 24 MB and a 48 MB buffer read 200 times by every SM, eight 512-byte pieces in flight per warp (ld.global.cg.v4)",
                   "peak_by_buffer_mb": peaks.get("l2_gbs_by_mb"),
                   "rows_pass_gbs": 0.5 * gather / (ms["ratio"] / max(steps, 1) * 1e-3) / 1e9,
                   "numerator_pass_gbs": 0.5 * gather / (ms["numerator"] / max(steps, 1) * 1e-3) / 1e9}
@@ -528,9 +528,8 @@ def run_ours(args):
     from multimodal_b200 import distributed as D
     peaks = measured_peaks()
     try:
-        # the L2 -> SM read bandwidth depends on the footprint (a buffer that fits ONE of the two L2 partitions is served
-        # from the near one): the roofline's denominator is the best of a 24 MB buffer (the W' block of the numerator
-        # pass) and a 48 MB one (the 51 MB dictionary of the rows pass)
+        # the roofline's denominator: the best of a 24 MB buffer (the W' block of the numerator pass) and a 48 MB one
+        # (the 51 MB dictionary of the rows pass), read the way the passes gather (eight 512-byte pieces in flight per warp)
         peaks["l2_gbs_by_mb"] = {mb: _native.l2_read_bandwidth(bytes=mb << 20, device=local) for mb in (24, 48)}
         peaks["l2_gbs"] = max(peaks["l2_gbs_by_mb"].values())
     except Exception:

@@ -380,15 +380,34 @@ int launch_colsum_w(klnmf_ctx *ctx, const void *W, const void *Wlo, double *out)
 // measurement support: sustained L2 -> SM read bandwidth (a buffer that fits the L2, read many times by every SM with
 // 16-byte loads) -- the denominator of the sparse path's L2 roofline (bench.py), whose gathers never leave the L2
 __global__ void l2_read_kernel(const float4 *__restrict__ p, int64_t n4, int iters, float *__restrict__ sink) {
+  // Shaped like the gathers it is the roofline of: a warp reads 512 contiguous bytes (16 per lane) at EIGHT places of
+  // the buffer before it consumes any of them -- eight independent 16-byte loads in flight per thread.  (One load per
+  // thread and loop trip, the first version, measured the latency of a load, not the bandwidth of the L2: 12-16 TB/s
+  // where the numerator pass of sparse.cu sustains 18-19 TB/s.)
   float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
-  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const uint32_t lane = threadIdx.x & 31;
+  const uint32_t warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t n_warps = (gridDim.x * blockDim.x) >> 5;
+  const uint32_t n_seg = (uint32_t)(n4 / 32);        // 512-byte segments (the host keeps n_seg > 8 * n_warps)
+  const uint32_t hop = n_seg / 8;                    // the eight places of one trip are an eighth of the buffer apart
+  const uint32_t trips = (n_seg + n_warps * 8 - 1) / (n_warps * 8);
   for (int it = 0; it < iters; it++) {
-    // a different starting offset per pass keeps the L1 out of it (every SM walks the whole buffer)
-    int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x + (int64_t)it * 4099 * blockDim.x) % n4;
-    for (int64_t c = 0; c < n4; c += stride, i = (i + stride >= n4 ? i + stride - n4 : i + stride)) {
-      float4 v;
-      asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "l"(p + i));
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    // a different starting segment per pass keeps the L1 out of it (every SM walks the whole buffer)
+    uint32_t s0 = (warp + (uint32_t)it * 4099u) % n_seg;
+    for (uint32_t t = 0; t < trips; t++) {
+      float4 v[8];
+#pragma unroll
+      for (int e = 0; e < 8; e++) {
+        uint32_t seg = s0 + e * hop;
+        seg = seg >= n_seg ? seg - n_seg : seg;
+        asm volatile("ld.global.cg.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(v[e].x), "=f"(v[e].y), "=f"(v[e].z), "=f"(v[e].w)
+                     : "l"(p + (uint64_t)(seg * 32u + lane)));
+      }
+#pragma unroll
+      for (int e = 0; e < 8; e++) { acc.x += v[e].x; acc.y += v[e].y; acc.z += v[e].z; acc.w += v[e].w; }
+      s0 += n_warps;
+      s0 = s0 >= n_seg ? s0 - n_seg : s0;
     }
   }
   if (acc.x + acc.y + acc.z + acc.w == 123.456f) sink[0] = acc.x;      // never true: keeps the loads alive
@@ -401,11 +420,11 @@ int l2_read_bench(int device, int64_t bytes, int iters, double *gbps) {
   float4 *buf = nullptr;
   float *sink = nullptr;
   const int64_t n4 = bytes / 16;
-  KL_CHECK(n4 > (int64_t)prop.multiProcessorCount * 8 * 256, KLNMF_EINVAL, "l2_read_bench: buffer smaller than one grid stride");
+  KL_CHECK(n4 > (int64_t)prop.multiProcessorCount * 8 * 256 && n4 < ((int64_t)1 << 31), KLNMF_EINVAL, "l2_read_bench: 1 MB <= buffer < 32 GB");
   KL_CUDA(cudaMalloc((void **)&buf, (size_t)n4 * 16));
   KL_CUDA(cudaMalloc((void **)&sink, 16));
   cudaMemset(buf, 0, (size_t)n4 * 16);
-  const int grid = prop.multiProcessorCount * 8, block = 256;
+  const int grid = prop.multiProcessorCount * 4, block = 256;
   l2_read_kernel<<<grid, block>>>(buf, n4, 2, sink);                     // warm the L2
   cudaEvent_t e0, e1;
   cudaEventCreate(&e0);
@@ -421,9 +440,9 @@ int l2_read_bench(int device, int64_t bytes, int iters, double *gbps) {
   cudaFree(buf);
   cudaFree(sink);
   if (se != cudaSuccess) { set_error("l2_read_bench: %s", cudaGetErrorString(se)); return KLNMF_ECUDA; }
-  // every pass reads ceil(n4 / stride) * stride elements
-  const int64_t stride = (int64_t)grid * block;
-  const double read = (double)((n4 + stride - 1) / stride * stride) * 16.0 * iters;
+  // every pass makes ceil(n_seg / (8 n_warps)) trips of 8 x 512 bytes per warp
+  const int64_t n_warps = (int64_t)grid * block / 32, n_seg = n4 / 32;
+  const double read = (double)((n_seg + n_warps * 8 - 1) / (n_warps * 8)) * (double)(n_warps * 8) * 512.0 * iters;
   *gbps = read / (ms * 1e-3) / 1e9;
   return KLNMF_OK;
 }
