@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define KLNMF_ABI_VERSION 2   /* bumped whenever a symbol or an argument list changes */
+#define KLNMF_ABI_VERSION 3   /* bumped whenever a symbol or an argument list changes */
 
 /* error codes */
 #define KLNMF_OK            0
@@ -102,6 +102,16 @@ typedef struct klnmf_block {
   int64_t nnz;
 } klnmf_block;
 int klnmf_set_stacked_blocks_host(klnmf_ctx *ctx, int n_blocks, const klnmf_block *blocks);
+/* Hybrid stacks (learner.py:53-56 + array_utils.py:5-9): when the dense blocks of a mixed stack have at
+ * least `cols` columns together (default 1024; 0 = never), klnmf_set_stacked_blocks_host keeps them DENSE -- they go
+ * through the contraction engine (tcgen05 / DMMA), the CSR blocks through the sparse passes, one coefficient matrix and
+ * one row normaliser of the dictionary over both.  The results are the reference's for its all-sparse stack: zeros of
+ * a dense block carry no ratio.  One-pass arithmetic for the dense block (TF32, TF32R, FP64 modes; TF32X3 keeps the
+ * all-CSR stack), single GPU, n x dense-columns within the scratch limit; anything else builds the CSR stack.
+ * Call before the data.  KLNMF_HYBRID=0 / 1 in the environment overrides: never / whenever possible. */
+int klnmf_set_hybrid_min_cols(klnmf_ctx *ctx, int64_t cols);
+/* 1 if the context holds a hybrid stack (its dense blocks kept dense), 0 otherwise */
+int klnmf_is_hybrid(klnmf_ctx *ctx);
 /* CSR with sorted-or-not column indices, no duplicate entries, explicit zeros already
  * removed (the reference calls eliminate_zeros() on the caller's matrix, nmf.py:66). */
 int klnmf_set_csr_host(klnmf_ctx *ctx, const int64_t *indptr, const int32_t *indices,

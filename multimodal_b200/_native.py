@@ -19,7 +19,7 @@ MODES = {"tf32": MODE_TF32, "tf32x3": MODE_TF32X3, "fp64": MODE_FP64, "tf32r": M
 # The one default of the library, the tests and bench.py: one tcgen05 pass on round-to-nearest TF32 copies of W, H and
 # the centered ratio, FP32 state, cancellation-free FP64-accumulated objective.
 DEFAULT_MODE = "tf32r"
-ABI_VERSION = 2
+ABI_VERSION = 3
 F32, F64 = 0, 1
 
 _c_i64 = ctypes.c_int64
@@ -46,6 +46,8 @@ PROTOTYPES = {
     "klnmf_set_dense_device": (_c_int, [_c_vp, _c_vp, _c_int, _c_i64]),
     "klnmf_set_dense_blocks_host": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp, _c_vp]),
     "klnmf_set_stacked_blocks_host": (_c_int, [_c_vp, _c_int, ctypes.POINTER(Block)]),
+    "klnmf_set_hybrid_min_cols": (_c_int, [_c_vp, _c_i64]),
+    "klnmf_is_hybrid": (_c_int, [_c_vp]),
     "klnmf_set_csr_host": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_i64]),
     "klnmf_set_csr_device": (_c_int, [_c_vp, _c_vp, _c_vp, _c_vp, _c_int, _c_i64]),
     "klnmf_create_column_view": (_c_int, [_c_vp, _c_int, _c_vp, _c_vp, _c_i64, ctypes.POINTER(_c_vp)]),
@@ -227,11 +229,20 @@ class Engine(object):
         pf = (ctypes.c_int * nb)(*f32)
         _check(self.lib.klnmf_set_dense_blocks_host(self.h, nb, ptrs, dts, lds, cols, scl, pf))
 
+    def set_hybrid_min_cols(self, cols):
+        """Dense columns from which a mixed stack keeps its dense blocks dense (klnmf_set_hybrid_min_cols; default 1024,
+        0 = never).  Call before set_stacked_blocks."""
+        _check(self.lib.klnmf_set_hybrid_min_cols(self.h, int(cols)))
+
+    def is_hybrid(self):
+        return bool(self.lib.klnmf_is_hybrid(self.h))
+
     def set_stacked_blocks(self, blocks, scales):
         """safe_hstack([c * m]) of learner.stack_data (learner.py:53-56) when a modality is sparse -- the reference then
         makes the whole stack sparse on the host (array_utils.py:5-9).  `blocks` are host ndarrays and canonical scipy CSR
         matrices (n, f_b); they are uploaded as they are and the scaled, stacked CSR matrix is built on the device
-        (klnmf_set_stacked_blocks_host)."""
+        (klnmf_set_stacked_blocks_host) -- or, when the dense blocks are wide enough (set_hybrid_min_cols), only the CSR
+        blocks are stacked and the dense ones stay dense (hybrid stack: tcgen05 contractions next to the sparse passes)."""
         import scipy.sparse as sp
         arr = (Block * len(blocks))()
         keep = []

@@ -125,6 +125,8 @@ int ensure_qlo(klnmf_ctx *ctx) {
   return dmalloc(&ctx->Qlo, ctx->panel_rows * ctx->ldq * (int64_t)ctx->es);
 }
 
+void release_hybrid(klnmf_ctx *ctx);
+
 void release_data(klnmf_ctx *ctx) {
   if (ctx->x_owned && ctx->X) cudaFree(ctx->X);
   if (ctx->csr_owned) {
@@ -140,6 +142,7 @@ void release_data(klnmf_ctx *ctx) {
 }
 
 int kind_guard(klnmf_ctx *ctx, bool sparse) {
+  KL_CHECK(!ctx->hyb, KLNMF_ESTATE, "a context that holds a hybrid (dense + CSR) stack keeps it for life; create a new one");
   KL_CHECK(!ctx->W[0] || ctx->sparse == sparse, KLNMF_ESTATE,
            "a context serves either dense or CSR data for its whole life; create a new one");
   ctx->sparse = sparse;
@@ -502,6 +505,72 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
   return KLNMF_OK;
 }
 
+// ------------------------------------------------------------------------------------------------------------------
+// Hybrid stacks (learner.py:53-56): a dense modality next to a CSR one.  The reference makes the whole stack
+// sparse (array_utils.py:5-9).  Here the CSR blocks form the context's CSR data (ctx->f counts THEIR columns) and go
+// through sparse.cu, the dense blocks stay dense (HybridSide) and go through the contraction engine:
+//   S_d = W.H_d -> Q_d = (X_d+eps)/(S_d+eps) with Q_d = 0 where X_d = 0 (structural zeros of the reference's stack carry
+//   no ratio), objective terms in the dense form -- x log q - x + s is exactly the sparse form's share of the block:
+//   the log term vanishes at x = 0 and sum(s) is the block's colsum(W).rowsum(H_d);
+//   G_d = Q_d.H_d^T (stored), the rows pass starts its G from it: W' = W (.) (G_d + G_s);
+//   N_d = W'^T.Q_d next to the CSR block's numerator, ONE normaliser per component over both (array_utils.py:19-22).
+// The dense block multiplies in the mode's one-pass form (TF32 / TF32R: tcgen05 kind::tf32 on plain FP32 operands; FP64:
+// DMMA); TF32X3 keeps the all-CSR stack (its FP32-grade promise).  One ratio panel: n x fd must fit the scratch limit.
+// ------------------------------------------------------------------------------------------------------------------
+struct HybridSide {
+  int64_t f_total = 0, fd = 0, ld = 0;       // ld = fd rounded up to 32: pitch of X, Q, H, num
+  void *X = nullptr, *Q = nullptr, *G = nullptr, *num = nullptr;
+  void *H[2] = {nullptr, nullptr};
+  double *total = nullptr;                   // k doubles: the joint normaliser
+  struct Range { int dense; int64_t col0, cols, off; };
+  std::vector<Range> ranges;                 // the stack's column ranges, in stack order; off = first column inside its part
+};
+
+void release_hybrid(klnmf_ctx *ctx) {
+  HybridSide *hy = (HybridSide *)ctx->hyb;
+  if (!hy) return;
+  void *ptrs[] = {hy->X, hy->Q, hy->G, hy->num, hy->H[0], hy->H[1], hy->total};
+  for (void *q : ptrs)
+    if (q) cudaFree(q);
+  delete hy;
+  ctx->hyb = nullptr;
+}
+
+// ratio + objective of the dense block, its ratio masked at the structural zeros, and (unless only the objective is
+// wanted) G_d = Q_d.H_d^T into hy->G
+int hybrid_dense_half(klnmf_ctx *ctx, bool only_error) {
+  HybridSide *hy = (HybridSide *)ctx->hyb;
+  const int cur = ctx->cur, hc = ctx->hcur;
+  const int *stop = only_error ? nullptr : ctx->flags + FL_STOP;
+  GemmDesc d{};
+  d.M = ctx->n; d.N = hy->fd; d.K = ctx->k;
+  d.A = ctx->W[cur]; d.a_sm = ctx->ldw; d.a_sk = 1;
+  d.B = hy->H[hc]; d.b_sk = hy->ld; d.b_sn = 1;
+  d.out = hy->Q; d.ldo = hy->ld;
+  d.aux = hy->X; d.ldaux = hy->ld;
+  d.kl = ctx->dred; d.stop = stop; d.only_kl = only_error ? 1 : 0;
+  KL_TRY(dense_gemm(ctx, EPI_RATIO, d));
+  if (only_error) return KLNMF_OK;
+  KL_TRY(launch_mask_ratio(ctx, hy->Q, hy->ld, hy->X, hy->ld, ctx->n, hy->fd, stop));
+  GemmDesc c{};
+  c.M = ctx->n; c.N = ctx->k; c.K = hy->fd;
+  c.A = hy->Q; c.a_sm = hy->ld; c.a_sk = 1;
+  c.B = hy->H[hc]; c.b_sk = 1; c.b_sn = hy->ld;
+  c.out = hy->G; c.ldo = ctx->ldw; c.stop = stop;
+  return dense_gemm(ctx, EPI_STORE, c);
+}
+// N_d += W'^T.Q_d with the updated coefficients Wn (stale ratio, new W: nmf.py:345-349)
+int hybrid_dense_numerator(klnmf_ctx *ctx, const void *Wn) {
+  HybridSide *hy = (HybridSide *)ctx->hyb;
+  KL_TRY(launch_zero(ctx, hy->num, ctx->k * hy->ld * (int64_t)ctx->es));
+  GemmDesc m{};
+  m.M = ctx->k; m.N = hy->fd; m.K = ctx->n;
+  m.A = Wn; m.a_sm = 1; m.a_sk = ctx->ldw;
+  m.B = hy->Q; m.b_sk = hy->ld; m.b_sn = 1;
+  m.out = hy->num; m.ldo = hy->ld; m.stop = ctx->flags + FL_STOP;
+  return dense_gemm(ctx, EPI_ACC, m);
+}
+
 int reset_reduction(klnmf_ctx *ctx) {
   KL_CUDA(cudaMemsetAsync(ctx->dred, 0, ctx->dred_len * 8, ctx->stream));
   KL_CUDA(cudaMemcpyAsync(ctx->dred + 1, ctx->dscal + DS_SUMX, 8, cudaMemcpyDeviceToDevice, ctx->stream));
@@ -581,6 +650,7 @@ int klnmf_destroy(klnmf_ctx *ctx) {
   fused_release(ctx);
   if (ctx->Ht) cudaFree(ctx->Ht);
   release_data(ctx);
+  release_hybrid(ctx);
   for (int i = 0; i < 2; i++) {
     if (ctx->W[i]) cudaFree(ctx->W[i]);
     if (ctx->H[i]) cudaFree(ctx->H[i]);
@@ -743,15 +813,87 @@ int klnmf_set_csr_host(klnmf_ctx *ctx, const int64_t *indptr, const int32_t *ind
   return KLNMF_OK;
 }
 
+int klnmf_set_hybrid_min_cols(klnmf_ctx *ctx, int64_t cols) {
+  KL_CHECK(ctx && cols >= 0, KLNMF_EINVAL, "set_hybrid_min_cols: bad argument");
+  ctx->hybrid_min_cols = cols;
+  return KLNMF_OK;
+}
+
+int klnmf_is_hybrid(klnmf_ctx *ctx) { return ctx && ctx->hyb ? 1 : 0; }
+
 int klnmf_set_stacked_blocks_host(klnmf_ctx *ctx, int n_blocks, const klnmf_block *blocks) {
   KL_CHECK(ctx && blocks, KLNMF_EINVAL, "set_stacked_blocks_host: NULL argument");
   KL_CUDA(cudaSetDevice(ctx->device));
   KL_TRY(kind_guard(ctx, true));
   release_data(ctx);
-  KL_TRY(stack_blocks_to_csr(ctx, n_blocks, blocks));
-  KL_TRY(dmalloc(&ctx->qnz, ctx->nnz * ctx->es));
-  KL_TRY(ensure_state(ctx));
-  KL_TRY(launch_sum_vals(ctx));
+  // Hybrid form (HybridSide above): the dense blocks stay dense when they are wide enough to pay for their contractions,
+  // the mode multiplies in one pass, the context is not part of a multi-GPU job, has no state yet, and one ratio panel
+  // n x fd fits the scratch limit.  hybrid_min_cols = 0 never, KLNMF_HYBRID=0 never, =1 whenever possible.
+  int64_t fd = 0, fs = 0, total = 0;
+  int n_dense = 0, n_csr = 0;
+  for (int b = 0; b < n_blocks; b++) {
+    KL_CHECK(blocks[b].cols >= 0 && (blocks[b].kind == 0 || blocks[b].kind == 1), KLNMF_EINVAL, "set_stacked_blocks_host: bad block %d", b);
+    if (blocks[b].kind == 0) { fd += blocks[b].cols; n_dense++; } else { fs += blocks[b].cols; n_csr++; }
+    total += blocks[b].cols;
+  }
+  const char *he = getenv("KLNMF_HYBRID");
+  const int64_t min_cols = he ? (atoi(he) == 0 ? 0 : 1) : ctx->hybrid_min_cols;
+  const int64_t ldd = round_up(fd, 32);
+  const bool hybrid = min_cols > 0 && fd >= min_cols && n_dense > 0 && n_csr > 0 && fs > 0 && ctx->n > 0 && total == ctx->f &&
+                      !ctx->W[0] && !ctx->comm && ctx->world == 1 && ctx->mode != KLNMF_MODE_TF32X3 && !ctx->debug_simt &&
+                      round_up(ctx->n, 128) * ldd * (int64_t)ctx->es <= ctx->scratch_limit;
+  if (!hybrid) {
+    KL_TRY(stack_blocks_to_csr(ctx, n_blocks, blocks));
+    KL_TRY(dmalloc(&ctx->qnz, ctx->nnz * ctx->es));
+    KL_TRY(ensure_state(ctx));
+    KL_TRY(launch_sum_vals(ctx));
+    KL_CUDA(cudaStreamSynchronize(ctx->stream));
+    ctx->have_x = true;
+    return KLNMF_OK;
+  }
+  HybridSide *hy = new HybridSide();
+  ctx->hyb = hy;
+  hy->f_total = total; hy->fd = fd; hy->ld = ldd;
+  const int64_t es = ctx->es;
+  std::vector<klnmf_block> csr;
+  int64_t col0 = 0, offd = 0, offs = 0;
+  int rc = KLNMF_OK;
+  auto fail = [&](int code) { release_hybrid(ctx); return code; };
+  if ((rc = dmalloc(&hy->X, ctx->n * ldd * es)) != KLNMF_OK) return fail(rc);
+  if (cudaMemsetAsync(hy->X, 0, ctx->n * ldd * es, ctx->stream) != cudaSuccess) return fail(KLNMF_ECUDA);
+  for (int b = 0; b < n_blocks; b++) {
+    const klnmf_block &s = blocks[b];
+    if (s.kind == 0) {
+      if (!(s.ld >= s.cols && (s.dense || s.cols == 0)) || !(s.dtype == KLNMF_F32 || s.dtype == KLNMF_F64)) {
+        set_error("set_stacked_blocks_host: bad dense block %d", b);
+        return fail(KLNMF_EINVAL);
+      }
+      hy->ranges.push_back({1, col0, s.cols, offd});
+      rc = upload_matrix(ctx, s.dense, s.dtype, s.ld, (char *)hy->X + offd * es, ldd, ctx->n, s.cols, false, s.scale,
+                         s.product_f32 && s.dtype == KLNMF_F32 ? 1 : 0);
+      if (rc != KLNMF_OK) return fail(rc);
+      offd += s.cols;
+    } else {
+      hy->ranges.push_back({0, col0, s.cols, offs});
+      csr.push_back(s);
+      offs += s.cols;
+    }
+    col0 += s.cols;
+  }
+  ctx->f = fs;                                   // from here on the context's CSR machinery sees the CSR columns only
+  if ((rc = stack_blocks_to_csr(ctx, (int)csr.size(), csr.data())) != KLNMF_OK) { ctx->f = total; return fail(rc); }
+  if ((rc = dmalloc(&ctx->qnz, ctx->nnz * es)) != KLNMF_OK || (rc = ensure_state(ctx)) != KLNMF_OK ||
+      (rc = launch_sum_vals(ctx)) != KLNMF_OK)
+    return fail(rc);
+  const int64_t hb = ctx->k * ldd * es;
+  if ((rc = dmalloc(&hy->Q, round_up(ctx->n, 128) * ldd * es)) != KLNMF_OK || (rc = dmalloc(&hy->G, ctx->n * ctx->ldw * es)) != KLNMF_OK ||
+      (rc = dmalloc(&hy->num, hb)) != KLNMF_OK || (rc = dmalloc(&hy->H[0], hb)) != KLNMF_OK ||
+      (rc = dmalloc(&hy->H[1], hb)) != KLNMF_OK || (rc = dmalloc((void **)&hy->total, (ctx->k + 1) * 8)) != KLNMF_OK)
+    return fail(rc);
+  cudaMemsetAsync(hy->H[0], 0, hb, ctx->stream);
+  cudaMemsetAsync(hy->H[1], 0, hb, ctx->stream);
+  cudaMemsetAsync(hy->num, 0, hb, ctx->stream);
+  cudaMemsetAsync(hy->G, 0, ctx->n * ctx->ldw * es, ctx->stream);
   KL_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->have_x = true;
   return KLNMF_OK;
@@ -831,6 +973,10 @@ int klnmf_check_input(klnmf_ctx *ctx, int32_t out[2]) {
   KL_CUDA(cudaMemsetAsync(ctx->flags + FL_NEG, 0, 8, ctx->stream));
   if (ctx->sparse) KL_TRY(launch_check(ctx, ctx->vals, ctx->es, 1, ctx->nnz, ctx->nnz));
   else KL_TRY(launch_check(ctx, ctx->X, ctx->es, ctx->n, ctx->f, ctx->ldx));
+  if (ctx->hyb) {
+    const HybridSide *hy = (const HybridSide *)ctx->hyb;
+    KL_TRY(launch_check(ctx, hy->X, ctx->es, ctx->n, hy->fd, hy->ld));
+  }
   int *h = (int *)ctx->pinned;
   KL_CUDA(cudaMemcpyAsync(h, ctx->flags + FL_NEG, 8, cudaMemcpyDeviceToHost, ctx->stream));
   KL_CUDA(cudaStreamSynchronize(ctx->stream));
@@ -843,9 +989,21 @@ int klnmf_check_input(klnmf_ctx *ctx, int32_t out[2]) {
 int klnmf_set_dictionary_host(klnmf_ctx *ctx, const double *H, int64_t ld) {
   KL_CHECK(ctx && H, KLNMF_EINVAL, "set_dictionary_host: NULL argument");
   KL_CHECK(ctx->have_x, KLNMF_ESTATE, "set the data before the dictionary");
-  KL_CHECK(ld >= ctx->f, KLNMF_EINVAL, "set_dictionary_host: ld < f");
+  KL_CHECK(ld >= (ctx->hyb ? ((HybridSide *)ctx->hyb)->f_total : ctx->f), KLNMF_EINVAL, "set_dictionary_host: ld < f");
   KL_CUDA(cudaSetDevice(ctx->device));
   const int hc = ctx->hcur;
+  if (ctx->hyb) {
+    // the stack's columns go to their part: dense ranges k x fd row-major, CSR ranges transposed f_s x k
+    HybridSide *hy = (HybridSide *)ctx->hyb;
+    for (const auto &r : hy->ranges) {
+      if (r.dense) KL_TRY(upload_matrix(ctx, H + r.col0, KLNMF_F64, ld, (char *)hy->H[hc] + r.off * ctx->es, hy->ld, ctx->k, r.cols, false));
+      else KL_TRY(upload_matrix(ctx, H + r.col0, KLNMF_F64, ld, (char *)ctx->H[hc] + r.off * ctx->ldh * ctx->es, ctx->ldh, ctx->k, r.cols, true));
+    }
+    KL_TRY(launch_rowsum_h(ctx));              // row sums of the CSR part: what the sparse objective multiplies colsum(W) with
+    ctx->have_h = true;
+    ctx->ht_stale = true;
+    return KLNMF_OK;
+  }
   // dense layout k x f; sparse layout transposed f x k
   KL_TRY(upload_matrix(ctx, H, KLNMF_F64, ld, ctx->H[hc], ctx->ldh, ctx->k, ctx->f, ctx->sparse));
   if (ctx->split)
@@ -861,6 +1019,15 @@ int klnmf_get_dictionary_host(klnmf_ctx *ctx, double *H, int64_t ld) {
   KL_CHECK(ctx && H && ctx->have_h, KLNMF_ESTATE, "get_dictionary_host: no dictionary");
   KL_CUDA(cudaSetDevice(ctx->device));
   const int hc = ctx->hcur;
+  if (ctx->hyb) {
+    HybridSide *hy = (HybridSide *)ctx->hyb;
+    KL_CHECK(ld >= hy->f_total, KLNMF_EINVAL, "get_dictionary_host: ld < f");
+    for (const auto &r : hy->ranges) {
+      if (r.dense) KL_TRY(download_matrix(ctx, (char *)hy->H[hc] + r.off * ctx->es, nullptr, hy->ld, H + r.col0, KLNMF_F64, ld, ctx->k, r.cols, false));
+      else KL_TRY(download_matrix(ctx, (char *)ctx->H[hc] + r.off * ctx->ldh * ctx->es, nullptr, ctx->ldh, H + r.col0, KLNMF_F64, ld, ctx->k, r.cols, true));
+    }
+    return KLNMF_OK;
+  }
   return download_matrix(ctx, ctx->H[hc], ctx->split ? ctx->Hlo[hc] : nullptr, ctx->ldh, H, KLNMF_F64, ld, ctx->k,
                          ctx->f, ctx->sparse);
 }
@@ -870,7 +1037,18 @@ int klnmf_init_coefficients(klnmf_ctx *ctx) {
   KL_CUDA(cudaSetDevice(ctx->device));
   if (ctx->n == 0) { ctx->have_w = true; return KLNMF_OK; }
   if (ctx->sparse) {
-    KL_TRY(sparse_init_w(ctx));
+    if (ctx->hyb) {   // W0 = X_d.H_d^T + X_s.H_s^T: the dense block's product first, the CSR pass starts from it
+      HybridSide *hy = (HybridSide *)ctx->hyb;
+      GemmDesc c{};
+      c.M = ctx->n; c.N = ctx->k; c.K = hy->fd;
+      c.A = hy->X; c.a_sm = hy->ld; c.a_sk = 1;
+      c.B = hy->H[ctx->hcur]; c.b_sk = 1; c.b_sn = hy->ld;
+      c.out = hy->G; c.ldo = ctx->ldw;
+      KL_TRY(dense_gemm(ctx, EPI_STORE, c));
+      KL_TRY(sparse_init_w(ctx, hy->G));
+    } else {
+      KL_TRY(sparse_init_w(ctx));
+    }
     ctx->have_w = true;
     return KLNMF_OK;
   }
@@ -937,6 +1115,7 @@ int klnmf_coefficients_device(klnmf_ctx *ctx, void **ptr, int64_t *ld, int *dtyp
 
 int klnmf_dictionary_device(klnmf_ctx *ctx, void **ptr, int64_t *ld, int *dtype) {
   KL_CHECK(ctx && ptr && ld && dtype && ctx->have_h, KLNMF_ESTATE, "dictionary_device: no dictionary");
+  KL_CHECK(!ctx->hyb, KLNMF_ESTATE, "dictionary_device: a hybrid stack keeps its dictionary in two parts; use get_dictionary_host");
   KL_CHECK(!ctx->split, KLNMF_ESTATE, "split-TF32 state is a (hi, lo) pair; use get_dictionary_host");
   *ptr = ctx->H[ctx->hcur]; *ld = ctx->ldh; *dtype = ctx->es == 8 ? KLNMF_F64 : KLNMF_F32;
   return KLNMF_OK;
@@ -993,8 +1172,17 @@ int klnmf_run_resume(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, doub
     ctx->num_reduced = false;
     if (fit) r = launch_zero(ctx, ctx->num, ctx->num_bytes);
     if (r == KLNMF_OK && ctx->sparse && ctx->n > 0) {
-      { PhaseTimer t(ctx, prof, PH_RATIO); r = sparse_rows(ctx, 0, fit ? 2 : 0); }
-      if (r == KLNMF_OK && fit) { PhaseTimer t(ctx, prof, PH_NUM); r = sparse_scatter(ctx, false); }
+      HybridSide *hy = (HybridSide *)ctx->hyb;
+      {
+        PhaseTimer t(ctx, prof, PH_RATIO);
+        if (hy) r = hybrid_dense_half(ctx, false);
+        if (r == KLNMF_OK) r = sparse_rows(ctx, 0, fit ? 2 : 0, hy ? hy->G : nullptr);
+      }
+      if (r == KLNMF_OK && fit) {
+        PhaseTimer t(ctx, prof, PH_NUM);
+        if (hy) r = hybrid_dense_numerator(ctx, ctx->W[ctx->cur ^ 1]);
+        if (r == KLNMF_OK) r = sparse_scatter(ctx, false);
+      }
     } else if (r == KLNMF_OK) {
       r = dense_iteration(ctx, fit, false, prof);
     }
@@ -1016,6 +1204,10 @@ int klnmf_run_resume(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, doub
     if (r == KLNMF_OK && fit) {
       PhaseTimer t(ctx, prof, PH_DICT);
       const int hc = ctx->hcur;
+      if (ctx->hyb) {
+        HybridSide *hy = (HybridSide *)ctx->hyb;
+        r = launch_dict_update_hybrid(ctx, ctx->H[hc], ctx->H[hc ^ 1], hy->H[hc], hy->H[hc ^ 1], hy->num, hy->fd, hy->ld, hy->total);
+      } else
       r = ctx->sparse ? launch_dict_update_t(ctx, ctx->H[hc], ctx->H[hc ^ 1])
                       : launch_dict_update(ctx, ctx->H[hc], ctx->H[hc ^ 1], ctx->split ? ctx->Hlo[hc ^ 1] : nullptr,
                                            ctx->centered ? ctx->colsumW : nullptr);
@@ -1088,7 +1280,12 @@ int klnmf_error(klnmf_ctx *ctx, double *out) {
   KL_CHECK(ctx->have_x && ctx->have_h && ctx->have_w, KLNMF_ESTATE, "klnmf_error needs data, dictionary and coefficients");
   KL_CUDA(cudaSetDevice(ctx->device));
   KL_TRY(reset_reduction(ctx));
-  if (ctx->sparse) { if (ctx->n > 0) KL_TRY(sparse_rows(ctx, 1)); }
+  if (ctx->sparse) {
+    if (ctx->n > 0) {
+      if (ctx->hyb) KL_TRY(hybrid_dense_half(ctx, true));
+      KL_TRY(sparse_rows(ctx, 1));
+    }
+  }
   else KL_TRY(dense_iteration(ctx, 0, true, nullptr));
   if (ctx->world > 1) KL_TRY(nccl_allreduce_sum_f64(ctx, ctx->dred, 2 + ctx->k));
   std::vector<double> h(2 + ctx->k), rs(ctx->k);
@@ -1109,6 +1306,7 @@ int klnmf_error(klnmf_ctx *ctx, double *out) {
 // _updated_H with Q=None (nmf.py:345-351): H <- rownorm(H (.) W^T Q(W,H)) with the CURRENT W.
 int klnmf_dictionary_step(klnmf_ctx *ctx) {
   KL_CHECK(ctx && ctx->have_x && ctx->have_h && ctx->have_w, KLNMF_ESTATE, "dictionary_step needs data, dictionary, coefficients");
+  KL_CHECK(!ctx->hyb, KLNMF_ESTATE, "dictionary_step: not available on a hybrid (dense + CSR) stack");
   KL_CUDA(cudaSetDevice(ctx->device));
   const int64_t hbytes = (ctx->sparse ? ctx->f : ctx->k) * ctx->ldh * (int64_t)ctx->es;
   KL_TRY(setup_num_chunks(ctx, 1));
@@ -1140,6 +1338,7 @@ int klnmf_dictionary_step(klnmf_ctx *ctx) {
 // _Q (nmf.py:325-336): dense -> n x f matrix; CSR -> nnz values in the order of the stored entries.
 int klnmf_ratio_host(klnmf_ctx *ctx, void *out, int dtype, int64_t ld) {
   KL_CHECK(ctx && out && ctx->have_x && ctx->have_h && ctx->have_w, KLNMF_ESTATE, "ratio_host needs data, dictionary, coefficients");
+  KL_CHECK(!ctx->hyb, KLNMF_ESTATE, "ratio_host: not available on a hybrid (dense + CSR) stack");
   KL_CUDA(cudaSetDevice(ctx->device));
   KL_TRY(reset_reduction(ctx));
   if (ctx->sparse) {
@@ -1159,6 +1358,7 @@ int klnmf_ratio_host(klnmf_ctx *ctx, void *out, int dtype, int64_t ld) {
 // _special_sparse_dot (nmf.py:52-70): (W.H) sampled at the stored entries of the CSR data.
 int klnmf_sddmm_host(klnmf_ctx *ctx, double *out_vals) {
   KL_CHECK(ctx && ctx->sparse && ctx->have_x && ctx->have_h && ctx->have_w, KLNMF_ESTATE, "sddmm_host needs CSR data, dictionary, coefficients");
+  KL_CHECK(!ctx->hyb, KLNMF_ESTATE, "sddmm_host: not available on a hybrid (dense + CSR) stack");
   KL_CUDA(cudaSetDevice(ctx->device));
   if (ctx->nnz == 0) return KLNMF_OK;
   KL_CHECK(out_vals, KLNMF_EINVAL, "sddmm_host: NULL output");
@@ -1222,6 +1422,7 @@ int klnmf_nccl_unique_id(void *id128) {
 }
 int klnmf_comm_init(klnmf_ctx *ctx, const void *id128, int rank, int world) {
   KL_CHECK(ctx && id128, KLNMF_EINVAL, "comm_init: NULL argument");
+  KL_CHECK(!ctx->hyb || world == 1, KLNMF_ESTATE, "comm_init: a hybrid (dense + CSR) stack is single-GPU; create the communicator before the data");
   return nccl_comm_init(ctx, id128, rank, world);
 }
 int klnmf_comm_create(void **comm, int device, const void *id128, int rank, int world) {
@@ -1233,6 +1434,7 @@ int klnmf_comm_create(void **comm, int device, const void *id128, int rank, int 
 }
 int klnmf_comm_attach(klnmf_ctx *ctx, void *comm, int rank, int world) {
   KL_CHECK(ctx && comm && world >= 1 && rank >= 0 && rank < world, KLNMF_EINVAL, "comm_attach: bad argument");
+  KL_CHECK(!ctx->hyb || world == 1, KLNMF_ESTATE, "comm_attach: a hybrid (dense + CSR) stack is single-GPU; attach the communicator before the data");
   nccl_comm_destroy(ctx);          // an owned communicator of an earlier klnmf_comm_init
   ctx->comm = comm;
   ctx->comm_owned = false;

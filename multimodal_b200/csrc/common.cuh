@@ -71,6 +71,8 @@ struct klnmf_ctx {
   bool csr_owned = false;
   void *qnz = nullptr;         // nnz ratio values (sparse path)
   void *bcsc = nullptr;        // blocked-CSC copy of the pattern for the numerator pass (sparse.cu), built lazily
+  void *hyb = nullptr;         // hybrid stack: the dense block's side (api.cu: HybridSide); ctx->f then counts the CSR columns
+  int64_t hybrid_min_cols = 1024;   // dense columns from which klnmf_set_stacked_blocks_host keeps the dense blocks dense
 
   // ---- state -------------------------------------------------------------------------
   bool have_h = false, have_w = false;
@@ -199,6 +201,10 @@ int launch_rsh32(klnmf_ctx *ctx);           // rsh32 <- rowsumH (FP32, zero padd
 int launch_colsum_w(klnmf_ctx *ctx, const void *W, const void *Wlo, double *out);   // out[a] += sum_i W[i,a]
 int launch_dict_update_t(klnmf_ctx *ctx, const void *Ht_old, void *Ht_new);     // sparse: f x k layout
 int launch_decide(klnmf_ctx *ctx, int iter_index);
+// hybrid stacks (api.cu: HybridSide): Q <- 0 where X == 0; the joint dictionary update of the dense and the CSR block
+int launch_mask_ratio(klnmf_ctx *ctx, void *Q, int64_t ldq, const void *X, int64_t ldx, int64_t rows, int64_t cols, const int *stop);
+int launch_dict_update_hybrid(klnmf_ctx *ctx, const void *Ht_old, void *Ht_new, const void *Hd_old, void *Hd_new, const void *Nd,
+                              int64_t fd, int64_t ldhd, double *total);
 int launch_split(klnmf_ctx *ctx, const float *src, float *hi, float *lo, int64_t rows, int64_t cols, int64_t ld);
 // dst = (src [+ src_lo]) converted; optional transpose
 int launch_convert(klnmf_ctx *ctx, const void *src, const void *src_lo, int src_dtype, int64_t src_ld, void *dst,
@@ -213,9 +219,9 @@ int l2_read_bench(int device, int64_t bytes, int iters, double *gbps);   // meas
 // ---- sparse path: sparse.cu ------------------------------------------------------------------------
 // mode: 0 full pass, 1 objective only, 3 SDDMM only.  q_order (mode 0): 0 the ratio is not kept (transform), 1 kept in
 // CSR order (the _Q hook), 2 kept in blocked-CSC order for the numerator pass (fit)
-int sparse_rows(klnmf_ctx *ctx, int mode, int q_order = 0);
+int sparse_rows(klnmf_ctx *ctx, int mode, int q_order = 0, const void *g0 = nullptr);   // g0: n x ldw, what G starts from
 int sparse_scatter(klnmf_ctx *ctx, bool use_current_w);
-int sparse_init_w(klnmf_ctx *ctx);
+int sparse_init_w(klnmf_ctx *ctx, const void *g0 = nullptr);
 int sparse_fill_synthetic(klnmf_ctx *ctx, int64_t nnz_per_row, uint64_t seed);
 void sparse_release_pattern(klnmf_ctx *ctx);   // drop the blocked-CSC copy (the data changed)
 

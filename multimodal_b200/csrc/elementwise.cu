@@ -95,7 +95,10 @@ template <typename T>
 __global__ void __launch_bounds__(256) dict_scale_t_kernel(const T *__restrict__ Ht, const T *__restrict__ Nt,
                                                            T *__restrict__ Htn, int64_t f, int64_t k, int64_t ld,
                                                            const double *__restrict__ hsum,
-                                                           double *__restrict__ rowsum, const int *stop) {
+                                                           double *__restrict__ rowsum, const int *stop,
+                                                           const double *__restrict__ rs_part) {
+  // rs_part (hybrid stacks): the share of hsum that belongs to THESE columns -- rowsum then is the row sum of this
+  // block of the dictionary only, which is what the sparse objective multiplies colsum(W) with
   if (*stop != 0) return;
   const int64_t total = f * k;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -103,7 +106,51 @@ __global__ void __launch_bounds__(256) dict_scale_t_kernel(const T *__restrict__
     int64_t j = i / k, a = i - j * k;
     double inv = 1.0 / (KL_NORM_EPS + hsum[a]);
     Htn[j * ld + a] = (T)((double)(Ht[j * ld + a] * Nt[j * ld + a]) * inv);
-    if (j == 0) rowsum[a] = hsum[a] * inv;
+    if (j == 0) rowsum[a] = (rs_part ? rs_part[a] : hsum[a]) * inv;
+  }
+}
+
+// ---- hybrid stacks (a dense block next to the CSR block, api.cu: HybridSide) -------------------------------------
+// structural zeros of the stack carry no ratio: the reference sparsifies the whole stack (array_utils.py:5-9) and
+// forms the ratio at its stored entries only (nmf.py:52-70, 332-336)
+template <typename T>
+__global__ void __launch_bounds__(256) mask_ratio_kernel(T *__restrict__ Q, int64_t ldq, const T *__restrict__ X, int64_t ldx,
+                                                         int64_t rows, int64_t cols, const int *stop) {
+  if (stop != nullptr && *stop != 0) return;
+  const int64_t total = rows * cols;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = i / cols, c = i - r * cols;
+    if (X[r * ldx + c] == (T)0) Q[r * ldq + c] = (T)0;
+  }
+}
+// hsum_d[a] = sum_j H[a,j] N[a,j] over the dense block's columns (k x f layout), one CTA per component
+template <typename T>
+__global__ void __launch_bounds__(256) hyb_rowsum_kernel(const T *__restrict__ H, const T *__restrict__ N, int64_t f, int64_t ld,
+                                                         double *__restrict__ hsum_d, const int *stop) {
+  if (*stop != 0) return;
+  __shared__ double red[32];
+  const int64_t a = blockIdx.x;
+  double s = 0.0;
+  for (int64_t j = threadIdx.x; j < f; j += blockDim.x) s += (double)(H[a * ld + j] * N[a * ld + j]);
+  s = block_sum(s, red);
+  if (threadIdx.x == 0) hsum_d[a] = s;
+}
+__global__ void hyb_total_kernel(double *__restrict__ hsum_d, const double *__restrict__ hsum_s, int64_t k, const int *stop) {
+  if (*stop != 0) return;
+  for (int64_t a = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; a < k; a += (int64_t)gridDim.x * blockDim.x)
+    hsum_d[a] += hsum_s[a];
+}
+// H'[a,j] = H[a,j] N[a,j] / (1e-16 + total[a])  (array_utils.py:19-22 over the WHOLE row of the stacked dictionary)
+template <typename T>
+__global__ void __launch_bounds__(256) hyb_scale_kernel(const T *__restrict__ H, const T *__restrict__ N, T *__restrict__ Hn,
+                                                        int64_t k, int64_t f, int64_t ld, const double *__restrict__ total,
+                                                        const int *stop) {
+  if (*stop != 0) return;
+  const int64_t cells = k * f;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < cells; i += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t a = i / f, j = i - a * f;
+    const double inv = 1.0 / (KL_NORM_EPS + total[a]);
+    Hn[a * ld + j] = (T)((double)(H[a * ld + j] * N[a * ld + j]) * inv);
   }
 }
 
@@ -322,16 +369,61 @@ int launch_dict_update_t(klnmf_ctx *ctx, const void *Ht_old, void *Ht_new) {
                                                               ctx->flags + FL_STOP);
     dict_scale_t_kernel<double><<<g2, 256, 0, ctx->stream>>>((const double *)Ht_old, (const double *)ctx->num,
                                                              (double *)Ht_new, ctx->f, ctx->k, ctx->ldh, ctx->hsum,
-                                                             ctx->rowsumH, ctx->flags + FL_STOP);
+                                                             ctx->rowsumH, ctx->flags + FL_STOP, nullptr);
   } else {
     dict_colsum_t_kernel<float><<<g1, 256, 0, ctx->stream>>>((const float *)Ht_old, (const float *)ctx->num,
                                                              ctx->f, ctx->k, ctx->ldh, ctx->hsum, rpb,
                                                              ctx->flags + FL_STOP);
     dict_scale_t_kernel<float><<<g2, 256, 0, ctx->stream>>>((const float *)Ht_old, (const float *)ctx->num,
                                                             (float *)Ht_new, ctx->f, ctx->k, ctx->ldh, ctx->hsum,
-                                                            ctx->rowsumH, ctx->flags + FL_STOP);
+                                                            ctx->rowsumH, ctx->flags + FL_STOP, nullptr);
   }
   ctx->n_launch += 2;
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
+int launch_mask_ratio(klnmf_ctx *ctx, void *Q, int64_t ldq, const void *X, int64_t ldx, int64_t rows, int64_t cols,
+                      const int *stop) {
+  if (rows * cols == 0) return KLNMF_OK;
+  const int g = grid_for(ctx, rows * cols, 256);
+  if (ctx->es == 8) mask_ratio_kernel<double><<<g, 256, 0, ctx->stream>>>((double *)Q, ldq, (const double *)X, ldx, rows, cols, stop);
+  else mask_ratio_kernel<float><<<g, 256, 0, ctx->stream>>>((float *)Q, ldq, (const float *)X, ldx, rows, cols, stop);
+  ctx->n_launch++;
+  KL_CUDA(cudaGetLastError());
+  return KLNMF_OK;
+}
+
+// The dictionary update of a hybrid stack (nmf.py:345-351): one normaliser per component over BOTH blocks.
+// Sparse block: Ht (f_s x k, numerator ctx->num), dense block: Hd (k x fd, numerator Nd).  total = scratch of k doubles.
+int launch_dict_update_hybrid(klnmf_ctx *ctx, const void *Ht_old, void *Ht_new, const void *Hd_old, void *Hd_new,
+                              const void *Nd, int64_t fd, int64_t ldhd, double *total) {
+  const int *stop = ctx->flags + FL_STOP;
+  KL_CUDA(cudaMemsetAsync(ctx->hsum, 0, sizeof(double) * ctx->k, ctx->stream));
+  const int rpb = 64;
+  const unsigned g1 = (unsigned)ceil_div(ctx->f, rpb);
+  const int g2 = grid_for(ctx, ctx->f * ctx->k, 256), g3 = grid_for(ctx, ctx->k * fd, 256);
+  const unsigned gk = (unsigned)ceil_div(ctx->k, 256);
+  if (ctx->es == 8) {
+    hyb_rowsum_kernel<double><<<(unsigned)ctx->k, 256, 0, ctx->stream>>>((const double *)Hd_old, (const double *)Nd, fd, ldhd, total, stop);
+    dict_colsum_t_kernel<double><<<g1, 256, 0, ctx->stream>>>((const double *)Ht_old, (const double *)ctx->num, ctx->f, ctx->k,
+                                                              ctx->ldh, ctx->hsum, rpb, stop);
+    hyb_total_kernel<<<gk, 256, 0, ctx->stream>>>(total, ctx->hsum, ctx->k, stop);
+    dict_scale_t_kernel<double><<<g2, 256, 0, ctx->stream>>>((const double *)Ht_old, (const double *)ctx->num, (double *)Ht_new,
+                                                             ctx->f, ctx->k, ctx->ldh, total, ctx->rowsumH, stop, ctx->hsum);
+    hyb_scale_kernel<double><<<g3, 256, 0, ctx->stream>>>((const double *)Hd_old, (const double *)Nd, (double *)Hd_new, ctx->k, fd,
+                                                          ldhd, total, stop);
+  } else {
+    hyb_rowsum_kernel<float><<<(unsigned)ctx->k, 256, 0, ctx->stream>>>((const float *)Hd_old, (const float *)Nd, fd, ldhd, total, stop);
+    dict_colsum_t_kernel<float><<<g1, 256, 0, ctx->stream>>>((const float *)Ht_old, (const float *)ctx->num, ctx->f, ctx->k,
+                                                             ctx->ldh, ctx->hsum, rpb, stop);
+    hyb_total_kernel<<<gk, 256, 0, ctx->stream>>>(total, ctx->hsum, ctx->k, stop);
+    dict_scale_t_kernel<float><<<g2, 256, 0, ctx->stream>>>((const float *)Ht_old, (const float *)ctx->num, (float *)Ht_new,
+                                                            ctx->f, ctx->k, ctx->ldh, total, ctx->rowsumH, stop, ctx->hsum);
+    hyb_scale_kernel<float><<<g3, 256, 0, ctx->stream>>>((const float *)Hd_old, (const float *)Nd, (float *)Hd_new, ctx->k, fd, ldhd,
+                                                         total, stop);
+  }
+  ctx->n_launch += 5;
   KL_CUDA(cudaGetLastError());
   return KLNMF_OK;
 }

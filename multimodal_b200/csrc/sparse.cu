@@ -118,7 +118,9 @@ __global__ void __launch_bounds__(WARPS * 32)
 sparse_rows_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                    const T *__restrict__ vals, const T *__restrict__ W, int64_t ldw, const T *__restrict__ Ht,
                    int64_t ldh, T *__restrict__ Wn, T *__restrict__ qnz, int64_t n, double *__restrict__ dred,
-                   const int *stop) {
+                   const int *stop, const T *__restrict__ g0) {
+  // g0 (MODE 0 and 2, may be null): n x ldw, what G starts from -- the dense block's share Q_d.H_d^T of a hybrid stack
+  // (api.cu: HybridSide), so that W' = W (.) (G_dense + G_sparse) comes out of this pass
   constexpr int B = Batch<T, VPL>::B, SH = Batch<T, VPL>::SH;
   if (stop != nullptr && *stop != 0) return;
   __shared__ double red[WARPS];
@@ -145,6 +147,7 @@ sparse_rows_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict
 #pragma unroll
       for (int e = 0; e < 4; e++) { w[c][e] = (T)0; g[c][e] = (T)0; }
       if (MODE != 2 && act[c]) ld4(W + i * ldw + 128 * c + 4 * lane, w[c]);
+      if ((MODE == 0 || MODE == 2) && g0 != nullptr && act[c]) ld4(g0 + i * ldw + 128 * c + 4 * lane, g[c]);
       if (MODE != 2) {
 #pragma unroll
         for (int e = 0; e < 4; e++) cs[c][e] += (double)w[c][e];
@@ -270,7 +273,7 @@ __global__ void __launch_bounds__(WARPS * 32, VPL <= 2 ? 2 : 1)
 sparse_rows_full_kernel(const int64_t *__restrict__ indptr, const int32_t *__restrict__ indices,
                         const float *__restrict__ vals, const float *__restrict__ W, const float *__restrict__ Ht,
                         uint32_t ld, float *__restrict__ Wn, float *__restrict__ qnz, int64_t n,
-                        double *__restrict__ dred, const int *stop) {
+                        double *__restrict__ dred, const int *stop, const float *__restrict__ g0) {
   constexpr int B = Batch<float, VPL>::B, SH = Batch<float, VPL>::SH;
   if (stop != nullptr && *stop != 0) return;
   __shared__ double red[WARPS];
@@ -320,6 +323,10 @@ sparse_rows_full_kernel(const int64_t *__restrict__ indptr, const int32_t *__res
       upk2(t.x, a0, a1); upk2(t.y, a2, a3);
       cs[c][0] += (double)a0; cs[c][1] += (double)a1; cs[c][2] += (double)a2; cs[c][3] += (double)a3;
       g[c][0] = pk2(0.f, 0.f); g[c][1] = pk2(0.f, 0.f);
+      if (MODE == 0 && g0 != nullptr) {           // hybrid stack: G starts from the dense block's share
+        const ulonglong2 t0 = (reinterpret_cast<const ulonglong2 *>(g0 + (uint64_t)i * ld) + lane)[32 * c];
+        g[c][0] = t0.x; g[c][1] = t0.y;
+      }
     }
     float klf = 0.f;
     int32_t jl_next = 0;
@@ -615,7 +622,7 @@ inline bool use_bcsc(const klnmf_ctx *ctx) {
 // q_order (mode 0 only): 0 = the ratio is not kept (transform: 4 bytes per stored entry less to write), 1 / 2 = kept in
 // CSR order, for the _Q hook / for the numerator pass
 template <typename T, int VPL>
-int run_rows(klnmf_ctx *ctx, int mode, const T *W, T *Wn, int q_order) {
+int run_rows(klnmf_ctx *ctx, int mode, const T *W, T *Wn, int q_order, const T *g0) {
   const int grid = (int)(ceil_div(ctx->n, WARPS) < (int64_t)ctx->sm_count * 8 ? ceil_div(ctx->n, WARPS)
                                                                                : (int64_t)ctx->sm_count * 8);
   const int *stop = ctx->flags + FL_STOP;
@@ -627,11 +634,11 @@ int run_rows(klnmf_ctx *ctx, int mode, const T *W, T *Wn, int q_order) {
     if (mode == 0)
       sparse_rows_full_kernel<VPL, 0><<<grid, WARPS * 32, 0, ctx->stream>>>(
           ctx->indptr, ctx->indices, (const float *)ctx->vals, (const float *)W, (const float *)Ht, (uint32_t)ctx->ldh,
-          (float *)Wn, q_order == 0 ? nullptr : (float *)ctx->qnz, ctx->n, ctx->dred, stop);
+          (float *)Wn, q_order == 0 ? nullptr : (float *)ctx->qnz, ctx->n, ctx->dred, stop, (const float *)g0);
     else
       sparse_rows_full_kernel<VPL, 1><<<grid, WARPS * 32, 0, ctx->stream>>>(
           ctx->indptr, ctx->indices, (const float *)ctx->vals, (const float *)W, (const float *)Ht, (uint32_t)ctx->ldh,
-          nullptr, nullptr, ctx->n, ctx->dred, nullptr);
+          nullptr, nullptr, ctx->n, ctx->dred, nullptr, nullptr);
     ctx->n_launch++;
     KL_CUDA(cudaGetLastError());
     return KLNMF_OK;
@@ -640,19 +647,19 @@ int run_rows(klnmf_ctx *ctx, int mode, const T *W, T *Wn, int q_order) {
     sparse_rows_kernel<T, VPL, 0><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->indptr, ctx->indices, (const T *)ctx->vals, W,
                                                                         ctx->ldw, Ht, ctx->ldh, Wn,
                                                                         q_order == 0 ? nullptr : (T *)ctx->qnz, ctx->n,
-                                                                        ctx->dred, stop);
+                                                                        ctx->dred, stop, g0);
   else if (mode == 1)
     sparse_rows_kernel<T, VPL, 1><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->indptr, ctx->indices, (const T *)ctx->vals, W,
                                                                         ctx->ldw, Ht, ctx->ldh, nullptr, nullptr, ctx->n,
-                                                                        ctx->dred, nullptr);
+                                                                        ctx->dred, nullptr, nullptr);
   else if (mode == 3)
     sparse_rows_kernel<T, VPL, 3><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->indptr, ctx->indices, (const T *)ctx->vals, W,
                                                                         ctx->ldw, Ht, ctx->ldh, nullptr, (T *)ctx->qnz, ctx->n,
-                                                                        ctx->dred, nullptr);
+                                                                        ctx->dred, nullptr, nullptr);
   else
     sparse_rows_kernel<T, VPL, 2><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->indptr, ctx->indices, (const T *)ctx->vals,
                                                                         nullptr, ctx->ldw, Ht, ctx->ldh, Wn, nullptr, ctx->n,
-                                                                        nullptr, nullptr);
+                                                                        nullptr, nullptr, g0);
   ctx->n_launch++;
   KL_CUDA(cudaGetLastError());
   return KLNMF_OK;
@@ -730,12 +737,12 @@ int run_scatter(klnmf_ctx *ctx, const T *Wn) {
 }
 
 template <typename T>
-int dispatch_rows(klnmf_ctx *ctx, int mode, const T *W, T *Wn, int q_order) {
+int dispatch_rows(klnmf_ctx *ctx, int mode, const T *W, T *Wn, int q_order, const T *g0) {
   const int64_t kp = ctx->ldw;
-  if (kp <= 128) return run_rows<T, 1>(ctx, mode, W, Wn, q_order);
-  if (kp <= 256) return run_rows<T, 2>(ctx, mode, W, Wn, q_order);
-  if (kp <= 512) return run_rows<T, 4>(ctx, mode, W, Wn, q_order);
-  if (kp <= 1024) return run_rows<T, 8>(ctx, mode, W, Wn, q_order);
+  if (kp <= 128) return run_rows<T, 1>(ctx, mode, W, Wn, q_order, g0);
+  if (kp <= 256) return run_rows<T, 2>(ctx, mode, W, Wn, q_order, g0);
+  if (kp <= 512) return run_rows<T, 4>(ctx, mode, W, Wn, q_order, g0);
+  if (kp <= 1024) return run_rows<T, 8>(ctx, mode, W, Wn, q_order, g0);
   set_error("sparse path supports n_components <= 1024 (got %lld)", (long long)ctx->k);
   return KLNMF_EINVAL;
 }
@@ -754,10 +761,12 @@ int dispatch_scatter(klnmf_ctx *ctx, const T *Wn) {
 
 // Pass 1 of the sparse iteration (SDDMM -> ratio -> objective -> SpMM -> W update), or with
 // only_error just the objective terms.
-int sparse_rows(klnmf_ctx *ctx, int mode, int q_order) {
+int sparse_rows(klnmf_ctx *ctx, int mode, int q_order, const void *g0) {
   const int cur = ctx->cur;
-  return ctx->es == 8 ? dispatch_rows<double>(ctx, mode, (const double *)ctx->W[cur], (double *)ctx->W[cur ^ 1], q_order)
-                      : dispatch_rows<float>(ctx, mode, (const float *)ctx->W[cur], (float *)ctx->W[cur ^ 1], q_order);
+  return ctx->es == 8 ? dispatch_rows<double>(ctx, mode, (const double *)ctx->W[cur], (double *)ctx->W[cur ^ 1], q_order,
+                                              (const double *)g0)
+                      : dispatch_rows<float>(ctx, mode, (const float *)ctx->W[cur], (float *)ctx->W[cur ^ 1], q_order,
+                                             (const float *)g0);
 }
 
 // Pass 2: dictionary numerator N^T[j,:] += q W'[i,:] over the stored non-zeros.
@@ -767,9 +776,9 @@ int sparse_scatter(klnmf_ctx *ctx, bool use_current_w) {
                       : dispatch_scatter<float>(ctx, (const float *)ctx->W[w]);
 }
 
-int sparse_init_w(klnmf_ctx *ctx) {
-  return ctx->es == 8 ? dispatch_rows<double>(ctx, 2, nullptr, (double *)ctx->W[ctx->cur], 0)
-                      : dispatch_rows<float>(ctx, 2, nullptr, (float *)ctx->W[ctx->cur], 0);
+int sparse_init_w(klnmf_ctx *ctx, const void *g0) {
+  return ctx->es == 8 ? dispatch_rows<double>(ctx, 2, nullptr, (double *)ctx->W[ctx->cur], 0, (const double *)g0)
+                      : dispatch_rows<float>(ctx, 2, nullptr, (float *)ctx->W[ctx->cur], 0, (const float *)g0);
 }
 
 void sparse_release_pattern(klnmf_ctx *ctx) {

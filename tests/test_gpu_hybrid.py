@@ -1,0 +1,125 @@
+"""-m gpu: hybrid stacks -- the dense modalities of a mixed stack kept dense and run through the contraction
+engine (tcgen05 / DMMA), the CSR modality through the sparse passes, one coefficient matrix and one dictionary
+normaliser over both (api.cu: HybridSide).  The answer is the reference's for its all-sparse stack (learner.py:53-56,
+array_utils.py:5-9, nmf.py:52-70): zeros of a dense block carry no ratio.
+"""
+import os
+
+import numpy as np
+import pytest
+import scipy.sparse as sp
+
+from multimodal_b200 import _native
+from multimodal_b200.learner import MultimodalLearner
+from multimodal_b200.lib.array_utils import MixedBlocks
+from multimodal_b200.lib.nmf import KLdivNMF
+from oracle import cases
+from oracle import klnmf_oracle as O
+
+pytestmark = pytest.mark.gpu
+
+# the dense block multiplies in the mode's one-pass form (tcgen05 kind::tf32 on plain FP32 operands, truncated by the
+# tensor core): stated = about 3 x the worst value measured (profiles/r2_parity_measured.json)
+TOL = {"fp64": 1e-12, "tf32r": 2e-3, "tf32": 2e-3}          # measured: 1.2e-15; W0 6.3e-4, W 3.7e-4, H 7.9e-5, dico 1.1e-4
+TOL_KL = {"fp64": 1e-12, "tf32r": 1e-3, "tf32": 1e-3}       # measured 3.1e-4
+
+
+@pytest.fixture
+def hybrid_on():
+    old = os.environ.get("KLNMF_HYBRID")
+    os.environ["KLNMF_HYBRID"] = "1"
+    yield
+    if old is None:
+        del os.environ["KLNMF_HYBRID"]
+    else:
+        os.environ["KLNMF_HYBRID"] = old
+
+
+def modalities(n, seed, f_motion=96, f_sound=400, f_image=70):
+    rs = np.random.RandomState(seed)
+    motion = rs.dirichlet(0.1 * np.ones(f_motion), n)
+    motion[motion < 1e-3] = 0.0                                   # real zeros in the dense modality
+    motion[7 % n, :] = 0.0                                        # and an all-zero row of it
+    sound = sp.random(n, f_sound, density=0.05, random_state=rs, format='csr')
+    sound.data = np.ceil(5 * sound.data)
+    sound.data[::17] = 0.0                                        # explicit zeros in the CSR modality
+    image = rs.random_sample((n, f_image)).astype(np.float32)
+    coefs = [1. / np.mean(np.sum(motion, axis=1)), 1. / np.mean(np.asarray(sound.sum(axis=1))), np.float32(0.5)]
+    return [motion, sound, image], coefs
+
+
+@pytest.mark.parametrize("mode", ["fp64", "tf32r", "tf32"])
+def test_hybrid_engine_against_the_oracle(hybrid_on, within, mode):
+    """The engine level: W0, ten fit iterations, the objective history and the objective after, against the oracle on
+    the reference's all-sparse stack; dense - CSR - dense block order, so the dictionary is scattered over both parts."""
+    n, k = 300, 24
+    mats, coefs = modalities(n, 31)
+    V = sp.hstack([c * m for m, c in zip(mats, coefs)]).tocsr()
+    V.eliminate_zeros()
+    f = V.shape[1]
+    np.random.seed(4)
+    H0 = O.init_dictionary(k, f)
+    W_ref, H_ref, errs_ref, _ = O.fit_transform(V.copy(), k=k, max_iter=10, tol=0, H0=H0)
+    with _native.Engine(n, f, k, mode=mode) as e:
+        e.set_stacked_blocks(MixedBlocks(mats, coefs).canonical().blocks, coefs)
+        assert e.is_hybrid()
+        assert e.check_input() == (0, 0)
+        e.set_dictionary(H0)
+        within("H0_roundtrip", cases.rel_fro(e.get_dictionary(), H0) + 1e-300, 1e-12 if mode == "fp64" else 1e-7)
+        e.init_coefficients()
+        within("W0", cases.rel_fro(e.get_coefficients(), V.dot(H0.T)), TOL[mode])
+        errs, n_iter = e.run(10, 0.0, True)
+        W, H = e.get_coefficients(), e.get_dictionary()
+        after = e.error()
+    assert n_iter == 10 and len(errs) == 10
+    np.testing.assert_allclose(H.sum(axis=1), 1.0, rtol=1e-5)
+    within("W", cases.rel_fro(W, W_ref), TOL[mode])
+    within("H", cases.rel_fro(H, H_ref), TOL[mode])
+    within("objective", float(np.max(np.abs(np.asarray(errs) - errs_ref) / np.abs(errs_ref))), TOL_KL[mode])
+    within("objective_after", abs(after - O.error(V, W_ref, H_ref)) / O.error(V, W_ref, H_ref), TOL_KL[mode])
+
+
+@pytest.mark.parametrize("mode", ["fp64", "tf32r"])
+def test_hybrid_learner_train_and_reconstruct(hybrid_on, within, mode):
+    """Through the drop-in API: MultimodalLearner.train on three modalities, coefficients of test samples from two of
+    them (a dense + CSR sub-stack: hybrid again) and from the CSR one alone, modality to modality."""
+    mats, coefs = modalities(260, 32)
+    mods, dims = ['motion', 'sound', 'image'], [m.shape[1] for m in mats]
+    lr = MultimodalLearner(mods, dims, coefs, 9, mode=mode)
+    assert isinstance(lr.stack_data(mods, mats), MixedBlocks)
+    np.random.seed(5)
+    lr.train(mats, 10)
+    ref = O.Learner(mods, dims, coefs, 9)
+    np.random.seed(5)
+    ref.train([mats[0], mats[1].copy(), mats[2]], 10)
+    within("dico", cases.rel_fro(lr.dico, ref.dico), TOL[mode])
+    test = [mats[0][:50], mats[1][:50]]
+    # the same dictionary on both sides: what is compared is the transform
+    ref.dico = np.array(lr.dico)
+    internal = lr.reconstruct_internal_multi(['motion', 'sound'], test, 10)
+    within("internal", cases.rel_fro(internal, ref.reconstruct_internal_multi(['motion', 'sound'], test, 10)), TOL[mode])
+    out = lr.modalities_to_modalities(['motion', 'sound'], ['image'], test, 10)
+    out_ref = ref.modalities_to_modalities(['motion', 'sound'], ['image'], test, 10)
+    within("to_image", cases.rel_fro(out[0], out_ref[0]), TOL[mode])
+    with pytest.raises(ValueError, match="Negative values"):
+        bad = mats[0].copy()
+        bad[3, 3] = -0.5
+        lr.train([bad, mats[1], mats[2]], 2)
+
+
+def test_hybrid_is_off_below_the_width_threshold_and_in_tf32x3(within):
+    """Default threshold: 1024 dense columns; tf32x3 keeps the all-CSR stack (FP32 FMA: its FP32-grade promise)."""
+    mats, coefs = modalities(64, 33)
+    blocks = MixedBlocks(mats, coefs).canonical().blocks
+    f = sum(m.shape[1] for m in mats)
+    with _native.Engine(64, f, 5, mode="tf32r") as e:
+        e.set_stacked_blocks(blocks, coefs)
+        assert not e.is_hybrid()
+    with _native.Engine(64, f, 5, mode="tf32r") as e:
+        e.set_hybrid_min_cols(100)
+        e.set_stacked_blocks(blocks, coefs)
+        assert e.is_hybrid()
+    with _native.Engine(64, f, 5, mode="tf32x3") as e:
+        e.set_hybrid_min_cols(100)
+        e.set_stacked_blocks(blocks, coefs)
+        assert not e.is_hybrid()

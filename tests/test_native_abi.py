@@ -22,7 +22,7 @@ def test_library_loads_and_exports_header_symbols():
     assert len(names) >= 30
     for n in names:
         assert hasattr(lib, n), "libklnmf.so lacks %s declared in include/klnmf.h" % n
-    assert lib.klnmf_abi_version() == _native.ABI_VERSION == 2
+    assert lib.klnmf_abi_version() == _native.ABI_VERSION == 3
 
 
 def test_python_prototypes_cover_the_header():
