@@ -837,7 +837,7 @@ int klnmf_set_stacked_blocks_host(klnmf_ctx *ctx, int n_blocks, const klnmf_bloc
     total += blocks[b].cols;
   }
   const char *he = getenv("KLNMF_HYBRID");
-  const int64_t min_cols = he ? (atoi(he) == 0 ? 0 : 1) : ctx->hybrid_min_cols;
+  const int64_t min_cols = ctx->hybrid_min_cols == 0 ? 0 : (he ? (atoi(he) == 0 ? 0 : 1) : ctx->hybrid_min_cols);   // an explicit 0 wins
   const int64_t ldd = round_up(fd, 32);
   const bool hybrid = min_cols > 0 && fd >= min_cols && n_dense > 0 && n_csr > 0 && fs > 0 && ctx->n > 0 && total == ctx->f &&
                       !ctx->W[0] && !ctx->comm && ctx->world == 1 && ctx->mode != KLNMF_MODE_TF32X3 && !ctx->debug_simt &&

@@ -158,6 +158,8 @@ class DeviceGroup(object):
             r0, r1 = bounds[r], bounds[r + 1]
             eng = _native.Engine(r1 - r0, X.shape[1], k, mode=self.mode, device=self.devices[r])
             try:
+                if world > 1:
+                    eng.set_hybrid_min_cols(0)                 # hybrid (dense + CSR) stacks are single-GPU: all-CSR shards
                 set_data(eng, _rows(X, r0, r1))
                 flags[r] = eng.check_input()
                 gate.wait()                                    # every shard validated before anybody iterates
