@@ -561,8 +561,7 @@ int hybrid_dense_half(klnmf_ctx *ctx, bool only_error) {
 }
 // N_d += W'^T.Q_d with the updated coefficients Wn (stale ratio, new W: nmf.py:345-349)
 int hybrid_dense_numerator(klnmf_ctx *ctx, const void *Wn) {
-  HybridSide *hy = (HybridSide *)ctx->hyb;
-  KL_TRY(launch_zero(ctx, hy->num, ctx->k * hy->ld * (int64_t)ctx->es));
+  HybridSide *hy = (HybridSide *)ctx->hyb;        // (hy->num was zeroed at the top of the iteration)
   GemmDesc m{};
   m.M = ctx->k; m.N = hy->fd; m.K = ctx->n;
   m.A = Wn; m.a_sm = 1; m.a_sk = ctx->ldw;
@@ -827,8 +826,9 @@ int klnmf_set_stacked_blocks_host(klnmf_ctx *ctx, int n_blocks, const klnmf_bloc
   KL_TRY(kind_guard(ctx, true));
   release_data(ctx);
   // Hybrid form (HybridSide above): the dense blocks stay dense when they are wide enough to pay for their contractions,
-  // the mode multiplies in one pass, the context is not part of a multi-GPU job, has no state yet, and one ratio panel
-  // n x fd fits the scratch limit.  hybrid_min_cols = 0 never, KLNMF_HYBRID=0 never, =1 whenever possible.
+  // the mode multiplies in one pass, the context has no state yet, and one ratio panel n x fd fits the scratch limit.
+  // hybrid_min_cols = 0 never, KLNMF_HYBRID=0 never, =1 whenever possible.  (The shards of a multi-GPU fit must all take
+  // the same form: distributed.DeviceGroup decides it once for all of them.)
   int64_t fd = 0, fs = 0, total = 0;
   int n_dense = 0, n_csr = 0;
   for (int b = 0; b < n_blocks; b++) {
@@ -839,9 +839,9 @@ int klnmf_set_stacked_blocks_host(klnmf_ctx *ctx, int n_blocks, const klnmf_bloc
   const char *he = getenv("KLNMF_HYBRID");
   const int64_t min_cols = ctx->hybrid_min_cols == 0 ? 0 : (he ? (atoi(he) == 0 ? 0 : 1) : ctx->hybrid_min_cols);   // an explicit 0 wins
   const int64_t ldd = round_up(fd, 32);
-  const bool hybrid = min_cols > 0 && fd >= min_cols && n_dense > 0 && n_csr > 0 && fs > 0 && ctx->n > 0 && total == ctx->f &&
-                      !ctx->W[0] && !ctx->comm && ctx->world == 1 && ctx->mode != KLNMF_MODE_TF32X3 && !ctx->debug_simt &&
-                      round_up(ctx->n, 128) * ldd * (int64_t)ctx->es <= ctx->scratch_limit;
+  const bool hybrid = min_cols > 0 && fd >= min_cols && n_dense > 0 && n_csr > 0 && fs > 0 && total == ctx->f &&
+                      !ctx->W[0] && ctx->mode != KLNMF_MODE_TF32X3 && !ctx->debug_simt &&
+                      round_up(ctx->n > 0 ? ctx->n : 1, 128) * ldd * (int64_t)ctx->es <= ctx->scratch_limit;
   if (!hybrid) {
     KL_TRY(stack_blocks_to_csr(ctx, n_blocks, blocks));
     KL_TRY(dmalloc(&ctx->qnz, ctx->nnz * ctx->es));
@@ -1171,6 +1171,10 @@ int klnmf_run_resume(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, doub
     int r = KLNMF_OK;
     ctx->num_reduced = false;
     if (fit) r = launch_zero(ctx, ctx->num, ctx->num_bytes);
+    if (fit && r == KLNMF_OK && ctx->hyb) {
+      HybridSide *hy = (HybridSide *)ctx->hyb;
+      r = launch_zero(ctx, hy->num, ctx->k * hy->ld * (int64_t)ctx->es);
+    }
     if (r == KLNMF_OK && ctx->sparse && ctx->n > 0) {
       HybridSide *hy = (HybridSide *)ctx->hyb;
       {
@@ -1193,6 +1197,10 @@ int klnmf_run_resume(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, doub
       if (r == KLNMF_OK) r = nccl_allreduce_sum_f64(ctx, ctx->dred, 2 + ctx->k);
       if (r == KLNMF_OK && fit && !ctx->num_reduced)     // (a shard without rows, the sparse path: the whole buffer at once)
         r = nccl_allreduce_sum(ctx, ctx->num, num_elems(ctx), ctx->es);
+      if (r == KLNMF_OK && fit && ctx->hyb) {           // hybrid stack: the dense block's numerator travels in the same group
+        HybridSide *hy = (HybridSide *)ctx->hyb;
+        r = nccl_allreduce_sum(ctx, hy->num, ctx->k * hy->ld, ctx->es);
+      }
       const int r_end = nccl_group_end();
       if (r == KLNMF_OK) r = r_end;
       if (r == KLNMF_OK && ctx->num_reduced && cudaStreamWaitEvent(ctx->stream, ctx->comm_done, 0) != cudaSuccess) {
@@ -1422,7 +1430,6 @@ int klnmf_nccl_unique_id(void *id128) {
 }
 int klnmf_comm_init(klnmf_ctx *ctx, const void *id128, int rank, int world) {
   KL_CHECK(ctx && id128, KLNMF_EINVAL, "comm_init: NULL argument");
-  KL_CHECK(!ctx->hyb || world == 1, KLNMF_ESTATE, "comm_init: a hybrid (dense + CSR) stack is single-GPU; create the communicator before the data");
   return nccl_comm_init(ctx, id128, rank, world);
 }
 int klnmf_comm_create(void **comm, int device, const void *id128, int rank, int world) {
@@ -1434,7 +1441,6 @@ int klnmf_comm_create(void **comm, int device, const void *id128, int rank, int 
 }
 int klnmf_comm_attach(klnmf_ctx *ctx, void *comm, int rank, int world) {
   KL_CHECK(ctx && comm && world >= 1 && rank >= 0 && rank < world, KLNMF_EINVAL, "comm_attach: bad argument");
-  KL_CHECK(!ctx->hyb || world == 1, KLNMF_ESTATE, "comm_attach: a hybrid (dense + CSR) stack is single-GPU; attach the communicator before the data");
   nccl_comm_destroy(ctx);          // an owned communicator of an earlier klnmf_comm_init
   ctx->comm = comm;
   ctx->comm_owned = false;

@@ -70,6 +70,27 @@ def draw_shared_dictionary(k, f):
 
 
 # ---- communicator caches -------------------------------------------------------------------------------------
+def _hybrid_for_all_shards(X, bounds, mode, min_cols=1024, scratch=16 << 30):
+    """A mixed (dense + CSR) stack on several GPUs: its shards must ALL keep the dense modalities dense (hybrid stack,
+    klnmf_set_stacked_blocks_host) or all build the CSR stack -- their numerators are summed element by element.  The
+    library decides per context (dense width, arithmetic mode, one ratio panel within the scratch limit); here the
+    same rule is applied once to the LARGEST shard.  None: X is not a mixed stack."""
+    import os
+    import scipy.sparse as sp
+    from .lib.array_utils import MixedBlocks
+    if not isinstance(X, MixedBlocks):
+        return None
+    env = os.environ.get("KLNMF_HYBRID")
+    if env is not None:
+        min_cols = 0 if int(env) == 0 else 1
+    fd = sum(b.shape[1] for b in X.blocks if not sp.issparse(b))
+    rows = max(bounds[r + 1] - bounds[r] for r in range(len(bounds) - 1))
+    es = 8 if _native.resolve_mode(mode) == _native.resolve_mode("fp64") else 4
+    panel = -(-max(rows, 1) // 128) * 128 * (-(-fd // 32) * 32) * es
+    return bool(min_cols > 0 and fd >= min_cols and _native.resolve_mode(mode) != _native.resolve_mode("tf32x3") and
+                panel <= scratch)
+
+
 _RANK_COMM = {}      # torchrun: (device, rank, world) -> _native.Comm
 _GROUP_COMMS = {}    # one process: tuple(devices) -> [_native.Comm per device]
 _CACHE_LOCK = threading.Lock()
@@ -153,13 +174,14 @@ class DeviceGroup(object):
         flags = [None] * world
         results = [None] * world
         gate = threading.Barrier(world)
+        hybrid = _hybrid_for_all_shards(X, bounds, self.mode)
 
         def shard(r):
             r0, r1 = bounds[r], bounds[r + 1]
             eng = _native.Engine(r1 - r0, X.shape[1], k, mode=self.mode, device=self.devices[r])
             try:
-                if world > 1:
-                    eng.set_hybrid_min_cols(0)                 # hybrid (dense + CSR) stacks are single-GPU: all-CSR shards
+                if world > 1 and hybrid is not None:
+                    eng.set_hybrid_min_cols(1 if hybrid else 0)   # every shard takes the same form of a mixed stack
                 set_data(eng, _rows(X, r0, r1))
                 flags[r] = eng.check_input()
                 gate.wait()                                    # every shard validated before anybody iterates

@@ -128,3 +128,33 @@ def test_learner_trains_over_two_devices(golden, within):
     np.random.seed(4)
     ref.train(mats, 10)
     within("dico_dense_blocks", cases.rel_fro(lr3.dico, ref.dico), 8e-4)
+
+
+@pytest.mark.parametrize("mode", ["fp64", "tf32r"])
+def test_sharded_hybrid_stack_through_the_learner(within, monkeypatch, mode):
+    """A mixed (dense + CSR) stack on two GPUs in its hybrid form: every shard keeps the dense modalities
+    dense (distributed._hybrid_for_all_shards decides once for all), the numerators of both parts are all-reduced in
+    one NCCL group; against the oracle's learner on the reference's all-sparse stack (learner.py:31-41, 53-56)."""
+    monkeypatch.setenv("KLNMF_HYBRID", "1")
+    rs = np.random.RandomState(41)
+    n = 301
+    motion = rs.dirichlet(0.1 * np.ones(96), n)
+    motion[motion < 1e-3] = 0.0
+    sound = sp.random(n, 400, density=0.05, random_state=rs, format='csr')
+    sound.data = np.ceil(5 * sound.data)
+    image = rs.random_sample((n, 70)).astype(np.float32)
+    mats = [motion, sound, image]
+    mods, dims = ['motion', 'sound', 'image'], [96, 400, 70]
+    coefs = [1. / np.mean(np.sum(motion, axis=1)), 1. / np.mean(np.asarray(sound.sum(axis=1))), np.float32(0.5)]
+    ref = O.Learner(mods, dims, coefs, 9)
+    np.random.seed(5)
+    ref.train([motion, sound.copy(), image], 10)
+    out = {}
+    for dev in (0, DEVICES):
+        lr = MultimodalLearner(mods, dims, coefs, 9, mode=mode, device=dev)
+        np.random.seed(5)
+        lr.train(mats, 10)
+        out[str(dev)] = np.array(lr.dico)
+    tol = 1e-12 if mode == "fp64" else 2e-3                       # tests/test_gpu_hybrid.py
+    within("dico", cases.rel_fro(out[str(DEVICES)], ref.dico), tol)
+    within("dico_vs_single", cases.rel_fro(out[str(DEVICES)], out["0"]) + 1e-300, 1e-12 if mode == "fp64" else 2e-4)
