@@ -107,7 +107,7 @@ int klnmf_set_stacked_blocks_host(klnmf_ctx *ctx, int n_blocks, const klnmf_bloc
  * through the contraction engine (tcgen05 / DMMA), the CSR blocks through the sparse passes, one coefficient matrix and
  * one row normaliser of the dictionary over both.  The results are the reference's for its all-sparse stack: zeros of
  * a dense block carry no ratio.  One-pass arithmetic for the dense block (TF32, TF32R, FP64 modes; TF32X3 keeps the
- * all-CSR stack), n x dense-columns within the scratch limit; anything else builds the CSR stack.  The shards of a
+ * all-CSR stack); anything else builds the CSR stack.  The shards of a
  * multi-GPU fit must all take the same form (the caller decides once: distributed.DeviceGroup).
  * Call before the data.  KLNMF_HYBRID=0 / 1 in the environment overrides: never / whenever possible. */
 int klnmf_set_hybrid_min_cols(klnmf_ctx *ctx, int64_t cols);

@@ -519,6 +519,7 @@ int dense_iteration(klnmf_ctx *ctx, int fit, bool only_error, Profiler *prof, bo
 // ------------------------------------------------------------------------------------------------------------------
 struct HybridSide {
   int64_t f_total = 0, fd = 0, ld = 0;       // ld = fd rounded up to 32: pitch of X, Q, H, num
+  int64_t panel_rows = 0;                    // rows of the ratio panel Q (the samples are walked in panels of that many)
   void *X = nullptr, *Q = nullptr, *G = nullptr, *num = nullptr;
   void *H[2] = {nullptr, nullptr};
   double *total = nullptr;                   // k doubles: the joint normaliser
@@ -536,38 +537,58 @@ void release_hybrid(klnmf_ctx *ctx) {
   ctx->hyb = nullptr;
 }
 
-// ratio + objective of the dense block, its ratio masked at the structural zeros, and (unless only the objective is
-// wanted) G_d = Q_d.H_d^T into hy->G
-int hybrid_dense_half(klnmf_ctx *ctx, bool only_error) {
+// Rows [r0, r0 + rows) (one panel): ratio + objective of the dense block, its ratio masked at the structural zeros, and
+// (unless only the objective is wanted) G_d = Q_d.H_d^T into the rows of hy->G
+int hybrid_dense_half(klnmf_ctx *ctx, bool only_error, int64_t r0, int64_t rows) {
   HybridSide *hy = (HybridSide *)ctx->hyb;
   const int cur = ctx->cur, hc = ctx->hcur;
+  const int64_t es = ctx->es;
   const int *stop = only_error ? nullptr : ctx->flags + FL_STOP;
+  const char *Xp = (const char *)hy->X + r0 * hy->ld * es;
   GemmDesc d{};
-  d.M = ctx->n; d.N = hy->fd; d.K = ctx->k;
-  d.A = ctx->W[cur]; d.a_sm = ctx->ldw; d.a_sk = 1;
+  d.M = rows; d.N = hy->fd; d.K = ctx->k;
+  d.A = (const char *)ctx->W[cur] + r0 * ctx->ldw * es; d.a_sm = ctx->ldw; d.a_sk = 1;
   d.B = hy->H[hc]; d.b_sk = hy->ld; d.b_sn = 1;
   d.out = hy->Q; d.ldo = hy->ld;
-  d.aux = hy->X; d.ldaux = hy->ld;
+  d.aux = Xp; d.ldaux = hy->ld;
   d.kl = ctx->dred; d.stop = stop; d.only_kl = only_error ? 1 : 0;
   KL_TRY(dense_gemm(ctx, EPI_RATIO, d));
   if (only_error) return KLNMF_OK;
-  KL_TRY(launch_mask_ratio(ctx, hy->Q, hy->ld, hy->X, hy->ld, ctx->n, hy->fd, stop));
+  KL_TRY(launch_mask_ratio(ctx, hy->Q, hy->ld, Xp, hy->ld, rows, hy->fd, stop));
   GemmDesc c{};
-  c.M = ctx->n; c.N = ctx->k; c.K = hy->fd;
+  c.M = rows; c.N = ctx->k; c.K = hy->fd;
   c.A = hy->Q; c.a_sm = hy->ld; c.a_sk = 1;
   c.B = hy->H[hc]; c.b_sk = 1; c.b_sn = hy->ld;
-  c.out = hy->G; c.ldo = ctx->ldw; c.stop = stop;
+  c.out = (char *)hy->G + r0 * ctx->ldw * es; c.ldo = ctx->ldw; c.stop = stop;
   return dense_gemm(ctx, EPI_STORE, c);
 }
-// N_d += W'^T.Q_d with the updated coefficients Wn (stale ratio, new W: nmf.py:345-349)
-int hybrid_dense_numerator(klnmf_ctx *ctx, const void *Wn) {
+// N_d += W'^T.Q_d over the panel's rows, with the updated coefficients (stale ratio, new W: nmf.py:345-349)
+int hybrid_dense_numerator(klnmf_ctx *ctx, int64_t r0, int64_t rows) {
   HybridSide *hy = (HybridSide *)ctx->hyb;        // (hy->num was zeroed at the top of the iteration)
   GemmDesc m{};
-  m.M = ctx->k; m.N = hy->fd; m.K = ctx->n;
-  m.A = Wn; m.a_sm = 1; m.a_sk = ctx->ldw;
+  m.M = ctx->k; m.N = hy->fd; m.K = rows;
+  m.A = (const char *)ctx->W[ctx->cur ^ 1] + r0 * ctx->ldw * (int64_t)ctx->es; m.a_sm = 1; m.a_sk = ctx->ldw;
   m.B = hy->Q; m.b_sk = hy->ld; m.b_sn = 1;
   m.out = hy->num; m.ldo = hy->ld; m.stop = ctx->flags + FL_STOP;
   return dense_gemm(ctx, EPI_ACC, m);
+}
+// The coefficient half-step of a hybrid stack (and, fitting, the dense block's numerator), panel by panel: the ratio
+// panel of the dense block lives for one panel only, so its numerator is taken before the next panel overwrites it.
+int hybrid_rows_passes(klnmf_ctx *ctx, int fit, Profiler *prof) {
+  HybridSide *hy = (HybridSide *)ctx->hyb;
+  for (int64_t r0 = 0; r0 < ctx->n; r0 += hy->panel_rows) {
+    const int64_t rows = ctx->n - r0 < hy->panel_rows ? ctx->n - r0 : hy->panel_rows;
+    {
+      PhaseTimer t(ctx, prof, PH_RATIO);
+      KL_TRY(hybrid_dense_half(ctx, false, r0, rows));
+      KL_TRY(sparse_rows(ctx, 0, fit ? 2 : 0, hy->G, r0, rows));
+    }
+    if (fit) {
+      PhaseTimer t(ctx, prof, PH_NUM);
+      KL_TRY(hybrid_dense_numerator(ctx, r0, rows));
+    }
+  }
+  return KLNMF_OK;
 }
 
 int reset_reduction(klnmf_ctx *ctx) {
@@ -826,8 +847,7 @@ int klnmf_set_stacked_blocks_host(klnmf_ctx *ctx, int n_blocks, const klnmf_bloc
   KL_TRY(kind_guard(ctx, true));
   release_data(ctx);
   // Hybrid form (HybridSide above): the dense blocks stay dense when they are wide enough to pay for their contractions,
-  // the mode multiplies in one pass, the context has no state yet, and one ratio panel n x fd fits the scratch limit.
-  // hybrid_min_cols = 0 never, KLNMF_HYBRID=0 never, =1 whenever possible.  (The shards of a multi-GPU fit must all take
+  // the mode multiplies in one pass and the context has no state yet.  hybrid_min_cols = 0 never, KLNMF_HYBRID=0 never, =1 whenever possible.  (The shards of a multi-GPU fit must all take
   // the same form: distributed.DeviceGroup decides it once for all of them.)
   int64_t fd = 0, fs = 0, total = 0;
   int n_dense = 0, n_csr = 0;
@@ -840,8 +860,7 @@ int klnmf_set_stacked_blocks_host(klnmf_ctx *ctx, int n_blocks, const klnmf_bloc
   const int64_t min_cols = ctx->hybrid_min_cols == 0 ? 0 : (he ? (atoi(he) == 0 ? 0 : 1) : ctx->hybrid_min_cols);   // an explicit 0 wins
   const int64_t ldd = round_up(fd, 32);
   const bool hybrid = min_cols > 0 && fd >= min_cols && n_dense > 0 && n_csr > 0 && fs > 0 && total == ctx->f &&
-                      !ctx->W[0] && ctx->mode != KLNMF_MODE_TF32X3 && !ctx->debug_simt &&
-                      round_up(ctx->n > 0 ? ctx->n : 1, 128) * ldd * (int64_t)ctx->es <= ctx->scratch_limit;
+                      !ctx->W[0] && ctx->mode != KLNMF_MODE_TF32X3 && !ctx->debug_simt;
   if (!hybrid) {
     KL_TRY(stack_blocks_to_csr(ctx, n_blocks, blocks));
     KL_TRY(dmalloc(&ctx->qnz, ctx->nnz * ctx->es));
@@ -886,7 +905,13 @@ int klnmf_set_stacked_blocks_host(klnmf_ctx *ctx, int n_blocks, const klnmf_bloc
       (rc = launch_sum_vals(ctx)) != KLNMF_OK)
     return fail(rc);
   const int64_t hb = ctx->k * ldd * es;
-  if ((rc = dmalloc(&hy->Q, round_up(ctx->n, 128) * ldd * es)) != KLNMF_OK || (rc = dmalloc(&hy->G, ctx->n * ctx->ldw * es)) != KLNMF_OK ||
+  {   // the ratio panel: as many rows as the scratch limit allows (like the dense path's panel, ensure_state)
+    int64_t pr = ctx->scratch_limit / (ldd * es) / 128 * 128;
+    if (pr < 128) pr = 128;
+    if (pr > round_up(ctx->n > 0 ? ctx->n : 1, 128)) pr = round_up(ctx->n > 0 ? ctx->n : 1, 128);
+    hy->panel_rows = pr;
+  }
+  if ((rc = dmalloc(&hy->Q, hy->panel_rows * ldd * es)) != KLNMF_OK || (rc = dmalloc(&hy->G, ctx->n * ctx->ldw * es)) != KLNMF_OK ||
       (rc = dmalloc(&hy->num, hb)) != KLNMF_OK || (rc = dmalloc(&hy->H[0], hb)) != KLNMF_OK ||
       (rc = dmalloc(&hy->H[1], hb)) != KLNMF_OK || (rc = dmalloc((void **)&hy->total, (ctx->k + 1) * 8)) != KLNMF_OK)
     return fail(rc);
@@ -1039,12 +1064,14 @@ int klnmf_init_coefficients(klnmf_ctx *ctx) {
   if (ctx->sparse) {
     if (ctx->hyb) {   // W0 = X_d.H_d^T + X_s.H_s^T: the dense block's product first, the CSR pass starts from it
       HybridSide *hy = (HybridSide *)ctx->hyb;
-      GemmDesc c{};
-      c.M = ctx->n; c.N = ctx->k; c.K = hy->fd;
-      c.A = hy->X; c.a_sm = hy->ld; c.a_sk = 1;
-      c.B = hy->H[ctx->hcur]; c.b_sk = 1; c.b_sn = hy->ld;
-      c.out = hy->G; c.ldo = ctx->ldw;
-      KL_TRY(dense_gemm(ctx, EPI_STORE, c));
+      for (int64_t r0 = 0; r0 < ctx->n; r0 += hy->panel_rows) {
+        GemmDesc c{};
+        c.M = ctx->n - r0 < hy->panel_rows ? ctx->n - r0 : hy->panel_rows; c.N = ctx->k; c.K = hy->fd;
+        c.A = (const char *)hy->X + r0 * hy->ld * ctx->es; c.a_sm = hy->ld; c.a_sk = 1;
+        c.B = hy->H[ctx->hcur]; c.b_sk = 1; c.b_sn = hy->ld;
+        c.out = (char *)hy->G + r0 * ctx->ldw * ctx->es; c.ldo = ctx->ldw;
+        KL_TRY(dense_gemm(ctx, EPI_STORE, c));
+      }
       KL_TRY(sparse_init_w(ctx, hy->G));
     } else {
       KL_TRY(sparse_init_w(ctx));
@@ -1176,16 +1203,15 @@ int klnmf_run_resume(klnmf_ctx *ctx, int max_iter, double tol_abs, int fit, doub
       r = launch_zero(ctx, hy->num, ctx->k * hy->ld * (int64_t)ctx->es);
     }
     if (r == KLNMF_OK && ctx->sparse && ctx->n > 0) {
-      HybridSide *hy = (HybridSide *)ctx->hyb;
-      {
+      if (ctx->hyb) {
+        r = hybrid_rows_passes(ctx, fit, prof);
+      } else {
         PhaseTimer t(ctx, prof, PH_RATIO);
-        if (hy) r = hybrid_dense_half(ctx, false);
-        if (r == KLNMF_OK) r = sparse_rows(ctx, 0, fit ? 2 : 0, hy ? hy->G : nullptr);
+        r = sparse_rows(ctx, 0, fit ? 2 : 0);
       }
       if (r == KLNMF_OK && fit) {
         PhaseTimer t(ctx, prof, PH_NUM);
-        if (hy) r = hybrid_dense_numerator(ctx, ctx->W[ctx->cur ^ 1]);
-        if (r == KLNMF_OK) r = sparse_scatter(ctx, false);
+        r = sparse_scatter(ctx, false);
       }
     } else if (r == KLNMF_OK) {
       r = dense_iteration(ctx, fit, false, prof);
@@ -1290,7 +1316,11 @@ int klnmf_error(klnmf_ctx *ctx, double *out) {
   KL_TRY(reset_reduction(ctx));
   if (ctx->sparse) {
     if (ctx->n > 0) {
-      if (ctx->hyb) KL_TRY(hybrid_dense_half(ctx, true));
+      if (ctx->hyb) {
+        const HybridSide *hy = (const HybridSide *)ctx->hyb;
+        for (int64_t r0 = 0; r0 < ctx->n; r0 += hy->panel_rows)
+          KL_TRY(hybrid_dense_half(ctx, true, r0, ctx->n - r0 < hy->panel_rows ? ctx->n - r0 : hy->panel_rows));
+      }
       KL_TRY(sparse_rows(ctx, 1));
     }
   }

@@ -219,9 +219,10 @@ int l2_read_bench(int device, int64_t bytes, int iters, double *gbps);   // meas
 // ---- sparse path: sparse.cu ------------------------------------------------------------------------
 // mode: 0 full pass, 1 objective only, 3 SDDMM only.  q_order (mode 0): 0 the ratio is not kept (transform), 1 kept in
 // CSR order (the _Q hook), 2 kept in blocked-CSC order for the numerator pass (fit)
-int sparse_rows(klnmf_ctx *ctx, int mode, int q_order = 0, const void *g0 = nullptr);   // g0: n x ldw, what G starts from
+// g0: n x ldw, what G starts from; [r0, r0 + rows): a row range (rows < 0: all)
+int sparse_rows(klnmf_ctx *ctx, int mode, int q_order = 0, const void *g0 = nullptr, int64_t r0 = 0, int64_t rows = -1);
 int sparse_scatter(klnmf_ctx *ctx, bool use_current_w);
-int sparse_init_w(klnmf_ctx *ctx, const void *g0 = nullptr);
+int sparse_init_w(klnmf_ctx *ctx, const void *g0 = nullptr, int64_t r0 = 0, int64_t rows = -1);
 int sparse_fill_synthetic(klnmf_ctx *ctx, int64_t nnz_per_row, uint64_t seed);
 void sparse_release_pattern(klnmf_ctx *ctx);   // drop the blocked-CSC copy (the data changed)
 

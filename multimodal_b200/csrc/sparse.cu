@@ -622,43 +622,48 @@ inline bool use_bcsc(const klnmf_ctx *ctx) {
 // q_order (mode 0 only): 0 = the ratio is not kept (transform: 4 bytes per stored entry less to write), 1 / 2 = kept in
 // CSR order, for the _Q hook / for the numerator pass
 template <typename T, int VPL>
-int run_rows(klnmf_ctx *ctx, int mode, const T *W, T *Wn, int q_order, const T *g0) {
-  const int grid = (int)(ceil_div(ctx->n, WARPS) < (int64_t)ctx->sm_count * 8 ? ceil_div(ctx->n, WARPS)
-                                                                               : (int64_t)ctx->sm_count * 8);
+int run_rows(klnmf_ctx *ctx, int mode, const T *W, T *Wn, int q_order, const T *g0, int64_t r0, int64_t n) {
+  // the rows [r0, r0 + n) of the data (hybrid stacks walk the samples in panels): stored-entry positions are absolute,
+  // so a row range is the same kernels on offset row pointers
+  const int64_t *indptr = ctx->indptr + r0;
+  if (W) W += r0 * ctx->ldw;
+  if (Wn) Wn += r0 * ctx->ldw;
+  if (g0) g0 += r0 * ctx->ldw;
+  const int grid = (int)(ceil_div(n, WARPS) < (int64_t)ctx->sm_count * 8 ? ceil_div(n, WARPS) : (int64_t)ctx->sm_count * 8);
   const int *stop = ctx->flags + FL_STOP;
   const T *Ht = (const T *)ctx->H[ctx->hcur];
   static const bool generic_only = getenv("KLNMF_SPARSE_GENERIC") && atoi(getenv("KLNMF_SPARSE_GENERIC")) == 1;
   if (sizeof(T) == 4 && (mode == 0 || mode == 1) && !generic_only && ctx->ldw == 128 * VPL && ctx->ldh == ctx->ldw &&
       ctx->f * ctx->ldh < ((int64_t)1 << 32) && ctx->nnz < ((int64_t)1 << 32) - 64 &&
-      ctx->n + (int64_t)grid * WARPS < ((int64_t)1 << 32)) {
+      n + (int64_t)grid * WARPS < ((int64_t)1 << 32)) {
     if (mode == 0)
       sparse_rows_full_kernel<VPL, 0><<<grid, WARPS * 32, 0, ctx->stream>>>(
-          ctx->indptr, ctx->indices, (const float *)ctx->vals, (const float *)W, (const float *)Ht, (uint32_t)ctx->ldh,
-          (float *)Wn, q_order == 0 ? nullptr : (float *)ctx->qnz, ctx->n, ctx->dred, stop, (const float *)g0);
+          indptr, ctx->indices, (const float *)ctx->vals, (const float *)W, (const float *)Ht, (uint32_t)ctx->ldh,
+          (float *)Wn, q_order == 0 ? nullptr : (float *)ctx->qnz, n, ctx->dred, stop, (const float *)g0);
     else
       sparse_rows_full_kernel<VPL, 1><<<grid, WARPS * 32, 0, ctx->stream>>>(
-          ctx->indptr, ctx->indices, (const float *)ctx->vals, (const float *)W, (const float *)Ht, (uint32_t)ctx->ldh,
-          nullptr, nullptr, ctx->n, ctx->dred, nullptr, nullptr);
+          indptr, ctx->indices, (const float *)ctx->vals, (const float *)W, (const float *)Ht, (uint32_t)ctx->ldh,
+          nullptr, nullptr, n, ctx->dred, nullptr, nullptr);
     ctx->n_launch++;
     KL_CUDA(cudaGetLastError());
     return KLNMF_OK;
   }
   if (mode == 0)
-    sparse_rows_kernel<T, VPL, 0><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->indptr, ctx->indices, (const T *)ctx->vals, W,
+    sparse_rows_kernel<T, VPL, 0><<<grid, WARPS * 32, 0, ctx->stream>>>(indptr, ctx->indices, (const T *)ctx->vals, W,
                                                                         ctx->ldw, Ht, ctx->ldh, Wn,
-                                                                        q_order == 0 ? nullptr : (T *)ctx->qnz, ctx->n,
+                                                                        q_order == 0 ? nullptr : (T *)ctx->qnz, n,
                                                                         ctx->dred, stop, g0);
   else if (mode == 1)
-    sparse_rows_kernel<T, VPL, 1><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->indptr, ctx->indices, (const T *)ctx->vals, W,
-                                                                        ctx->ldw, Ht, ctx->ldh, nullptr, nullptr, ctx->n,
+    sparse_rows_kernel<T, VPL, 1><<<grid, WARPS * 32, 0, ctx->stream>>>(indptr, ctx->indices, (const T *)ctx->vals, W,
+                                                                        ctx->ldw, Ht, ctx->ldh, nullptr, nullptr, n,
                                                                         ctx->dred, nullptr, nullptr);
   else if (mode == 3)
-    sparse_rows_kernel<T, VPL, 3><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->indptr, ctx->indices, (const T *)ctx->vals, W,
-                                                                        ctx->ldw, Ht, ctx->ldh, nullptr, (T *)ctx->qnz, ctx->n,
+    sparse_rows_kernel<T, VPL, 3><<<grid, WARPS * 32, 0, ctx->stream>>>(indptr, ctx->indices, (const T *)ctx->vals, W,
+                                                                        ctx->ldw, Ht, ctx->ldh, nullptr, (T *)ctx->qnz, n,
                                                                         ctx->dred, nullptr, nullptr);
   else
-    sparse_rows_kernel<T, VPL, 2><<<grid, WARPS * 32, 0, ctx->stream>>>(ctx->indptr, ctx->indices, (const T *)ctx->vals,
-                                                                        nullptr, ctx->ldw, Ht, ctx->ldh, Wn, nullptr, ctx->n,
+    sparse_rows_kernel<T, VPL, 2><<<grid, WARPS * 32, 0, ctx->stream>>>(indptr, ctx->indices, (const T *)ctx->vals,
+                                                                        nullptr, ctx->ldw, Ht, ctx->ldh, Wn, nullptr, n,
                                                                         nullptr, nullptr, g0);
   ctx->n_launch++;
   KL_CUDA(cudaGetLastError());
@@ -737,12 +742,12 @@ int run_scatter(klnmf_ctx *ctx, const T *Wn) {
 }
 
 template <typename T>
-int dispatch_rows(klnmf_ctx *ctx, int mode, const T *W, T *Wn, int q_order, const T *g0) {
+int dispatch_rows(klnmf_ctx *ctx, int mode, const T *W, T *Wn, int q_order, const T *g0, int64_t r0, int64_t rows) {
   const int64_t kp = ctx->ldw;
-  if (kp <= 128) return run_rows<T, 1>(ctx, mode, W, Wn, q_order, g0);
-  if (kp <= 256) return run_rows<T, 2>(ctx, mode, W, Wn, q_order, g0);
-  if (kp <= 512) return run_rows<T, 4>(ctx, mode, W, Wn, q_order, g0);
-  if (kp <= 1024) return run_rows<T, 8>(ctx, mode, W, Wn, q_order, g0);
+  if (kp <= 128) return run_rows<T, 1>(ctx, mode, W, Wn, q_order, g0, r0, rows);
+  if (kp <= 256) return run_rows<T, 2>(ctx, mode, W, Wn, q_order, g0, r0, rows);
+  if (kp <= 512) return run_rows<T, 4>(ctx, mode, W, Wn, q_order, g0, r0, rows);
+  if (kp <= 1024) return run_rows<T, 8>(ctx, mode, W, Wn, q_order, g0, r0, rows);
   set_error("sparse path supports n_components <= 1024 (got %lld)", (long long)ctx->k);
   return KLNMF_EINVAL;
 }
@@ -761,12 +766,14 @@ int dispatch_scatter(klnmf_ctx *ctx, const T *Wn) {
 
 // Pass 1 of the sparse iteration (SDDMM -> ratio -> objective -> SpMM -> W update), or with
 // only_error just the objective terms.
-int sparse_rows(klnmf_ctx *ctx, int mode, int q_order, const void *g0) {
+int sparse_rows(klnmf_ctx *ctx, int mode, int q_order, const void *g0, int64_t r0, int64_t rows) {
   const int cur = ctx->cur;
+  if (rows < 0) { r0 = 0; rows = ctx->n; }
+  if (rows == 0) return KLNMF_OK;
   return ctx->es == 8 ? dispatch_rows<double>(ctx, mode, (const double *)ctx->W[cur], (double *)ctx->W[cur ^ 1], q_order,
-                                              (const double *)g0)
+                                              (const double *)g0, r0, rows)
                       : dispatch_rows<float>(ctx, mode, (const float *)ctx->W[cur], (float *)ctx->W[cur ^ 1], q_order,
-                                             (const float *)g0);
+                                             (const float *)g0, r0, rows);
 }
 
 // Pass 2: dictionary numerator N^T[j,:] += q W'[i,:] over the stored non-zeros.
@@ -776,9 +783,11 @@ int sparse_scatter(klnmf_ctx *ctx, bool use_current_w) {
                       : dispatch_scatter<float>(ctx, (const float *)ctx->W[w]);
 }
 
-int sparse_init_w(klnmf_ctx *ctx, const void *g0) {
-  return ctx->es == 8 ? dispatch_rows<double>(ctx, 2, nullptr, (double *)ctx->W[ctx->cur], 0, (const double *)g0)
-                      : dispatch_rows<float>(ctx, 2, nullptr, (float *)ctx->W[ctx->cur], 0, (const float *)g0);
+int sparse_init_w(klnmf_ctx *ctx, const void *g0, int64_t r0, int64_t rows) {
+  if (rows < 0) { r0 = 0; rows = ctx->n; }
+  if (rows == 0) return KLNMF_OK;
+  return ctx->es == 8 ? dispatch_rows<double>(ctx, 2, nullptr, (double *)ctx->W[ctx->cur], 0, (const double *)g0, r0, rows)
+                      : dispatch_rows<float>(ctx, 2, nullptr, (float *)ctx->W[ctx->cur], 0, (const float *)g0, r0, rows);
 }
 
 void sparse_release_pattern(klnmf_ctx *ctx) {

@@ -70,11 +70,11 @@ def draw_shared_dictionary(k, f):
 
 
 # ---- communicator caches -------------------------------------------------------------------------------------
-def _hybrid_for_all_shards(X, bounds, mode, min_cols=1024, scratch=16 << 30):
+def _hybrid_for_all_shards(X, bounds, mode, min_cols=1024):
     """A mixed (dense + CSR) stack on several GPUs: its shards must ALL keep the dense modalities dense (hybrid stack,
     klnmf_set_stacked_blocks_host) or all build the CSR stack -- their numerators are summed element by element.  The
-    library decides per context (dense width, arithmetic mode, one ratio panel within the scratch limit); here the
-    same rule is applied once to the LARGEST shard.  None: X is not a mixed stack."""
+    library decides per context (dense width, arithmetic mode); here the same rule is applied once for all shards.
+    None: X is not a mixed stack."""
     import os
     import scipy.sparse as sp
     from .lib.array_utils import MixedBlocks
@@ -84,11 +84,7 @@ def _hybrid_for_all_shards(X, bounds, mode, min_cols=1024, scratch=16 << 30):
     if env is not None:
         min_cols = 0 if int(env) == 0 else 1
     fd = sum(b.shape[1] for b in X.blocks if not sp.issparse(b))
-    rows = max(bounds[r + 1] - bounds[r] for r in range(len(bounds) - 1))
-    es = 8 if _native.resolve_mode(mode) == _native.resolve_mode("fp64") else 4
-    panel = -(-max(rows, 1) // 128) * 128 * (-(-fd // 32) * 32) * es
-    return bool(min_cols > 0 and fd >= min_cols and _native.resolve_mode(mode) != _native.resolve_mode("tf32x3") and
-                panel <= scratch)
+    return bool(min_cols > 0 and fd >= min_cols and _native.resolve_mode(mode) != _native.resolve_mode("tf32x3"))
 
 
 _RANK_COMM = {}      # torchrun: (device, rank, world) -> _native.Comm

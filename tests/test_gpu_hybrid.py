@@ -123,3 +123,33 @@ def test_hybrid_is_off_below_the_width_threshold_and_in_tf32x3(within):
         e.set_hybrid_min_cols(100)
         e.set_stacked_blocks(blocks, coefs)
         assert not e.is_hybrid()
+
+
+@pytest.mark.parametrize("mode", ["fp64", "tf32r"])
+def test_hybrid_walks_the_samples_in_panels(hybrid_on, within, mode):
+    """The ratio panel of the dense block is bounded by the scratch limit: with 128-row panels a 300-sample fit takes
+    three (the last one ragged); same results as with one panel and as the oracle."""
+    n, k = 300, 16
+    mats, coefs = modalities(n, 35)
+    blocks = MixedBlocks(mats, coefs).canonical().blocks
+    V = sp.hstack([c * m for m, c in zip(mats, coefs)]).tocsr()
+    V.eliminate_zeros()
+    f = V.shape[1]
+    np.random.seed(8)
+    H0 = O.init_dictionary(k, f)
+    W_ref, H_ref, errs_ref, _ = O.fit_transform(V.copy(), k=k, max_iter=6, tol=0, H0=H0)
+    out = {}
+    for panels, limit in (("one", None), ("three", 128 * 192 * 8)):
+        with _native.Engine(n, f, k, mode=mode, scratch_limit=limit) as e:
+            e.set_stacked_blocks(blocks, coefs)
+            assert e.is_hybrid()
+            e.set_dictionary(H0)
+            e.init_coefficients()
+            errs, _ = e.run(6, 0.0, True)
+            out[panels] = (e.get_coefficients(), e.get_dictionary(), np.asarray(errs), e.error())
+    for a, b in zip(out["three"][:3], (W_ref, H_ref, errs_ref)):
+        within("vs_oracle", cases.rel_fro(np.atleast_2d(a), np.atleast_2d(b)), TOL[mode])
+    same = 1e-12 if mode == "fp64" else 6e-5                       # the panels change the order of the numerator sums only (measured 1.9e-5)
+    within("W_vs_one_panel", cases.rel_fro(out["three"][0], out["one"][0]) + 1e-300, same)
+    within("H_vs_one_panel", cases.rel_fro(out["three"][1], out["one"][1]) + 1e-300, same)
+    within("objective_after", abs(out["three"][3] - out["one"][3]) / abs(out["one"][3]) + 1e-300, same)
