@@ -54,7 +54,7 @@ def parse():
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--alt-mode", default=os.environ.get("KLNMF_BENCH_ALT", "tf32,tf32x3"),
                     help="further arithmetic modes reported under alt_modes, comma separated ('' to skip)")
-    ap.add_argument("--no-extra", action="store_true", help="skip the cfg3 / cfg4 entries under `workloads`")
+    ap.add_argument("--no-extra", action="store_true", help="skip the cfg3 / cfg4 / mixed-stack entries under `workloads`")
     ap.add_argument("--balance", action="store_true",
                     help="several ranks: size the shards by each GPU's measured samples/s instead of the equal split "
                          "(experimental: under a power cap a GPU's speed depends on how long it idles in the all-reduce, "
@@ -521,6 +521,48 @@ def measure_workload(args, name, mode, ctx, with_clocks, keep_engine=False, step
     return out
 
 
+def measure_mixed_stack(_native, device, steps, warmup, n=65536, fd=4096, fs=50000, per_row=250, k=256):
+    """a wide dense modality next to a sparse one (learner.py:53-56).  The hybrid stack (dense block through
+    the contraction engine, CSR block through the sparse passes) and the all-CSR stack the reference would
+    build (array_utils.py:5-9), the same fit on both, device-timed like the other workloads."""
+    import scipy.sparse as sp
+    rs = np.random.RandomState(0)
+    dense = rs.random_sample((n, fd)).astype(np.float32)
+    dense[dense < 0.1] = 0.0                                    # 10 % structural zeros in the dense modality
+    lo = (np.arange(per_row) * fs) // per_row
+    width = ((np.arange(per_row) + 1) * fs) // per_row - lo
+    idx = (lo[None, :] + (rs.random_sample((n, per_row)) * width[None, :]).astype(np.int64)).astype(np.int32)
+    vals = (1.0 - rs.random_sample((n, per_row))).astype(np.float32)
+    sparse = sp.csr_matrix((vals.ravel(), idx.ravel(), np.arange(n + 1, dtype=np.int64) * per_row), shape=(n, fs))
+    f = fd + fs
+    np.random.seed(1)
+    H0 = np.abs(np.random.random((k, f))) + .01
+    H0 = H0 / (1.e-16 + H0.sum(axis=1, keepdims=True))
+    out = {"workload": "mixed stack fit: n=%d, dense modality %d columns + CSR modality %d columns (%d stored entries per row), k=%d"
+                       % (n, fd, fs, per_row, k), "unit": "iterations/s", "steps": steps, "warmup": warmup}
+    old = os.environ.get("KLNMF_HYBRID")
+    try:
+        for name, flag in (("all_csr_stack", "0"), ("hybrid_stack", "1")):
+            os.environ["KLNMF_HYBRID"] = flag
+            with _native.Engine(n, f, k, mode=_native.DEFAULT_MODE, device=device) as e:
+                e.set_stacked_blocks([dense, sparse], [1.0, 1.0])
+                assert e.is_hybrid() == (flag == "1")
+                e.set_dictionary(H0)
+                e.init_coefficients()
+                e.run(warmup, 0.0, True)
+                errs, _ = e.run(steps, 0.0, True)
+                ms, _ = e.last_run_profile()
+                out[name] = {"ms_per_step": ms["total"] / steps, "value": steps / (ms["total"] * 1e-3),
+                             "objective_last": float(errs[-1])}
+    finally:
+        if old is None:
+            os.environ.pop("KLNMF_HYBRID", None)
+        else:
+            os.environ["KLNMF_HYBRID"] = old
+    out["hybrid_speedup"] = out["all_csr_stack"]["ms_per_step"] / out["hybrid_stack"]["ms_per_step"]
+    return out
+
+
 def run_ours(args):
     rank, world, local, dist = dist_setup(args)
     os.environ.setdefault("KLNMF_PROFILE", "1")
@@ -637,6 +679,12 @@ def run_ours(args):
             extra[name] = {"workload": r["desc"], "value": r["value"], "unit": "iterations/s", "ms_per_step": r["ms_per_step"],
                            "steps": r["steps"], "warmup": r["warmup"], "rows_per_rank": r["n_local"], "mode": args.mode,
                            "gpu_launches": r["launches"], "roofline": r["roofline"], "clocks": r["clocks"]}
+
+        if world == 1:
+            try:
+                extra["mixed_stack"] = measure_mixed_stack(_native, local, max(args.steps, 5), max(args.warmup, 3))
+            except Exception as ex:                       # an extra: never takes the headline line down with it
+                extra["mixed_stack"] = {"error": str(ex)[:200]}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:

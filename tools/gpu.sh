@@ -32,7 +32,7 @@ try:
     print("N=%d ms/step %.3f it/s %.3f e2e %.3f it/s (%.2f s) e2e50 %s" % (d["n_gpus"], d["ms_per_step"], d["value"], e.get("value", 0), e.get("seconds", 0), (e.get("at_reference_iterations") or {}).get("value")))
     print("  phases min/max over ranks:", {k: [round(x, 3) for x in v] for k, v in (r.get("phase_ms_per_step_min_max_over_ranks") or {}).items()})
     print("  clocks", d.get("clocks"))
-    for k, v in (d.get("workloads") or {}).items(): print("  %s: %.3f ms/step %.2f it/s frac %s" % (k, v["ms_per_step"], v["value"], (v.get("roofline") or {}).get("frac")))
+    for k, v in (d.get("workloads") or {}).items(): print(("  %s: %.3f ms/step %.2f it/s frac %s" % (k, v["ms_per_step"], v["value"], (v.get("roofline") or {}).get("frac"))) if "ms_per_step" in v else ("  %s: %s" % (k, {a: b for a, b in v.items() if a != "workload"})))
     for k, v in (d.get("alt_modes") or {}).items(): print("  alt %s: %.3f ms/step" % (k, v["ms_per_step"]))
 except Exception as ex:
     print("no bench line:", ex)'
