@@ -362,6 +362,13 @@ def phase_roofline(ms, cnt, n_local, f, k, kind, steps, peaks, mode):
          "phase_ms_per_step": {p: ms[p] / max(steps, 1) for p in ("ratio", "coefficient", "numerator", "dictionary", "allreduce")}}
     if mode == "tf32x3":
         r["issued_frac"] = 3.0 * ach / peak      # three TF32 MMAs are issued per algorithmic product
+    # the whole iteration against the same peak: SURVEY 8d's algorithmic work, 6 n k f (fit) or 4 n k f (transform),
+    # over the time of its contraction phases on this rank
+    t_step = sum(ms[p_] for p_ in ("ratio", "coefficient", "numerator")) / max(steps, 1) * 1e-3
+    if t_step > 0:
+        alg = (4.0 if kind == "dense_transform" else 6.0) * n_local * k * f
+        r["whole_step"] = {"achieved": alg / t_step / 1e12, "frac": alg / t_step / 1e12 / peak, "unit": "TFLOP/s",
+                           "algorithmic_flop": alg}
     return r
 
 
