@@ -68,3 +68,39 @@ def test_sparse_transform_wide_k_vs_oracle(within, mode, k):
     W, errs = est.fit_transform(X.copy(), _fit=False, return_errors=True)
     within("W", cases.rel_fro(W, W_ref), TOL_WH[mode])
     within("objective", maxrel(errs, errs_ref), TOL_KL[mode])
+
+
+@pytest.mark.parametrize("k", [128, 256, 512, 1024])
+def test_sparse_full_kernel_row_patterns(within, k):
+    """The packed-FMA rows kernel fetches the NEXT batch's column indices one batch ahead, across rows: rows without
+    stored entries (leading, trailing, in runs), rows of 1, 7, 8, 9, 16, 33 entries (batches of 8, 4 and 2 entries at
+    k <= 256, 512, 1024), more warps than rows -- tf32r (FP32 FMA) against the fp64 mode of the same engine and against
+    the oracle."""
+    from multimodal_b200 import _native
+    counts = [0, 0, 1, 7, 8, 9, 16, 0, 33, 0, 2, 64, 0, 0, 5, 0]
+    n, f = 3 * len(counts), 700
+    rs = np.random.RandomState(k)
+    rows, cols, vals = [], [], []
+    for i in range(n):
+        c = counts[i % len(counts)]
+        js = np.sort(rs.choice(f, size=c, replace=False))
+        rows += [i] * c
+        cols += list(js)
+        vals += list(1.0 - rs.random_sample(c))
+    X = sp.csr_matrix((vals, (rows, cols)), shape=(n, f))
+    np.random.seed(k + 1)
+    H0 = O.init_dictionary(k, f)
+    W_ref, H_ref, errs_ref, _ = O.fit_transform(X.copy(), k=k, max_iter=4, tol=0, H0=H0)
+    out = {}
+    for mode in ("tf32r", "fp64"):
+        with _native.Engine(n, f, k, mode=mode) as e:
+            e.set_csr(X)
+            e.set_dictionary(H0)
+            e.init_coefficients()
+            errs, _ = e.run(4, 0.0, True)
+            out[mode] = (e.get_coefficients(), e.get_dictionary(), np.asarray(errs))
+    assert np.isfinite(out["tf32r"][0]).all() and (out["tf32r"][0][np.asarray(counts * 3) == 0] == 0).all()
+    within("W_vs_oracle", cases.rel_fro(out["tf32r"][0], W_ref), TOL_WH["tf32r"])
+    within("H_vs_oracle", cases.rel_fro(out["tf32r"][1], H_ref), TOL_WH["tf32r"])
+    within("objective", maxrel(out["tf32r"][2], errs_ref), TOL_KL["tf32r"])
+    within("fp64_W", cases.rel_fro(out["fp64"][0], W_ref), 1e-12)
