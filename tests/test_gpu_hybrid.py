@@ -153,3 +153,22 @@ def test_hybrid_walks_the_samples_in_panels(hybrid_on, within, mode):
     within("W_vs_one_panel", cases.rel_fro(out["three"][0], out["one"][0]) + 1e-300, same)
     within("H_vs_one_panel", cases.rel_fro(out["three"][1], out["one"][1]) + 1e-300, same)
     within("objective_after", abs(out["three"][3] - out["one"][3]) / abs(out["one"][3]) + 1e-300, same)
+
+
+@pytest.mark.parametrize("mode", ["fp64", "tf32r"])
+def test_hybrid_against_the_reference_golden_learner(hybrid_on, golden, within, mode):
+    """tests/golden/learner_small.npz was written by the REAL reference's MultimodalLearner (oracle/make_golden.py): a
+    dense motion modality next to a CSR sound one, i.e. its all-sparse stack (learner.py:53-56).  The hybrid stack must
+    give that dictionary and those coefficients."""
+    g = golden("learner_small")
+    mot, snd, coefs = cases.learner_small()
+    lr = MultimodalLearner(['motion', 'sound'], [mot.shape[1], snd.shape[1]], coefs, 8, mode=mode)
+    np.random.seed(3)
+    lr.train([mot, snd.copy()], 20)
+    tol = TOL[mode]
+    within("dico", cases.rel_fro(lr.dico, g["dico"]), tol)
+    lr.dico = np.array(g["dico"])                                  # the same dictionary on both sides from here on
+    both = lr.reconstruct_internal_multi(['motion', 'sound'], [mot[:25], snd[:25].copy()], 15)
+    within("internal_both", cases.rel_fro(both, g["internal_both"]), tol)
+    m2s = lr.modality_to_modality('motion', 'sound', mot[:25], 15)
+    within("motion_to_sound", cases.rel_fro(m2s, g["motion_to_sound"]), TOL["tf32r"] if mode != "fp64" else 1e-12)
