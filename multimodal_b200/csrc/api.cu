@@ -522,6 +522,11 @@ struct HybridSide {
   int64_t panel_rows = 0;                    // rows of the ratio panel Q (the samples are walked in panels of that many)
   void *X = nullptr, *Q = nullptr, *G = nullptr, *num = nullptr;
   void *H[2] = {nullptr, nullptr};
+  // FP32 modes: round-to-nearest TF32 copies of what the dense block's contractions multiply -- the dictionary part
+  // (k x ld) and the panel's rows of W / W' (panel_rows x ldw); the ratio panel is rounded where it is masked.  The
+  // tensor core would TRUNCATE its operands (a bias of 2^-12 per operand that short contractions do not average out:
+  // 1.4e-3 on the dictionary of the golden learner after 20 iterations, 3.6e-4 with the rounded copies).
+  void *Hr = nullptr, *Wr = nullptr;
   double *total = nullptr;                   // k doubles: the joint normaliser
   struct Range { int dense; int64_t col0, cols, off; };
   std::vector<Range> ranges;                 // the stack's column ranges, in stack order; off = first column inside its part
@@ -530,7 +535,7 @@ struct HybridSide {
 void release_hybrid(klnmf_ctx *ctx) {
   HybridSide *hy = (HybridSide *)ctx->hyb;
   if (!hy) return;
-  void *ptrs[] = {hy->X, hy->Q, hy->G, hy->num, hy->H[0], hy->H[1], hy->total};
+  void *ptrs[] = {hy->X, hy->Q, hy->G, hy->num, hy->H[0], hy->H[1], hy->total, hy->Hr, hy->Wr};
   for (void *q : ptrs)
     if (q) cudaFree(q);
   delete hy;
@@ -545,20 +550,25 @@ int hybrid_dense_half(klnmf_ctx *ctx, bool only_error, int64_t r0, int64_t rows)
   const int64_t es = ctx->es;
   const int *stop = only_error ? nullptr : ctx->flags + FL_STOP;
   const char *Xp = (const char *)hy->X + r0 * hy->ld * es;
+  const void *Wp = (const char *)ctx->W[cur] + r0 * ctx->ldw * es, *Hd = hy->H[hc];
+  if (hy->Hr) {   // (hy->Hr was refreshed by the caller: once per pass over the panels)
+    KL_TRY(launch_split(ctx, (const float *)Wp, (float *)hy->Wr, nullptr, rows, ctx->ldw, ctx->ldw));
+    Wp = hy->Wr; Hd = hy->Hr;
+  }
   GemmDesc d{};
   d.M = rows; d.N = hy->fd; d.K = ctx->k;
-  d.A = (const char *)ctx->W[cur] + r0 * ctx->ldw * es; d.a_sm = ctx->ldw; d.a_sk = 1;
-  d.B = hy->H[hc]; d.b_sk = hy->ld; d.b_sn = 1;
+  d.A = Wp; d.a_sm = ctx->ldw; d.a_sk = 1;
+  d.B = Hd; d.b_sk = hy->ld; d.b_sn = 1;
   d.out = hy->Q; d.ldo = hy->ld;
   d.aux = Xp; d.ldaux = hy->ld;
   d.kl = ctx->dred; d.stop = stop; d.only_kl = only_error ? 1 : 0;
   KL_TRY(dense_gemm(ctx, EPI_RATIO, d));
   if (only_error) return KLNMF_OK;
-  KL_TRY(launch_mask_ratio(ctx, hy->Q, hy->ld, Xp, hy->ld, rows, hy->fd, stop));
+  KL_TRY(launch_mask_ratio(ctx, hy->Q, hy->ld, Xp, hy->ld, rows, hy->fd, stop, hy->Hr ? 1 : 0));
   GemmDesc c{};
   c.M = rows; c.N = ctx->k; c.K = hy->fd;
   c.A = hy->Q; c.a_sm = hy->ld; c.a_sk = 1;
-  c.B = hy->H[hc]; c.b_sk = 1; c.b_sn = hy->ld;
+  c.B = Hd; c.b_sk = 1; c.b_sn = hy->ld;
   c.out = (char *)hy->G + r0 * ctx->ldw * es; c.ldo = ctx->ldw; c.stop = stop;
   return dense_gemm(ctx, EPI_STORE, c);
 }
@@ -567,15 +577,27 @@ int hybrid_dense_numerator(klnmf_ctx *ctx, int64_t r0, int64_t rows) {
   HybridSide *hy = (HybridSide *)ctx->hyb;        // (hy->num was zeroed at the top of the iteration)
   GemmDesc m{};
   m.M = ctx->k; m.N = hy->fd; m.K = rows;
-  m.A = (const char *)ctx->W[ctx->cur ^ 1] + r0 * ctx->ldw * (int64_t)ctx->es; m.a_sm = 1; m.a_sk = ctx->ldw;
+  const void *Wn = (const char *)ctx->W[ctx->cur ^ 1] + r0 * ctx->ldw * (int64_t)ctx->es;
+  if (hy->Wr) {
+    KL_TRY(launch_split(ctx, (const float *)Wn, (float *)hy->Wr, nullptr, rows, ctx->ldw, ctx->ldw));
+    Wn = hy->Wr;
+  }
+  m.A = Wn; m.a_sm = 1; m.a_sk = ctx->ldw;
   m.B = hy->Q; m.b_sk = hy->ld; m.b_sn = 1;
   m.out = hy->num; m.ldo = hy->ld; m.stop = ctx->flags + FL_STOP;
   return dense_gemm(ctx, EPI_ACC, m);
 }
 // The coefficient half-step of a hybrid stack (and, fitting, the dense block's numerator), panel by panel: the ratio
 // panel of the dense block lives for one panel only, so its numerator is taken before the next panel overwrites it.
+int hybrid_round_dictionary(klnmf_ctx *ctx) {
+  HybridSide *hy = (HybridSide *)ctx->hyb;
+  if (!hy->Hr) return KLNMF_OK;
+  return launch_split(ctx, (const float *)hy->H[ctx->hcur], (float *)hy->Hr, nullptr, ctx->k, hy->ld, hy->ld);
+}
+
 int hybrid_rows_passes(klnmf_ctx *ctx, int fit, Profiler *prof) {
   HybridSide *hy = (HybridSide *)ctx->hyb;
+  KL_TRY(hybrid_round_dictionary(ctx));
   for (int64_t r0 = 0; r0 < ctx->n; r0 += hy->panel_rows) {
     const int64_t rows = ctx->n - r0 < hy->panel_rows ? ctx->n - r0 : hy->panel_rows;
     {
@@ -915,6 +937,8 @@ int klnmf_set_stacked_blocks_host(klnmf_ctx *ctx, int n_blocks, const klnmf_bloc
       (rc = dmalloc(&hy->num, hb)) != KLNMF_OK || (rc = dmalloc(&hy->H[0], hb)) != KLNMF_OK ||
       (rc = dmalloc(&hy->H[1], hb)) != KLNMF_OK || (rc = dmalloc((void **)&hy->total, (ctx->k + 1) * 8)) != KLNMF_OK)
     return fail(rc);
+  if (es == 4 && ((rc = dmalloc(&hy->Hr, hb)) != KLNMF_OK || (rc = dmalloc(&hy->Wr, hy->panel_rows * ctx->ldw * es)) != KLNMF_OK))
+    return fail(rc);
   cudaMemsetAsync(hy->H[0], 0, hb, ctx->stream);
   cudaMemsetAsync(hy->H[1], 0, hb, ctx->stream);
   cudaMemsetAsync(hy->num, 0, hb, ctx->stream);
@@ -1064,11 +1088,16 @@ int klnmf_init_coefficients(klnmf_ctx *ctx) {
   if (ctx->sparse) {
     if (ctx->hyb) {   // W0 = X_d.H_d^T + X_s.H_s^T: the dense block's product first, the CSR pass starts from it
       HybridSide *hy = (HybridSide *)ctx->hyb;
+      KL_TRY(hybrid_round_dictionary(ctx));
       for (int64_t r0 = 0; r0 < ctx->n; r0 += hy->panel_rows) {
         GemmDesc c{};
         c.M = ctx->n - r0 < hy->panel_rows ? ctx->n - r0 : hy->panel_rows; c.N = ctx->k; c.K = hy->fd;
         c.A = (const char *)hy->X + r0 * hy->ld * ctx->es; c.a_sm = hy->ld; c.a_sk = 1;
         c.B = hy->H[ctx->hcur]; c.b_sk = 1; c.b_sn = hy->ld;
+        if (hy->Hr) {   // rounded copies of the data panel (through the ratio panel's buffer) and of the dictionary
+          KL_TRY(launch_split(ctx, (const float *)c.A, (float *)hy->Q, nullptr, c.M, hy->ld, hy->ld));
+          c.A = hy->Q; c.B = hy->Hr;
+        }
         c.out = (char *)hy->G + r0 * ctx->ldw * ctx->es; c.ldo = ctx->ldw;
         KL_TRY(dense_gemm(ctx, EPI_STORE, c));
       }
@@ -1318,6 +1347,7 @@ int klnmf_error(klnmf_ctx *ctx, double *out) {
     if (ctx->n > 0) {
       if (ctx->hyb) {
         const HybridSide *hy = (const HybridSide *)ctx->hyb;
+        KL_TRY(hybrid_round_dictionary(ctx));
         for (int64_t r0 = 0; r0 < ctx->n; r0 += hy->panel_rows)
           KL_TRY(hybrid_dense_half(ctx, true, r0, ctx->n - r0 < hy->panel_rows ? ctx->n - r0 : hy->panel_rows));
       }

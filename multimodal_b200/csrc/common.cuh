@@ -202,7 +202,8 @@ int launch_colsum_w(klnmf_ctx *ctx, const void *W, const void *Wlo, double *out)
 int launch_dict_update_t(klnmf_ctx *ctx, const void *Ht_old, void *Ht_new);     // sparse: f x k layout
 int launch_decide(klnmf_ctx *ctx, int iter_index);
 // hybrid stacks (api.cu: HybridSide): Q <- 0 where X == 0; the joint dictionary update of the dense and the CSR block
-int launch_mask_ratio(klnmf_ctx *ctx, void *Q, int64_t ldq, const void *X, int64_t ldx, int64_t rows, int64_t cols, const int *stop);
+int launch_mask_ratio(klnmf_ctx *ctx, void *Q, int64_t ldq, const void *X, int64_t ldx, int64_t rows, int64_t cols, const int *stop,
+                      int round_q);
 int launch_dict_update_hybrid(klnmf_ctx *ctx, const void *Ht_old, void *Ht_new, const void *Hd_old, void *Hd_new, const void *Nd,
                               int64_t fd, int64_t ldhd, double *total);
 int launch_split(klnmf_ctx *ctx, const float *src, float *hi, float *lo, int64_t rows, int64_t cols, int64_t ld);

@@ -113,14 +113,19 @@ __global__ void __launch_bounds__(256) dict_scale_t_kernel(const T *__restrict__
 // ---- hybrid stacks (a dense block next to the CSR block, api.cu: HybridSide) -------------------------------------
 // structural zeros of the stack carry no ratio: the reference sparsifies the whole stack (array_utils.py:5-9) and
 // forms the ratio at its stored entries only (nmf.py:52-70, 332-336)
+// (round_q, FP32 only: the ratio is also rounded to nearest TF32, so that the tensor core, which would truncate it,
+// multiplies exactly what is stored -- the one-pass modes' treatment of every operand)
+__device__ __forceinline__ float round_operand(float v) { return tf32_hi(v); }
+__device__ __forceinline__ double round_operand(double v) { return v; }
 template <typename T>
 __global__ void __launch_bounds__(256) mask_ratio_kernel(T *__restrict__ Q, int64_t ldq, const T *__restrict__ X, int64_t ldx,
-                                                         int64_t rows, int64_t cols, const int *stop) {
+                                                         int64_t rows, int64_t cols, const int *stop, int round_q) {
   if (stop != nullptr && *stop != 0) return;
   const int64_t total = rows * cols;
   for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
     const int64_t r = i / cols, c = i - r * cols;
     if (X[r * ldx + c] == (T)0) Q[r * ldq + c] = (T)0;
+    else if (round_q) Q[r * ldq + c] = round_operand(Q[r * ldq + c]);
   }
 }
 // hsum_d[a] = sum_j H[a,j] N[a,j] over the dense block's columns (k x f layout), one CTA per component
@@ -384,11 +389,11 @@ int launch_dict_update_t(klnmf_ctx *ctx, const void *Ht_old, void *Ht_new) {
 }
 
 int launch_mask_ratio(klnmf_ctx *ctx, void *Q, int64_t ldq, const void *X, int64_t ldx, int64_t rows, int64_t cols,
-                      const int *stop) {
+                      const int *stop, int round_q) {
   if (rows * cols == 0) return KLNMF_OK;
   const int g = grid_for(ctx, rows * cols, 256);
-  if (ctx->es == 8) mask_ratio_kernel<double><<<g, 256, 0, ctx->stream>>>((double *)Q, ldq, (const double *)X, ldx, rows, cols, stop);
-  else mask_ratio_kernel<float><<<g, 256, 0, ctx->stream>>>((float *)Q, ldq, (const float *)X, ldx, rows, cols, stop);
+  if (ctx->es == 8) mask_ratio_kernel<double><<<g, 256, 0, ctx->stream>>>((double *)Q, ldq, (const double *)X, ldx, rows, cols, stop, 0);
+  else mask_ratio_kernel<float><<<g, 256, 0, ctx->stream>>>((float *)Q, ldq, (const float *)X, ldx, rows, cols, stop, round_q);
   ctx->n_launch++;
   KL_CUDA(cudaGetLastError());
   return KLNMF_OK;

@@ -18,10 +18,15 @@ from oracle import klnmf_oracle as O
 
 pytestmark = pytest.mark.gpu
 
-# the dense block multiplies in the mode's one-pass form (tcgen05 kind::tf32 on plain FP32 operands, truncated by the
-# tensor core): stated = about 3 x the worst value measured (profiles/r2_parity_measured.json)
-TOL = {"fp64": 1e-12, "tf32r": 2e-3, "tf32": 2e-3}          # measured: 1.2e-15; W0 6.3e-4, W 3.7e-4, H 7.9e-5, dico 1.1e-4
-TOL_KL = {"fp64": 1e-12, "tf32r": 1e-3, "tf32": 1e-3}       # measured 3.1e-4
+# The dense block multiplies in the mode's one-pass form: tcgen05 kind::tf32 on round-to-nearest TF32 copies of its
+# operands (api.cu: HybridSide::Hr, Wr).  Stated = about 3 x the worst value measured (profiles/r2_parity_measured.json):
+# W0 3.9e-5, W 1.2e-4, H 7.2e-5, coefficients of test samples 1.6e-4, objective 6.2e-7.
+TOL = {"fp64": 1e-12, "tf32r": 5e-4, "tf32": 5e-4}
+TOL_KL = {"fp64": 1e-12, "tf32r": 2e-5, "tf32": 2e-5}
+# the golden learner: 20 fit iterations on a 60-column dense block with k = 8 -- nothing averages the 2^-12 operand
+# rounding over a contraction this short, and the fit amplifies it (measured 2.1e-3 on the dictionary; the default
+# threshold keeps such narrow modalities in the CSR stack, whose FP32 FMA gives 1e-6)
+TOL_GOLDEN = {"fp64": 1e-12, "tf32r": 6e-3}
 
 
 @pytest.fixture
@@ -165,10 +170,10 @@ def test_hybrid_against_the_reference_golden_learner(hybrid_on, golden, within, 
     lr = MultimodalLearner(['motion', 'sound'], [mot.shape[1], snd.shape[1]], coefs, 8, mode=mode)
     np.random.seed(3)
     lr.train([mot, snd.copy()], 20)
-    tol = TOL[mode]
+    tol = TOL_GOLDEN[mode]
     within("dico", cases.rel_fro(lr.dico, g["dico"]), tol)
     lr.dico = np.array(g["dico"])                                  # the same dictionary on both sides from here on
     both = lr.reconstruct_internal_multi(['motion', 'sound'], [mot[:25], snd[:25].copy()], 15)
     within("internal_both", cases.rel_fro(both, g["internal_both"]), tol)
     m2s = lr.modality_to_modality('motion', 'sound', mot[:25], 15)
-    within("motion_to_sound", cases.rel_fro(m2s, g["motion_to_sound"]), TOL["tf32r"] if mode != "fp64" else 1e-12)
+    within("motion_to_sound", cases.rel_fro(m2s, g["motion_to_sound"]), tol)
