@@ -20,8 +20,8 @@ pytestmark = pytest.mark.gpu
 
 # The dense block multiplies in the mode's one-pass form: tcgen05 kind::tf32 on round-to-nearest TF32 copies of its
 # operands (api.cu: HybridSide::Hr, Wr).  Stated = about 3 x the worst value measured (profiles/r2_parity_measured.json):
-# W0 3.9e-5, W 1.2e-4, H 7.2e-5, coefficients of test samples 1.6e-4, objective 6.2e-7.
-TOL = {"fp64": 1e-12, "tf32r": 5e-4, "tf32": 5e-4}
+# W0 3.9e-5, W 1.2e-4, H 7.2e-5, coefficients of test samples 1.6e-4 (2.0e-4 motion -> sound), objective 6.2e-7.
+TOL = {"fp64": 1e-12, "tf32r": 6e-4, "tf32": 6e-4}
 TOL_KL = {"fp64": 1e-12, "tf32r": 2e-5, "tf32": 2e-5}
 # the golden learner: 20 fit iterations on a 60-column dense block with k = 8 -- nothing averages the 2^-12 operand
 # rounding over a contraction this short, and the fit amplifies it (measured 2.1e-3 on the dictionary; the default
@@ -170,8 +170,8 @@ def test_hybrid_against_the_reference_golden_learner(hybrid_on, golden, within, 
     lr = MultimodalLearner(['motion', 'sound'], [mot.shape[1], snd.shape[1]], coefs, 8, mode=mode)
     np.random.seed(3)
     lr.train([mot, snd.copy()], 20)
-    tol = TOL_GOLDEN[mode]
-    within("dico", cases.rel_fro(lr.dico, g["dico"]), tol)
+    tol = TOL[mode]
+    within("dico", cases.rel_fro(lr.dico, g["dico"]), TOL_GOLDEN[mode])
     lr.dico = np.array(g["dico"])                                  # the same dictionary on both sides from here on
     both = lr.reconstruct_internal_multi(['motion', 'sound'], [mot[:25], snd[:25].copy()], 15)
     within("internal_both", cases.rel_fro(both, g["internal_both"]), tol)

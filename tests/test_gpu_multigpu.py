@@ -155,6 +155,6 @@ def test_sharded_hybrid_stack_through_the_learner(within, monkeypatch, mode):
         np.random.seed(5)
         lr.train(mats, 10)
         out[str(dev)] = np.array(lr.dico)
-    tol = 1e-12 if mode == "fp64" else 5e-4                       # tests/test_gpu_hybrid.py
+    tol = 1e-12 if mode == "fp64" else 6e-4                       # tests/test_gpu_hybrid.py
     within("dico", cases.rel_fro(out[str(DEVICES)], ref.dico), tol)
     within("dico_vs_single", cases.rel_fro(out[str(DEVICES)], out["0"]) + 1e-300, 1e-12 if mode == "fp64" else 2e-4)
