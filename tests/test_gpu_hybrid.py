@@ -177,3 +177,24 @@ def test_hybrid_against_the_reference_golden_learner(hybrid_on, golden, within, 
     within("internal_both", cases.rel_fro(both, g["internal_both"]), tol)
     m2s = lr.modality_to_modality('motion', 'sound', mot[:25], 15)
     within("motion_to_sound", cases.rel_fro(m2s, g["motion_to_sound"]), tol)
+
+
+def test_hybrid_cfg2_full_shapes_learner_vs_oracle(hybrid_on, within):
+    """BASELINE.json configs[1] at its real shapes in the hybrid form: 1000 samples, the 450-column
+    dense motion modality through the contraction engine, the 110 000-column CSR sound modality through the sparse
+    passes, k = 50; training iterations and the coefficients of test samples from BOTH modalities against the float64
+    oracle on the reference's all-sparse stack (3 iterations keep the oracle's runtime in seconds)."""
+    motion, sound, coefs = cases.cfg2_inputs()
+    mods, dims = ['motion', 'sound'], [motion.shape[1], sound.shape[1]]
+    lr = MultimodalLearner(mods, dims, coefs, 50)
+    np.random.seed(3)
+    lr.train([motion, sound.copy()], 3)
+    ref = O.Learner(mods, dims, coefs, 50)
+    np.random.seed(3)
+    ref.train([motion, sound.copy()], 3)
+    assert lr.dico.shape == (50, 110450)
+    within("dico", cases.rel_fro(lr.dico, ref.dico), TOL["tf32r"])
+    ref.dico = np.array(lr.dico)
+    test = [motion[:40], sound[:40]]
+    internal = lr.reconstruct_internal_multi(mods, test, 5)
+    within("internal", cases.rel_fro(internal, ref.reconstruct_internal_multi(mods, [motion[:40], sound[:40].copy()], 5)), TOL["tf32r"])
