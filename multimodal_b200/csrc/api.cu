@@ -869,8 +869,9 @@ int klnmf_set_stacked_blocks_host(klnmf_ctx *ctx, int n_blocks, const klnmf_bloc
   KL_TRY(kind_guard(ctx, true));
   release_data(ctx);
   // Hybrid form (HybridSide above): the dense blocks stay dense when they are wide enough to pay for their contractions,
-  // the mode multiplies in one pass and the context has no state yet.  hybrid_min_cols = 0 never, KLNMF_HYBRID=0 never, =1 whenever possible.  (The shards of a multi-GPU fit must all take
-  // the same form: distributed.DeviceGroup decides it once for all of them.)
+  // the mode multiplies in one pass and the context has no state yet.  hybrid_min_cols = 0: never; KLNMF_HYBRID=0: never,
+  // =1: whenever possible.  (The shards of a multi-GPU fit must all take the same form: distributed.DeviceGroup decides
+  // it once for all of them.)
   int64_t fd = 0, fs = 0, total = 0;
   int n_dense = 0, n_csr = 0;
   for (int b = 0; b < n_blocks; b++) {
@@ -899,7 +900,7 @@ int klnmf_set_stacked_blocks_host(klnmf_ctx *ctx, int n_blocks, const klnmf_bloc
   std::vector<klnmf_block> csr;
   int64_t col0 = 0, offd = 0, offs = 0;
   int rc = KLNMF_OK;
-  auto fail = [&](int code) { release_hybrid(ctx); return code; };
+  auto fail = [&](int code) { ctx->f = total; release_data(ctx); release_hybrid(ctx); return code; };
   if ((rc = dmalloc(&hy->X, ctx->n * ldd * es)) != KLNMF_OK) return fail(rc);
   if (cudaMemsetAsync(hy->X, 0, ctx->n * ldd * es, ctx->stream) != cudaSuccess) return fail(KLNMF_ECUDA);
   for (int b = 0; b < n_blocks; b++) {
@@ -922,7 +923,7 @@ int klnmf_set_stacked_blocks_host(klnmf_ctx *ctx, int n_blocks, const klnmf_bloc
     col0 += s.cols;
   }
   ctx->f = fs;                                   // from here on the context's CSR machinery sees the CSR columns only
-  if ((rc = stack_blocks_to_csr(ctx, (int)csr.size(), csr.data())) != KLNMF_OK) { ctx->f = total; return fail(rc); }
+  if ((rc = stack_blocks_to_csr(ctx, (int)csr.size(), csr.data())) != KLNMF_OK) return fail(rc);
   if ((rc = dmalloc(&ctx->qnz, ctx->nnz * es)) != KLNMF_OK || (rc = ensure_state(ctx)) != KLNMF_OK ||
       (rc = launch_sum_vals(ctx)) != KLNMF_OK)
     return fail(rc);
