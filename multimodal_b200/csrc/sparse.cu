@@ -299,7 +299,8 @@ sparse_rows_full_kernel(const int64_t *__restrict__ indptr, const int32_t *__res
   // What bounds the pass is the rate at which the L2 answers 1 KB gathers spread over the whole 51 MB dictionary
   // (cfg4): 512 GB in 33.5 ms = 15.3 TB/s, 0.94 of what klnmf_l2_read_bench gets out of a 48 MB buffer.  Measured and
   // dropped (profiles/r2_run26..29_*.log): FP16 gather copies (half the bytes: -5 %, at 100x the error), register
-  // double-buffering of half batches (+34 %), L1 prefetches of the next batch (+19 %; +40 % with no-allocate loads).
+  // double-buffering of half batches (+34 %), L1 prefetches of the next batch (+19 %; +40 % with no-allocate loads),
+  // half batches at three CTAs per SM (80 registers: +20 %).
   // (row and entry positions fit 32 bits: the host checks n, nnz < 2^32)
   uint32_t i = (uint32_t)warp_global;
   const uint32_t nn = (uint32_t)n, step = (uint32_t)n_warps;
