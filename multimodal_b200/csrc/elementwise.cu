@@ -162,33 +162,39 @@ __global__ void __launch_bounds__(256) hyb_scale_kernel(const T *__restrict__ H,
 // The reference's stopping test on the device (nmf.py:214-220).  dred = [kl, sum(X.data), colsum(W)...]
 __global__ void decide_kernel(double *dred, double *dscal, int *flags, double *errors, int errors_cap,
                               const double *rowsumH, int64_t k, int sparse, double *colsum_out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  double e = dred[0];
-  if (sparse) {
-    double wh = 0.0;
-    for (int64_t a = 0; a < k; a++) wh += dred[2 + a] * rowsumH[a];
-    e = e - dred[1] + wh;                       // nmf.py:301-308
-  }
-  if (flags[FL_STOP] == 0) {
-    const double prev = dscal[DS_PREV];
-    // DS_WHSUM holds the relative objective noise of the arithmetic mode (see klnmf_run): a tolerance at or below that
-    // noise (tol == 0 above all) asks "did the objective rise", and a rise has to exceed the noise to count
-    const double noise = dscal[DS_WHSUM] * (isfinite(prev) ? fabs(prev) : 0.0);
-    double tol = dscal[DS_TOL];
-    if (tol <= noise) tol -= noise;
-    if (prev - e < tol) {
-      flags[FL_STOP] = 1;
-    } else {
-      dscal[DS_PREV] = e;
-      int ne = flags[FL_NERR];
-      if (ne < errors_cap) errors[ne] = e;
-      flags[FL_NERR] = ne + 1;
+  // one warp: the k-long loops are strided over its lanes (one thread walking k = 512 global values took 90 us)
+  if (blockIdx.x != 0 || threadIdx.x >= 32) return;
+  const int lane = threadIdx.x;
+  double wh = 0.0;
+  if (sparse)
+    for (int64_t a = lane; a < k; a += 32) wh += dred[2 + a] * rowsumH[a];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) wh += __shfl_xor_sync(0xffffffffu, wh, o);
+  if (lane == 0) {
+    double e = dred[0];
+    if (sparse) e = e - dred[1] + wh;             // nmf.py:301-308
+    if (flags[FL_STOP] == 0) {
+      const double prev = dscal[DS_PREV];
+      // DS_WHSUM holds the relative objective noise of the arithmetic mode (see klnmf_run): a tolerance at or below that
+      // noise (tol == 0 above all) asks "did the objective rise", and a rise has to exceed the noise to count
+      const double noise = dscal[DS_WHSUM] * (isfinite(prev) ? fabs(prev) : 0.0);
+      double tol = dscal[DS_TOL];
+      if (tol <= noise) tol -= noise;
+      if (prev - e < tol) {
+        flags[FL_STOP] = 1;
+      } else {
+        dscal[DS_PREV] = e;
+        int ne = flags[FL_NERR];
+        if (ne < errors_cap) errors[ne] = e;
+        flags[FL_NERR] = ne + 1;
+      }
     }
+    dscal[DS_KL] = e;
+    dred[0] = 0.0;
+    dred[1] = dscal[DS_SUMX];
   }
-  dscal[DS_KL] = e;
-  dred[0] = 0.0;
-  dred[1] = dscal[DS_SUMX];
-  for (int64_t a = 0; a < k; a++) {
+  __syncwarp();
+  for (int64_t a = lane; a < k; a += 32) {
     if (colsum_out) colsum_out[a] = dred[2 + a];     // colsum(W') of all ranks, for the dictionary update
     dred[2 + a] = 0.0;
   }
@@ -244,6 +250,51 @@ __global__ void __launch_bounds__(256) colsum_w_kernel(const T *__restrict__ W, 
       }
       __syncthreads();
     }
+  }
+}
+
+// The same sums for FP32 state (the one-pass and split modes run it once per fit iteration over all of W': 16 GB at cfg5).
+// The generic kernel above converts and adds every element in FP64 (4-byte loads, F2F + DADD per element: 2.4 TB/s,
+// 6.8 ms per iteration at cfg5 under the power cap, outside every timed phase).  Here a thread owns one float4 column
+// group, adds hi + lo of 32 rows in FP32 (non-negative terms: <= 32 * 2^-24 relative) and only then in FP64.
+__global__ void __launch_bounds__(256) colsum_w_f32_kernel(const float *__restrict__ W, const float *__restrict__ Wlo, int64_t n,
+                                                           int64_t ld, double *__restrict__ out, const int *stop) {
+  if (*stop != 0) return;
+  const int G = (int)(ld >> 2);                       // float4 groups per row (ld is a multiple of 32)
+  const int per = 256 / G > 0 ? 256 / G : 1;          // rows per sweep of the CTA (G <= 256)
+  const int g = threadIdx.x % G, r0 = threadIdx.x / G;
+  extern __shared__ double4 part[];                   // per x G partial sums
+  double4 acc = make_double4(0.0, 0.0, 0.0, 0.0);
+  if (r0 < per) {
+    const int64_t rows_per_cta = (n + gridDim.x - 1) / gridDim.x;
+    const int64_t lo_row = (int64_t)blockIdx.x * rows_per_cta;
+    const int64_t hi_row = lo_row + rows_per_cta < n ? lo_row + rows_per_cta : n;
+    for (int64_t base = lo_row + r0; base < hi_row; base += (int64_t)per * 32) {
+      float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 8
+      for (int t = 0; t < 32; t++) {
+        const int64_t i = base + (int64_t)t * per;
+        if (i < hi_row) {
+          const float4 v = __ldg(reinterpret_cast<const float4 *>(W + i * ld) + g);
+          a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w;
+          if (Wlo) {
+            const float4 l = __ldg(reinterpret_cast<const float4 *>(Wlo + i * ld) + g);
+            a.x += l.x; a.y += l.y; a.z += l.z; a.w += l.w;
+          }
+        }
+      }
+      acc.x += (double)a.x; acc.y += (double)a.y; acc.z += (double)a.z; acc.w += (double)a.w;
+    }
+    part[r0 * G + g] = acc;
+  }
+  __syncthreads();
+  if (r0 == 0) {
+    for (int r = 1; r < per; r++) {
+      const double4 o = part[r * G + g];
+      acc.x += o.x; acc.y += o.y; acc.z += o.z; acc.w += o.w;
+    }
+    atomicAdd(&out[4 * g], acc.x); atomicAdd(&out[4 * g + 1], acc.y);
+    atomicAdd(&out[4 * g + 2], acc.z); atomicAdd(&out[4 * g + 3], acc.w);
   }
 }
 
@@ -466,7 +517,14 @@ int launch_colsum_w(klnmf_ctx *ctx, const void *W, const void *Wlo, double *out)
   if (ctx->es == 8)
     colsum_w_kernel<double><<<grid, 256, 0, ctx->stream>>>((const double *)W, (const double *)Wlo, ctx->n, ctx->k, ctx->ldw, out,
                                                            ctx->flags + FL_STOP);
-  else
+  else if (ctx->ldw <= 1024 && !(getenv("KLNMF_COLSUM_GENERIC") && atoi(getenv("KLNMF_COLSUM_GENERIC")) == 1)) {
+    // (columns k .. ldw of W are zero padding: their sums land in the padding of `out`, which has ldw + 32 slots)
+    const int G = (int)(ctx->ldw >> 2), per = 256 / G > 0 ? 256 / G : 1;
+    const int64_t want2 = ceil_div(ctx->n, (int64_t)per * 32);
+    const int grid2 = (int)(want2 < (int64_t)ctx->sm_count * 8 ? (want2 > 0 ? want2 : 1) : (int64_t)ctx->sm_count * 8);
+    colsum_w_f32_kernel<<<grid2, 256, (size_t)per * G * sizeof(double4), ctx->stream>>>((const float *)W, (const float *)Wlo, ctx->n,
+                                                                                      ctx->ldw, out, ctx->flags + FL_STOP);
+  } else
     colsum_w_kernel<float><<<grid, 256, 0, ctx->stream>>>((const float *)W, (const float *)Wlo, ctx->n, ctx->k, ctx->ldw, out,
                                                           ctx->flags + FL_STOP);
   ctx->n_launch++;
